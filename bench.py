@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the next-clip denoising hot path (BASELINE.json: next-clip latency / tokens/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg5|cfg1]
+
+One "step" = one next-clip prediction of the named workload: context prefill + all Euler
+steps with CFG (50 at full size), synthetic latents, random-init weights.  Prints ONE JSON line
+(rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+
+* ``value``   : tokens/s = (1+cfg) * T_gen * euler_steps * clips / time, latents resident in HBM,
+                timed with CUDA events, max over ranks.
+* ``e2e``     : same metric through ``LVMPipeline.next_clip_latents`` with HOST latents in pinned
+                memory and the generated latents read back to the host, inside the timed region.
+* ``roofline``: the tcgen05 GEMM (dominant kernel) timed live with CUDA events on the launch
+                stream over all layers' weights (7.2 GB > L2), algorithmic FLOPs / duration.
+* ``cpu_baseline`` / ``--impl reference``: the oracle restatement of the reference's own
+                PyTorch path (no cache, padded unconditional row, dense mask) on the host cores,
+                bounded sample, extrapolated and labelled as such.
+N > 1 (torchrun): independent videos data-parallel across ranks (weak scaling, no collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (dims, n_ctx, n_gen, height, width, euler_steps)
+    "cfg2": ("full", 4, 4, 256, 256, 50),   # BASELINE.json configs[1]: the config the metric is quoted on
+    "cfg5": ("full", 4, 4, 512, 512, 50),   # configs[4]
+    "cfg1": ("reduced", 4, 4, 256, 256, 4),  # configs[0] (the reference's CPU-runnable case)
+}
+GUIDANCE = 1.5
+
+
+def _dims(kind):
+    from videogpt_b200 import synth
+    return synth.FULL_SIZE if kind == "full" else synth.REDUCED
+
+
+def algorithmic_flops(dims, n_ctx, n_gen, block, euler_steps):
+    """per clip, context K/V cached, uncond row unpadded."""
+    h, i, L = dims.hidden_size, dims.intermediate_size, dims.num_hidden_layers
+    per_tok = 2 * (4 * h * h + 3 * h * i) * L
+    t_ctx, t_gen = n_ctx * block, n_gen * block
+    step = 2 * t_gen * per_tok + L * 4 * h * (t_gen * (t_ctx + t_gen) + t_gen * t_gen)
+    prefill = t_ctx * per_tok + L * 4 * h * block * block * sum(range(1, n_ctx + 1))
+    return step, prefill, step * euler_steps + prefill
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_model(dims, device):
+    """Random-init full model directly on the GPU (no checkpoint: no network), final layer re-drawn
+    N(0, 0.02) because the reference zero-initialises it (LVM/model.py:241-244)."""
+    from transformers import Phi3Config
+    from videogpt_b200 import LVM
+    torch.manual_seed(0)
+    model = LVM(Phi3Config(**dims.phi3_kwargs()), device=device, materialize_pos_embed=False)
+    with torch.no_grad():
+        for lin in (model.final_layer.linear, getattr(model.final_layer.adaLN_modulation, "1")):
+            lin.weight.normal_(std=0.02)
+        for n, p in model.named_parameters():
+            if n.endswith("layernorm.weight") or n == "llm.norm.weight":
+                p.uniform_(0.9, 1.1)
+    model.to(torch.bfloat16).eval()
+    return model
+
+
+def gemm_roofline(model, rows, reps=3):
+    """Time every projection GEMM of one Euler step (4 per layer x all layers, real weights) with
+    CUDA events on the launch stream; returns (avg seconds per launch, flops per launch, launches)."""
+    from videogpt_b200 import ops
+    e = model.engine()
+    h, i = e.hs, e.inter
+    x = torch.randn(rows, h, device=e.device).to(torch.bfloat16)
+    xi = torch.randn(rows, i, device=e.device).to(torch.bfloat16)
+    qkv = torch.empty(rows, 3 * h, device=e.device, dtype=torch.bfloat16)
+    hid = torch.zeros(rows, h, device=e.device, dtype=torch.bfloat16)
+    mh = torch.empty(rows, i, device=e.device, dtype=torch.bfloat16)
+
+    def one_pass():
+        for lw in e.w.layers:
+            ops.gemm(x, lw["qkv"], out=qkv)
+            ops.gemm(x, lw["o"], out=hid, residual=hid, epilogue=ops.EPI_RESIDUAL)
+            ops.gemm(x, lw["gate_up"], out=mh, epilogue=ops.EPI_SWIGLU)
+            ops.gemm(xi, lw["down"], out=hid, residual=hid, epilogue=ops.EPI_RESIDUAL)
+
+    one_pass()
+    torch.cuda.synchronize()
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        one_pass()
+    t.record()
+    torch.cuda.synchronize()
+    launches = reps * 4 * len(e.w.layers)
+    flops_per_layer = 2 * rows * (4 * h * h + 3 * h * i)
+    return s.elapsed_time(t) * 1e-3 / launches, flops_per_layer / 4.0, launches
+
+
+def cpu_reference_sample(dims, n_ctx, n_gen, height, width, euler_steps, layers_sample, threads):
+    """The reference's own PyTorch path (oracle restatement: no cache, padded uncond row, dense
+    mask) on the host cores: one Euler step restricted to `layers_sample` decoder layers, timed,
+    then extrapolated to all layers x euler_steps.  Returns (tokens/s, description)."""
+    from oracle import model_oracle as mo, processor_oracle as po
+    from videogpt_b200 import synth
+    torch.set_num_threads(threads)
+    small = synth.BackboneDims(hidden_size=dims.hidden_size, intermediate_size=dims.intermediate_size,
+                               num_hidden_layers=layers_sample, num_attention_heads=dims.num_attention_heads,
+                               vocab_size=dims.vocab_size)
+    dtype = torch.bfloat16 if dims.hidden_size >= 1024 else torch.float32
+    sd = synth.init_state_dict(small, seed=0, dtype=dtype, with_pos_embed=False)
+    sd["pos_embed"] = torch.zeros(1, dims.pos_embed_max_size ** 2, dims.hidden_size, dtype=dtype)
+    cfg = mo.OracleConfig(hidden_size=small.hidden_size, intermediate_size=small.intermediate_size,
+                          num_hidden_layers=layers_sample, num_attention_heads=small.num_attention_heads)
+    d = po.frame_block_inputs(n_ctx, n_gen, height, width, True, 1)
+    lat = [x.to(dtype) for x in synth.synthetic_latents(n_ctx + n_gen, height, width, seed=42)]
+    args = (d["input_ids"], lat[:n_ctx], d["input_image_sizes"], d["attention_mask"], d["position_ids"],
+            d["denoise_image_sizes"], d["time_emb_inx"])
+    z = lat[n_ctx:] * 2
+    t = torch.full((len(z),), 0.5)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        mo.frame_block_forward(sd, cfg, z, t, *args)
+        dt = time.perf_counter() - t0
+    per_step = dt * dims.num_hidden_layers / layers_sample
+    block = height * width // 256 + 2
+    tokens = 2 * n_gen * block * euler_steps
+    desc = (f"oracle port of the reference path ({str(dtype).split('.')[-1]}), 1 Euler step x {layers_sample} of "
+            f"{dims.num_hidden_layers} layers at L={d['input_ids'].shape[1]}, B=2 timed ({dt:.2f} s), "
+            f"extrapolated to {dims.num_hidden_layers} layers x {euler_steps} steps")
+    return tokens / (per_step * euler_steps), desc, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    kind, n_ctx, n_gen, H, W, euler = WORKLOADS[args.config]
+    dims = _dims(kind)
+    threads = os.cpu_count() or 1
+    layers_sample = 4 if kind == "full" else dims.num_hidden_layers
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, desc, dt = cpu_reference_sample(dims, n_ctx, n_gen, H, W, euler, layers_sample, threads)
+        if i >= args.warmup:
+            vals.append(v); times.append(dt)
+    value = sum(vals) / len(vals)
+    block = H * W // 256 + 2
+    line = {"impl": "reference", "metric": "next_clip_tokens_per_s", "value": value, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (2 * n_gen * block * euler) / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if kind == "full" else "f32", "data": "synthetic",
+            "config": {"workload": args.config, "context_frames": n_ctx, "generated_frames": n_gen,
+                       "height": H, "width": W, "euler_steps": euler, "cfg": True},
+            "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from videogpt_b200 import LVMPipeline, LVMProcessor, LVMScheduler, synth
+    from videogpt_b200.synth import SingleIdTagTokenizer as FakeTokenizer
+    kind, n_ctx, n_gen, H, W, euler = WORKLOADS[args.config]
+    dims = _dims(kind)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    model = build_model(dims, dev)
+    pipe = LVMPipeline(None, model, LVMProcessor(FakeTokenizer()), device=dev)
+    block = H * W // 256 + 2
+    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42 + rank)
+    ctx_host = [x.to(torch.bfloat16).pin_memory() for x in lat[:n_ctx]]
+    noise_host = [x.to(torch.bfloat16).pin_memory() for x in lat[n_ctx:]]
+    ctx_dev = [x.to(dev) for x in ctx_host]
+    noise_dev = [x.to(dev) for x in noise_host]
+    kw = dict(num_inference_steps=euler, img_guidance_scale=GUIDANCE, prediction_type="x1")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def clip_device():
+        # a fresh context tensor list every clip => the engine re-runs the prefill (as a new clip would)
+        return pipe.next_clip_latents([x.clone() for x in ctx_dev], n_gen, initial_noise=noise_dev, **kw)
+
+    def clip_host():
+        out = pipe.next_clip_latents(ctx_host, n_gen, initial_noise=noise_host, **kw)
+        return [x.to("cpu", non_blocking=False) for x in out]
+
+    for _ in range(max(args.warmup, 3)):
+        clip_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s.record()
+    for _ in range(args.steps):
+        clip_device()
+    t.record()
+    barrier()
+    dt = s.elapsed_time(t) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+
+    clip_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        clip_host()
+    barrier()
+    dt_e2e = time.perf_counter() - t0
+
+    if world > 1:
+        tt = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        return
+    tokens_per_clip = 2 * n_gen * block * euler
+    value = world * tokens_per_clip * args.steps / dt
+    e2e = world * tokens_per_clip * args.steps / dt_e2e
+    step_fl, prefill_fl, clip_fl = algorithmic_flops(dims, n_ctx, n_gen, block, euler)
+    e = model.engine()
+    launches = args.steps * (e.launches_per_prefill + euler * (e.launches_per_predict + 1))
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    sec, fl, n_launch = gemm_roofline(model, 2 * n_gen * block)
+    achieved = fl / sec / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (qkv/o/gate_up/down, M=%d)" % (2 * n_gen * block),
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if peaks else "fallback 1590",
+                "traffic": None, "avg_launch_us": sec * 1e6, "launches_timed": n_launch,
+                "whole_clip_tflops": clip_fl * args.steps / dt / 1e12,
+                "whole_clip_frac_of_sustained": clip_fl * args.steps / dt / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
+
+    threads = os.cpu_count() or 1
+    cpu_v, cpu_desc, _ = cpu_reference_sample(dims, n_ctx, n_gen, H, W, euler, 8 if kind == "full" else dims.num_hidden_layers, threads)
+    lat_bytes = 4 * (H // 8) * (W // 8) * 2
+    line = {"metric": "next_clip_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
+            "s_per_clip": dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.config, "model": "Phi-3-mini-class random-init" if kind == "full" else "2 layers / hidden 512",
+                       "context_frames": n_ctx, "generated_frames": n_gen, "height": H, "width": W,
+                       "euler_steps": euler, "cfg": True, "guidance": GUIDANCE, "prediction_type": "x1",
+                       "parallelism": f"dp{world} (independent videos)",
+                       "l2": "weights 7.2 GB streamed every Euler step (> 126 MB L2); no explicit flush"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": "tokens/s", "s_per_clip": dt_e2e / args.steps,
+                    "h2d_bytes_per_step": (n_ctx + n_gen) * lat_bytes, "d2h_bytes_per_step": n_gen * lat_bytes},
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": cpu_desc}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,127 @@
+/* vgpt_b200 -- C ABI of the B200-native next-clip denoising path of Video-GPT.
+ *
+ * The reference (zhuangshaobin/Video-GPT) is pure Python and has no FFI layer; the interfaces it
+ * swaps implementations through are the Python seams S1-S3 of SURVEY.md section 8(b).  Each entry
+ * point below is what the Python shim for one of those seams binds (videogpt_b200/_lib.py via
+ * ctypes; the stub is shown in INTEGRATION.md) and names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  All data pointers are DEVICE pointers
+ * (bf16 = uint16 storage unless stated) in the current CUDA context; `stream` is a cudaStream_t
+ * passed as void*.  Functions only enqueue work: they never allocate or free caller memory and
+ * never synchronise the stream, so they are CUDA-graph capturable and re-entrant per
+ * (device, stream).  Return value: 0 = ok, negative = argument error, positive = cudaError_t;
+ * vgpt_last_error() returns a thread-local message for the last non-zero return.
+ */
+#ifndef VGPT_B200_H_
+#define VGPT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VGPT_ABI_VERSION 1
+#define VGPT_PAGE_TOKENS 128 /* tokens per KV-cache page */
+
+enum { VGPT_EPI_STORE = 0, VGPT_EPI_RESIDUAL = 1, VGPT_EPI_SWIGLU = 2 };
+enum { VGPT_ROW_TOKEN = 0, VGPT_ROW_TIME = 1, VGPT_ROW_NOISY_PATCH = 2, VGPT_ROW_CONTEXT_PATCH = 3 };
+
+/* One sequence of an attention call (device-resident array). */
+typedef struct VgptAttnSeq {
+  int32_t q_row0;   /* first row of this sequence's queries in q / out / q_code            */
+  int32_t n_q;      /* number of query rows                                              */
+  int32_t kv_len;   /* number of valid keys: logical cache positions [0, kv_len)         */
+  int32_t reserved;
+} VgptAttnSeq;
+
+int vgpt_abi_version(void);
+const char* vgpt_last_error(void);
+
+/* C[M,N] = A[M,K] x W[N,K]^T, bf16 in / fp32 accumulate / bf16 out, tcgen05 + TMEM + TMA.
+ * Replaces qkv_proj / o_proj (LVM/transform/sdpa_transform.py:39, 89) and gate_up_proj /
+ * down_proj of transformers' Phi3MLP.  epilogue: VGPT_EPI_STORE; VGPT_EPI_RESIDUAL
+ * (C = bf16(A W^T) + R, R may alias C: the in-place residual stream of Phi3DecoderLayer);
+ * VGPT_EPI_SWIGLU (W packed by vgpt_pack_gate_up, C[M,N/2] = up * silu(gate)).
+ * K % 64 == 0, N % 64 == 0; block_n 0 = auto (256 or 128). */
+int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
+                   int ldc, int epilogue, int block_n, void* stream);
+
+/* gate_up_proj.weight [2I,K] ([gate | up] rows, Phi3MLP chunk(2)) -> block-interleaved rows. */
+int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream);
+
+/* Phi3RMSNorm (transformers 4.47.1): y = w * bf16(x * rsqrt(mean(x^2) + eps)). */
+int vgpt_rmsnorm(const void* x, const void* weight, void* y, int rows, int hidden, float eps, void* stream);
+
+/* cos/sin table [max_pos][head_dim] bf16 = cos[0:D/2] | sin[0:D/2] of pos * inv_freq (fp32)
+ * (Phi3RotaryEmbedding.forward, called at sdpa_transform.py:52). */
+int vgpt_rope_table(const float* inv_freq, void* table, int max_pos, int head_dim, void* stream);
+
+/* apply_rotary_pos_emb on q (in place in qkv[rows, 3*H*D]) and k, and the KV-cache update
+ * (sdpa_transform.py:52-57): post-RoPE k and v of each row go to slot row_slot[row]
+ * (= pool_page * VGPT_PAGE_TOKENS + offset; < 0: not cached) of pools [page][H][128][D]. */
+int vgpt_rope_kv_append(void* qkv, const int32_t* row_pos, const int32_t* row_slot, const void* table,
+                        void* k_pool, void* v_pool, int rows, int H, int D, void* stream);
+
+/* Clip-block-causal flash attention over the paged KV pools; replaces
+ * F.scaled_dot_product_attention with the dense additive mask (sdpa_transform.py:152-166,
+ * OmniGen/transformer.py:128-145).  allowed(q,k) <=> q_code[q] >= k_code[k]; k_code is
+ * [num_seqs][max_pages*128], k_tile_minmax [num_seqs][max_k_tiles][2] holds (min,max) of k_code
+ * per 64-key tile, page_table [num_seqs][max_pages].  q/out rows are [.., H*D] with leading
+ * dimensions q_ld / out_ld (q may point into the fused qkv buffer). */
+int vgpt_attn_clip_causal(const void* q, int q_ld, void* out, int out_ld, const void* k_pool,
+                          const void* v_pool, const int32_t* page_table, int max_pages,
+                          const VgptAttnSeq* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
+                          const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H,
+                          int D, float scale, void* stream);
+
+/* Sequence assembly (LVM/model.py:419-454): hidden[row] = embed_tokens[a] | time_tokens[a] |
+ * PatchEmbedMR(z[a] or ctx[a]) patch b + pos_rows[b], per row_kind (VGPT_ROW_*).
+ * z / ctx: [n, C=4, lat_h, lat_w]; conv weights [hidden, 4, 2, 2]; pos_rows [tokens, hidden]. */
+int vgpt_embed_assemble(void* hidden, int rows, int hidden_size, const int32_t* row_kind,
+                        const int32_t* row_a, const int32_t* row_b, const void* embed_tokens,
+                        const void* time_tokens, const void* z, const void* ctx, int channels, int lat_h,
+                        int lat_w, const void* w_noisy, const void* b_noisy, const void* w_ctx,
+                        const void* b_ctx, const void* pos_rows, void* stream);
+
+/* TimestepEmbedder.timestep_embedding (LVM/model.py:39-58): out[n, dim] = [cos | sin](t * freqs). */
+int vgpt_timestep_sinusoid(const float* t, const float* freqs, void* out, int n, int dim, void* stream);
+
+/* out[n,N] = post(pre(in[n,K]) W[N,K]^T + bias), n <= 16, optional SiLU before / after
+ * (TimestepEmbedder.mlp and FinalLayer.adaLN_modulation, LVM/model.py:32-36, 74-77). */
+int vgpt_linear_small(const void* in, const void* W, const void* bias, void* out, int n, int N, int K,
+                      int pre_silu, int post_silu, void* stream);
+
+/* FinalLayer + unpatchify (LVM/model.py:79-83, 255-265, 478-486): for latent j the image-token
+ * rows hidden[lat_row0[j] .. +tokens) -> pred[j, C, lat_h, lat_w]; mod[j] = [shift | scale]. */
+int vgpt_final_layer(const void* hidden, int hidden_size, const int32_t* lat_row0, const void* mod,
+                     const void* w, const void* bias, void* pred, int n_lat, int channels, int lat_h,
+                     int lat_w, void* stream);
+
+/* x1 -> velocity, CFG and the Euler update (LVM/scheduler.py:178-204, LVM/model.py:554-562) on
+ * z/pred laid out [cond latents | uncond latents] (half_numel elements each; one half if
+ * !use_cfg).  scalars_dev (optional, device float[3] = {1-sigma, sigma_next-sigma, guidance})
+ * overrides the by-value scalars so a captured graph can be replayed per step.
+ * vel_out (optional) receives the applied velocity of the cond half. */
+int vgpt_cfg_euler(void* z, const void* pred, void* vel_out, int half_numel, int use_cfg, int x1_mode,
+                   float one_minus_sigma, float dsigma, float guidance, const float* scalars_dev,
+                   void* stream);
+
+/* v-mode CFG inside the model (LVM/model.py:554-562): both halves of pred <- u + g * (c - u). */
+int vgpt_cfg_combine(void* pred, int half_numel, float guidance, void* stream);
+
+/* out[q][k] = q_code[q] >= k_code[k] (uint8): the reference's dense mask
+ * (LVM/processor.py:682-731) from the codes the attention kernel consumes. */
+int vgpt_mask_from_codes(const int32_t* q_code, const int32_t* k_code, void* out, int Lq, int Lk,
+                         void* stream);
+
+/* Test hook: run k_steps tcgen05.mma on raw shared-memory images with caller-built descriptors. */
+int vgpt_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
+                          uint64_t a_desc_base, uint64_t b_desc_base, uint32_t idesc, int k_steps,
+                          uint32_t a_step_bytes, uint32_t b_step_bytes, float* d_out, int n_cols,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGPT_B200_H_ */

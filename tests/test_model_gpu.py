@@ -1,0 +1,181 @@
+"""End-to-end parity of the CUDA path (LVM + LVMScheduler of videogpt_b200, through the C ABI)
+against the oracle -- the reference's own PyTorch path restated (oracle/), run in bf16 on the
+same device with identical weights and latents -- and against the golden outputs of the
+unmodified reference (fp32, tests/golden/).
+
+Tolerances are BASELINE.json's: per-step velocity relative L2 <= 1e-2 (bf16) and final-latent
+cosine >= 0.999.  The fp32 golden comparison bounds the total bf16 error of the CUDA path and
+is reported next to the bf16 oracle's own error against the same golden.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as mo, processor_oracle as po, scheduler_oracle as so
+from videogpt_b200 import synth
+
+from helpers import FakeTokenizer, cosine, load_npz, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV, BF = "cuda", torch.bfloat16
+
+VEL_TOL = 1e-2      # BASELINE.json: per-step velocity relative L2 error, bf16
+COS_TOL = 0.999     # BASELINE.json: final-latent cosine
+
+
+def _build(dims, seed=0):
+    from transformers import Phi3Config
+    from videogpt_b200 import LVM
+    sd = synth.init_state_dict(dims, seed=seed)
+    model = LVM(Phi3Config(**dims.phi3_kwargs()), device=DEV)
+    model.load_state_dict(sd)
+    model.to(BF).eval()
+    return model, sd
+
+
+def _oracle_cfg(dims):
+    return mo.OracleConfig(hidden_size=dims.hidden_size, intermediate_size=dims.intermediate_size,
+                           num_hidden_layers=dims.num_hidden_layers, num_attention_heads=dims.num_attention_heads)
+
+
+def _inputs(n_ctx, n_gen, H, W, device, dtype):
+    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)
+    ctx = [x.to(device, dtype) for x in lat[:n_ctx]]
+    z0 = [x.to(device, dtype) for x in lat[n_ctx:]]
+    mk = dict(input_ids=d["input_ids"].to(device), input_img_latents=ctx,
+              input_image_sizes=d["input_image_sizes"], attention_mask=d["attention_mask"].to(device),
+              position_ids=d["position_ids"].to(device), denoise_image_sizes=d["denoise_image_sizes"],
+              time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5, use_img_cfg=True, use_kv_cache=False,
+              offload_model=False, vae=None)
+    return mk, z0
+
+
+def _oracle_run(sd, dims, mk, z0, steps, pt, dtype):
+    w = {k: v.to(DEV, dtype) for k, v in sd.items()}
+    cfg = _oracle_cfg(dims)
+    rec = []
+    with torch.no_grad():
+        out = so.euler_sample([x.clone() for x in z0] * 2,
+                              lambda z, t, **kw: mo.frame_block_forward_with_cfg(w, cfg, z, t, **kw),
+                              mk, num_steps=steps, prediction_type=pt, record=rec)
+    return out, rec
+
+
+def _cuda_run(model, mk, z0, steps, pt, use_graph=True):
+    from videogpt_b200 import LVMScheduler
+    model.use_cuda_graph = use_graph
+    sch = LVMScheduler(num_steps=steps)
+    sch.record_velocity = []
+    out = sch([x.clone() for x in z0] * 2, model.frame_block_forward_with_cfg, mk, use_kv_cache=False,
+              prediction_type=pt)
+    torch.cuda.synchronize()
+    return out, sch.record_velocity
+
+
+@pytest.mark.parametrize("case", [("tiny", 2, 2, 64, 64, 4), ("ragged", 3, 2, 64, 96, 3), ("cfg1", 4, 4, 256, 256, 4)])
+@pytest.mark.parametrize("pt", ["x1", "v"])
+def test_next_clip_matches_oracle_bf16(case, pt):
+    name, n_ctx, n_gen, H, W, steps = case
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    mk, z0 = _inputs(n_ctx, n_gen, H, W, DEV, BF)
+    want, want_vel = _oracle_run(sd, dims, mk, z0, steps, pt, BF)
+    got, got_vel = _cuda_run(model, mk, z0, steps, pt)
+    assert len(got) == 2 * n_gen and all(torch.equal(got[i], got[n_gen + i]) for i in range(n_gen))   # q7
+    for i in range(steps):
+        v_ref = torch.cat(want_vel[i][:n_gen], 0)
+        err = rel_l2(got_vel[i], v_ref)
+        assert err <= VEL_TOL, f"step {i}: velocity rel-L2 {err:.3e}"
+    cos = cosine(torch.cat(got[:n_gen], 0), torch.cat(want[:n_gen], 0))
+    assert cos >= COS_TOL, cos
+
+
+@pytest.mark.parametrize("name,pt", [("tiny_fp32", "x1"), ("tiny_fp32", "v"), ("tiny_ragged_fp32", "x1"),
+                                     ("cfg1_fp32", "x1"), ("cfg1_fp32", "v")])
+def test_next_clip_vs_reference_golden_fp32(name, pt):
+    """CUDA path (bf16) vs the unmodified reference (fp32 CPU golden).  The bound is the bf16
+    oracle's own distance to the same golden, times 2."""
+    g = load_npz(f"model_{name}.npz")
+    n_ctx, n_gen, H, W, steps = [int(x) for x in g["meta"][:5]]
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    mk, z0 = _inputs(n_ctx, n_gen, H, W, DEV, BF)
+    got, _ = _cuda_run(model, mk, z0, steps, pt)
+    ref_bf16, _ = _oracle_run(sd, dims, mk, z0, steps, pt, BF)
+    gold = torch.from_numpy(g[f"final_{pt}"])[:n_gen].to(DEV)
+    e_cuda = rel_l2(torch.cat(got[:n_gen], 0), gold)
+    e_ref = rel_l2(torch.cat(ref_bf16[:n_gen], 0), gold)
+    assert cosine(torch.cat(got[:n_gen], 0), gold) >= COS_TOL
+    assert e_cuda <= max(2.0 * e_ref, 2e-2), (e_cuda, e_ref)
+
+
+def test_model_callback_seam_matches_engine_loop():
+    """Seam S2: driving ``frame_block_forward_with_cfg`` through a foreign scheduler loop (here the
+    oracle's) gives the same latents as the fused engine loop, with and without CUDA graphs."""
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    mk, z0 = _inputs(2, 2, 64, 64, DEV, BF)
+    for pt in ("x1", "v"):
+        fused, _ = _cuda_run(model, mk, z0, 3, pt, use_graph=True)
+        eager, _ = _cuda_run(model, mk, z0, 3, pt, use_graph=False)
+        assert all(torch.equal(a, b) for a, b in zip(fused, eager))
+        with torch.no_grad():
+            seam = so.euler_sample([x.clone() for x in z0] * 2,
+                                   lambda z, t, **kw: model.frame_block_forward_with_cfg(z, t, past_key_values=None, **kw)[0],
+                                   mk, num_steps=3, prediction_type=pt)
+        assert all(torch.equal(a, b) for a, b in zip(fused, seam)), pt
+
+
+def test_raw_prediction_matches_golden_single_call():
+    g = load_npz("model_tiny_fp32.npz")
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    mk, z0 = _inputs(2, 2, 64, 64, DEV, BF)
+    t = torch.full((4,), 0.25, device=DEV)
+    pred, cache = model.frame_block_forward_with_cfg([x.clone() for x in z0] * 2, t, past_key_values=None,
+                                                     prediction_type="x1", **mk)
+    assert cache is None and len(pred) == 4
+    gold = torch.from_numpy(g["pred_t025"]).to(DEV)
+    assert rel_l2(torch.cat(pred, 0), gold) < 2e-2
+
+
+def test_context_change_invalidates_prefill():
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    mk, z0 = _inputs(2, 2, 64, 64, DEV, BF)
+    a, _ = _cuda_run(model, mk, z0, 2, "x1")
+    mk2 = dict(mk)
+    mk2["input_img_latents"] = [x + 0.5 for x in mk["input_img_latents"]]
+    b, _ = _cuda_run(model, mk2, z0, 2, "x1")
+    c, _ = _cuda_run(model, mk, z0, 2, "x1")
+    assert not torch.equal(a[0], b[0]) and torch.equal(a[0], c[0])
+
+
+def test_wrong_mask_is_rejected():
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    mk, z0 = _inputs(2, 2, 64, 64, DEV, BF)
+    mk["attention_mask"] = torch.ones_like(mk["attention_mask"])
+    with pytest.raises(ValueError):
+        _cuda_run(model, mk, z0, 1, "x1")
+    mk["attention_mask"] = mk["attention_mask"][0]
+    with pytest.raises(Exception):
+        _cuda_run(model, mk, z0, 1, "x1")
+
+
+def test_pipeline_next_clip_latents_host_to_host():
+    """Public API with HOST latents in and out (what bench.py's e2e leg times)."""
+    from videogpt_b200 import LVMPipeline, LVMProcessor
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    pipe = LVMPipeline(None, model, LVMProcessor(FakeTokenizer()), device=torch.device(DEV))
+    lat = synth.synthetic_latents(4, 64, 64, seed=42)
+    ctx, noise = lat[:2], lat[2:]
+    out = pipe.next_clip_latents([x.pin_memory() for x in ctx], 2, num_inference_steps=4, img_guidance_scale=1.5,
+                                 prediction_type="x1", initial_noise=noise)
+    mk, z0 = _inputs(2, 2, 64, 64, DEV, BF)
+    want, _ = _cuda_run(model, mk, z0, 4, "x1")
+    assert len(out) == 2 and all(torch.equal(a, b) for a, b in zip(out, want[:2]))
+    seeded = pipe.next_clip_latents(ctx, 2, num_inference_steps=2, img_guidance_scale=1.0, seed=7)
+    assert len(seeded) == 2 and all(torch.isfinite(x.float()).all() for x in seeded)

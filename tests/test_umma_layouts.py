@@ -1,0 +1,55 @@
+"""Pins the shared-memory layouts / tcgen05 descriptor encodings the production kernels use,
+with the probe entry point (vgpt_debug_umma_probe): raw smem images built on the host + the
+descriptor fields -> the accumulator tile must equal A @ B^T exactly (small integers)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def smem_desc(lbo_bytes, sbo_bytes, layout):
+    return ((lbo_bytes >> 4) << 16) | ((sbo_bytes >> 4) << 32) | (1 << 46) | (layout << 61)
+
+
+def idesc(m, n, a_mn=0, b_mn=0):
+    return (1 << 4) | (1 << 7) | (1 << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24)
+
+
+def kmajor_image(mat: torch.Tensor, swizzle_bytes: int) -> torch.Tensor:
+    """[rows, k] bf16 -> bytes of the K-major swizzled tile TMA would write: each row is
+    `swizzle_bytes` wide, 16-byte chunk c of row r lands at chunk c ^ (r % (swizzle_bytes/16))."""
+    rows, k = mat.shape
+    assert k * 2 == swizzle_bytes
+    chunks = swizzle_bytes // 16
+    raw = mat.contiguous().view(torch.uint8).view(rows, chunks, 16)
+    out = torch.empty_like(raw)
+    r = torch.arange(rows)[:, None]
+    c = torch.arange(chunks)[None, :]
+    out[r, c ^ (r % chunks)] = raw
+    return out.reshape(-1)
+
+
+def ints(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(-4, 5, shape, generator=g).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_kmajor_sw128_gemm_layout(n):
+    """The GEMM's operand layout: 64-element (128 B) rows, SBO = 1024 B, +32 B per K=16 step."""
+    from videogpt_b200 import ops
+    a, b = ints((128, 64), 1), ints((n, 64), 2)
+    d = ops.umma_probe(kmajor_image(a, 128).to(DEV), kmajor_image(b, 128).to(DEV),
+                       smem_desc(16, 1024, 2), smem_desc(16, 1024, 2), idesc(128, n), 4, 32, 32, n)
+    assert torch.equal(d.cpu(), a.float() @ b.float().t())
+
+
+def test_kmajor_sw64_layout():
+    """32-element (64 B) rows, SBO = 512 B: the head_dim-96 = 3 x 32 split of attention Q/K."""
+    from videogpt_b200 import ops
+    a, b = ints((128, 32), 3), ints((128, 32), 4)
+    d = ops.umma_probe(kmajor_image(a, 64).to(DEV), kmajor_image(b, 64).to(DEV),
+                       smem_desc(16, 512, 4), smem_desc(16, 512, 4), idesc(128, 128), 2, 32, 32, 128)
+    assert torch.equal(d.cpu(), a.float() @ b.float().t())

@@ -1,0 +1,67 @@
+"""ctypes binding of libvgpt_b200.so (C ABI: include/vgpt_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_uint32, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvgpt_b200.so")
+
+P, I, F = c_void_p, c_int, c_float
+
+# name -> argument types; every symbol declared in include/vgpt_b200.h
+SIGNATURES = {
+    "vgpt_abi_version": [],
+    "vgpt_last_error": [],
+    "vgpt_gemm_bf16": [P, P, P, P, I, I, I, I, I, I, I, P],
+    "vgpt_pack_gate_up": [P, P, I, I, P],
+    "vgpt_rmsnorm": [P, P, P, I, I, F, P],
+    "vgpt_rope_table": [P, P, I, I, P],
+    "vgpt_rope_kv_append": [P, P, P, P, P, P, I, I, I, P],
+    "vgpt_attn_clip_causal": [P, I, P, I, P, P, P, I, P, I, I, P, P, P, I, I, I, F, P],
+    "vgpt_embed_assemble": [P, I, I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, P],
+    "vgpt_timestep_sinusoid": [P, P, P, I, I, P],
+    "vgpt_linear_small": [P, P, P, P, I, I, I, I, I, P],
+    "vgpt_final_layer": [P, I, P, P, P, P, P, I, I, I, I, P],
+    "vgpt_cfg_euler": [P, P, P, I, I, I, F, F, F, P, P],
+    "vgpt_cfg_combine": [P, I, F, P],
+    "vgpt_mask_from_codes": [P, P, P, I, I, P],
+    "vgpt_debug_umma_probe": [P, I, P, I, c_uint64, c_uint64, c_uint32, I, c_uint32, c_uint32, P, I, P],
+}
+
+_lib = None
+
+
+class VgptError(RuntimeError):
+    pass
+
+
+def load(path: str = LIB_PATH) -> ctypes.CDLL:
+    """Load the shared library and bind every exported symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: the CUDA library has not been built. Run "
+            "`python -m videogpt_b200.build` (needs nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = c_char_p if name == "vgpt_last_error" else c_int
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point; raise VgptError on a non-zero return."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.vgpt_last_error()
+        raise VgptError(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")

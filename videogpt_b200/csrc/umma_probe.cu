@@ -1,0 +1,79 @@
+// Descriptor probe: runs a handful of tcgen05.mma instructions on caller-supplied raw shared
+// memory images and descriptor fields, and returns the fp32 accumulator tile.  It exists so the
+// shared-memory layouts / descriptor encodings the production kernels rely on (K-major and
+// MN-major operands, 32/64/128-byte swizzles, K-advance strides) are pinned by a test on the GPU
+// (tests/test_umma_layouts.py) instead of being assumed.  Not on the hot path.
+#include "common.cuh"
+#include "vgpt_internal.h"
+
+namespace vgpt {
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* __restrict__ b_img,
+                  int b_bytes, uint64_t a_desc_base, uint64_t b_desc_base, uint32_t idesc,
+                  int k_steps, uint32_t a_step_bytes, uint32_t b_step_bytes,
+                  float* __restrict__ d_out, int n_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_off = 0, b_off = (uint32_t)((a_bytes + 1023) & ~1023);
+  for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(gen + a_off)[i] = a_img[i];
+  for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(gen + b_off)[i] = b_img[i];
+  fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor core
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < k_steps; ++k) {
+      const uint64_t da = a_desc_base + (uint64_t)(((base + a_off + k * a_step_bytes) >> 4) & 0x3fffu);
+      const uint64_t db = b_desc_base + (uint64_t)(((base + b_off + k * b_step_bytes) >> 4) & 0x3fffu);
+      umma_f16_ss(tmem, da, db, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < n_cols; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32 && c + j < n_cols; ++j) d_out[(size_t)row * n_cols + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t a_desc_base,
+               uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t a_step_bytes,
+               uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s) {
+  VGPT_CHECK_ARG(a_img && b_img && d_out, "vgpt_debug_umma_probe: null pointer");
+  VGPT_CHECK_ARG(a_bytes > 0 && b_bytes > 0 && a_bytes % 16 == 0 && b_bytes % 16 == 0 &&
+                     a_bytes <= 96 * 1024 && b_bytes <= 96 * 1024,
+                 "vgpt_debug_umma_probe: image sizes must be multiples of 16 and <= 96 KiB");
+  VGPT_CHECK_ARG(n_cols > 0 && n_cols <= 256 && k_steps > 0, "vgpt_debug_umma_probe: bad n_cols / k_steps");
+  const int smem = ((a_bytes + 1023) & ~1023) + ((b_bytes + 1023) & ~1023) + 1024;
+  VGPT_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_probe_kernel<<<1, 128, smem, s>>>((const uint4*)a_img, a_bytes, (const uint4*)b_img, b_bytes,
+                                         a_desc_base, b_desc_base, idesc, k_steps, a_step_bytes,
+                                         b_step_bytes, d_out, n_cols);
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace vgpt

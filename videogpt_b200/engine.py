@@ -1,0 +1,395 @@
+"""Next-clip denoising engine: plans, paged KV cache, and the per-step kernel sequence.
+
+This is the host side of the hot path.  It owns device memory through
+PyTorch and enqueues the hand-written sm_100a kernels of ``libvgpt_b200.so``; it does no
+arithmetic on tensors itself.
+
+Design (B200-first, not the reference's control flow):
+
+* A *sequence* is a step-invariant PREFIX (context frames) followed by ACTIVE rows (the
+  clip being denoised).  Prefix rows never see active rows (mask closed form), so their K/V
+  are computed once per clip (``prefill``) into a paged KV pool and every Euler step only
+  runs the active rows (``predict``): the reference recomputes the context 50x and pads the
+  unconditional row to full length (``LVM/scheduler.py:174``, ``LVM/processor.py:812-838``).
+* The mask is never materialised: each token carries an integer code and the attention
+  kernel evaluates ``code_q >= code_k`` (see ``processor.token_codes``).
+* All rows of all sequences (cond / uncond / batch) are packed into one ``[M, hidden]``
+  matrix, so every projection is one GEMM launch per layer.
+* One step = 9 + 8 x layers kernel launches, captured once in a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import PAGE_TOKENS, ATTN_KV_TILE
+
+INT_MAX = 2 ** 31 - 1
+
+
+# --------------------------------------------------------------------------------------------
+# weights
+# --------------------------------------------------------------------------------------------
+class EngineWeights:
+    """bf16 CUDA views of a state dict with the reference's names plus the
+    packed copies the kernels want (gate/up block-interleaved for the SwiGLU epilogue)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], num_layers: int, device):
+        def g(name):
+            t = sd[name]
+            if t.device != torch.device(device) or t.dtype != torch.bfloat16 or not t.is_contiguous():
+                t = t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+            return t.detach()
+
+        self.embed_tokens = g("llm.embed_tokens.weight")
+        self.x_w, self.x_b = g("x_embedder.proj.weight"), g("x_embedder.proj.bias")
+        self.cx_w, self.cx_b = g("input_x_embedder.proj.weight"), g("input_x_embedder.proj.bias")
+        self.time_token = [g(f"time_token.mlp.{i}.{k}") for i in (0, 2) for k in ("weight", "bias")]
+        self.t_embedder = [g(f"t_embedder.mlp.{i}.{k}") for i in (0, 2) for k in ("weight", "bias")]
+        self.ada_w, self.ada_b = g("final_layer.adaLN_modulation.1.weight"), g("final_layer.adaLN_modulation.1.bias")
+        self.final_w, self.final_b = g("final_layer.linear.weight"), g("final_layer.linear.bias")
+        self.norm = g("llm.norm.weight")
+        self.layers = []
+        for n in range(num_layers):
+            p = f"llm.layers.{n}."
+            gate_up = g(p + "mlp.gate_up_proj.weight")
+            self.layers.append(dict(
+                ln1=g(p + "input_layernorm.weight"), qkv=g(p + "self_attn.qkv_proj.weight"),
+                o=g(p + "self_attn.o_proj.weight"), ln2=g(p + "post_attention_layernorm.weight"),
+                gate_up=ops.pack_gate_up(gate_up), down=g(p + "mlp.down_proj.weight")))
+        self.pos_embed = sd.get("pos_embed")          # optional full table [1, max*max, h]
+
+
+# --------------------------------------------------------------------------------------------
+# plans
+# --------------------------------------------------------------------------------------------
+@dataclass
+class SequenceSpec:
+    """Host description of one sequence (all arrays int32, length n_prefix + n_active)."""
+    n_prefix: int
+    n_active: int
+    positions: np.ndarray
+    codes: np.ndarray
+    kinds: np.ndarray
+    arg_a: np.ndarray
+    arg_b: np.ndarray
+    latent_rows: List[tuple] = field(default_factory=list)   # (latent index, seq-relative first image row)
+
+
+@dataclass
+class PhaseArrays:
+    rows: int
+    row_pos: torch.Tensor
+    row_slot: torch.Tensor
+    q_code: torch.Tensor
+    kind: torch.Tensor
+    arg_a: torch.Tensor
+    arg_b: torch.Tensor
+    seqs: torch.Tensor
+    max_q_rows: int
+
+
+@dataclass
+class ClipPlan:
+    specs: List[SequenceSpec]
+    n_latents: int
+    n_ctx_latents: int
+    lat_h: int
+    lat_w: int
+    page_table: torch.Tensor
+    k_code: torch.Tensor
+    k_tile_minmax: torch.Tensor
+    total_pages: int
+    prefix: PhaseArrays
+    step: PhaseArrays
+    lat_row0: torch.Tensor
+    max_pos: int
+
+
+def frame_block_specs(input_ids, position_ids, input_image_sizes, denoise_image_sizes, time_emb_inx):
+    """Sequence specs of the frame-block (next-clip) layout from the reference's collated index
+    dicts (``LVM/processor.py:964-1000``); row b of the batch becomes sequence b.
+
+    Latent numbering follows the order the reference consumes them in
+    (``LVM/model.py:436-453``): context latents and noisy latents are global running counters
+    over rows."""
+    ids = input_ids.cpu().numpy()
+    pos = position_ids.cpu().numpy()
+    B, L = ids.shape
+    specs, ctx_counter, lat_counter = [], 0, 0
+    for b in range(B):
+        ctx_ranges = list(input_image_sizes.get(b, []))
+        gen_ranges = list(denoise_image_sizes.get(b, []))
+        if not gen_ranges:
+            raise ValueError(f"row {b}: no frames to denoise")
+        t_inx = list(time_emb_inx.get(b, []))
+        if len(t_inx) != len(gen_ranges):
+            raise ValueError(f"row {b}: time_emb_inx does not match denoise_image_sizes")
+        n_frames = len(ctx_ranges) + len(gen_ranges)
+        first = (ctx_ranges or gen_ranges)[0][0]
+        pad = first - 1 if ctx_ranges else first - 2          # processor.py:508-511
+        token_l = gen_ranges[-1][1] - pad
+        if gen_ranges[-1][1] != L or token_l % n_frames != 0:
+            raise ValueError(f"row {b}: frame blocks must have equal length and end at the sequence end")
+        bl = token_l // n_frames
+        n_ctx, n_gen = len(ctx_ranges), len(gen_ranges)
+        T = token_l
+        kinds = np.full(T, ops.ROW_TOKEN, np.int32)
+        arg_a = ids[b, pad:].astype(np.int32).copy()
+        arg_b = np.zeros(T, np.int32)
+        for s, e in ctx_ranges:
+            kinds[s - pad:e - pad] = ops.ROW_CONTEXT_PATCH
+            arg_a[s - pad:e - pad] = ctx_counter
+            arg_b[s - pad:e - pad] = np.arange(e - s)
+            ctx_counter += 1
+        latent_rows = []
+        for (s, e), ti in zip(gen_ranges, t_inx):
+            if ti != s - 1:
+                raise ValueError(f"row {b}: time slot must precede its image tokens")
+            kinds[ti - pad] = ops.ROW_TIME
+            arg_a[ti - pad] = lat_counter
+            kinds[s - pad:e - pad] = ops.ROW_NOISY_PATCH
+            arg_a[s - pad:e - pad] = lat_counter
+            arg_b[s - pad:e - pad] = np.arange(e - s)
+            latent_rows.append((lat_counter, s - pad))
+            lat_counter += 1
+        # codes: 4 * min(frame, n_ctx) + rank  (module docstring of processor.py)
+        i = np.arange(T)
+        f, o = i // bl, i % bl
+        gen = f >= n_ctx
+        r = np.where(gen, np.minimum(o, 2), np.where(o == 0, 0, np.where(o == bl - 1, 2, 1)))
+        codes = (4 * np.minimum(f, n_ctx) + r).astype(np.int32)
+        specs.append(SequenceSpec(n_prefix=n_ctx * bl, n_active=n_gen * bl,
+                                  positions=pos[b, pad:].astype(np.int32), codes=codes, kinds=kinds,
+                                  arg_a=arg_a, arg_b=arg_b, latent_rows=latent_rows))
+    return specs, lat_counter, ctx_counter
+
+
+def codes_dense_mask(spec_codes: np.ndarray, pad: int) -> np.ndarray:
+    """Dense bool mask (with ``pad`` left-pad tokens) implied by a code array -- host mirror of
+    ``vgpt_mask_from_codes``, used to validate a caller-supplied ``attention_mask``."""
+    T = len(spec_codes)
+    L = T + pad
+    qc = np.concatenate([np.full(pad, INT_MAX, np.int64), spec_codes.astype(np.int64)])
+    kc = np.concatenate([np.full(pad, INT_MAX - 1, np.int64), spec_codes.astype(np.int64)])
+    return qc[:, None] >= kc[None, :]
+
+
+def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int, lat_h: int,
+               lat_w: int, device) -> ClipPlan:
+    S = len(specs)
+    for sp in specs:
+        T = sp.n_prefix + sp.n_active
+        assert all(len(a) == T for a in (sp.positions, sp.codes, sp.kinds, sp.arg_a, sp.arg_b))
+        if sp.n_prefix and sp.n_active:
+            # caching the prefix is exact only if no prefix query can see an active key
+            if int(sp.codes[:sp.n_prefix].max()) >= int(sp.codes[sp.n_prefix:].min()):
+                raise ValueError("prefix rows can see active rows: this mask cannot be prefix-cached")
+    pages = [(sp.n_prefix + sp.n_active + PAGE_TOKENS - 1) // PAGE_TOKENS for sp in specs]
+    max_pages = max(pages)
+    page_table = np.zeros((S, max_pages), np.int32)
+    base = 0
+    for s, n in enumerate(pages):
+        page_table[s, :n] = np.arange(base, base + n)
+        base += n
+    tiles_per_page = PAGE_TOKENS // ATTN_KV_TILE
+    max_k_tiles = max_pages * tiles_per_page
+    k_code = np.full((S, max_pages * PAGE_TOKENS), INT_MAX, np.int32)
+    minmax = np.zeros((S, max_k_tiles, 2), np.int32)
+    minmax[:, :, 0] = INT_MAX
+    minmax[:, :, 1] = INT_MAX
+    for s, sp in enumerate(specs):
+        T = sp.n_prefix + sp.n_active
+        k_code[s, :T] = sp.codes
+        for t in range((T + ATTN_KV_TILE - 1) // ATTN_KV_TILE):
+            seg = sp.codes[t * ATTN_KV_TILE:min(T, (t + 1) * ATTN_KV_TILE)]
+            minmax[s, t] = (seg.min(), seg.max())
+
+    def phase(which: str) -> PhaseArrays:
+        pos, slot, qc, kd, aa, ab, seqs = [], [], [], [], [], [], []
+        row0, max_q = 0, 0
+        for s, sp in enumerate(specs):
+            lo, hi = (0, sp.n_prefix) if which == "prefix" else (sp.n_prefix, sp.n_prefix + sp.n_active)
+            n = hi - lo
+            logical = np.arange(lo, hi)
+            pos.append(sp.positions[lo:hi])
+            slot.append(page_table[s, logical // PAGE_TOKENS] * PAGE_TOKENS + logical % PAGE_TOKENS)
+            qc.append(sp.codes[lo:hi]); kd.append(sp.kinds[lo:hi]); aa.append(sp.arg_a[lo:hi]); ab.append(sp.arg_b[lo:hi])
+            seqs.append([row0, n, hi, 0])      # kv_len = everything up to the end of these rows
+            row0 += n
+            max_q = max(max_q, n)
+        cat = lambda xs: torch.from_numpy(np.concatenate(xs).astype(np.int32) if xs else np.zeros(0, np.int32)).to(device)
+        return PhaseArrays(rows=row0, row_pos=cat(pos), row_slot=cat(slot), q_code=cat(qc), kind=cat(kd),
+                           arg_a=cat(aa), arg_b=cat(ab),
+                           seqs=torch.tensor(seqs, dtype=torch.int32, device=device), max_q_rows=max_q)
+
+    prefix, step = phase("prefix"), phase("step")
+    lat_row0 = np.zeros(max(n_latents, 1), np.int32)
+    row0 = 0
+    for sp in specs:
+        for lat, first in sp.latent_rows:
+            lat_row0[lat] = row0 + first - sp.n_prefix
+        row0 += sp.n_active
+    max_pos = int(max(int(sp.positions.max()) for sp in specs)) + 1
+    return ClipPlan(specs=list(specs), n_latents=n_latents, n_ctx_latents=n_ctx_latents, lat_h=lat_h,
+                    lat_w=lat_w, page_table=torch.from_numpy(page_table).to(device),
+                    k_code=torch.from_numpy(k_code).to(device),
+                    k_tile_minmax=torch.from_numpy(minmax).to(device), total_pages=base,
+                    prefix=prefix, step=step, lat_row0=torch.from_numpy(lat_row0).to(device),
+                    max_pos=max_pos)
+
+
+# --------------------------------------------------------------------------------------------
+# engine
+# --------------------------------------------------------------------------------------------
+class NextClipEngine:
+    def __init__(self, weights: EngineWeights, hidden_size: int, intermediate_size: int, num_layers: int,
+                 num_heads: int, rms_eps: float, rope_theta: float, device, pos_embed_max_size: int = 192,
+                 patch_size: int = 2, use_cuda_graph: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("videogpt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.w = weights
+        self.hs, self.inter, self.L, self.H = hidden_size, intermediate_size, num_layers, num_heads
+        self.D = hidden_size // num_heads
+        self.eps, self.theta = rms_eps, rope_theta
+        self.device = torch.device(device)
+        self.pos_max, self.patch = pos_embed_max_size, patch_size
+        self.use_cuda_graph = use_cuda_graph
+        self.plan: Optional[ClipPlan] = None
+        self._graph = None
+        self._rope_tab = None
+        half = 128
+        self._t_freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half).to(self.device)
+        self._inv_freq = (1.0 / (rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).float() / self.D))).to(self.device)
+
+    # ---- setup ---------------------------------------------------------------------------------
+    def set_plan(self, plan: ClipPlan):
+        self.plan = plan
+        self._graph = None
+        dev, bf = self.device, torch.bfloat16
+        rows = max(plan.prefix.rows, plan.step.rows, 1)
+        self.hidden = torch.empty(rows, self.hs, device=dev, dtype=bf)
+        self.xn = torch.empty(rows, self.hs, device=dev, dtype=bf)
+        self.qkv = torch.empty(rows, 3 * self.hs, device=dev, dtype=bf)
+        self.attn = torch.empty(rows, self.hs, device=dev, dtype=bf)
+        self.mlp_h = torch.empty(rows, self.inter, device=dev, dtype=bf)
+        # paged KV pools: [layer][k|v][page][H][128][D]
+        self.kv = torch.zeros(self.L, 2, plan.total_pages, self.H, PAGE_TOKENS, self.D, device=dev, dtype=bf)
+        n = max(plan.n_latents, 1)
+        self.z = torch.zeros(n, 4, plan.lat_h, plan.lat_w, device=dev, dtype=bf)
+        self.pred = torch.zeros_like(self.z)
+        self.ctx = torch.zeros(max(plan.n_ctx_latents, 1), 4, plan.lat_h, plan.lat_w, device=dev, dtype=bf)
+        self.t = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.t_sin = torch.empty(n, 256, device=dev, dtype=bf)
+        self.t_h1 = torch.empty(n, self.hs, device=dev, dtype=bf)
+        self.time_tokens = torch.empty(n, self.hs, device=dev, dtype=bf)
+        self.t_emb = torch.empty(n, self.hs, device=dev, dtype=bf)
+        self.mod = torch.empty(n, 2 * self.hs, device=dev, dtype=bf)
+        self.scalars = torch.zeros(3, device=dev, dtype=torch.float32)
+        self.pos_rows = self._pos_rows(plan.lat_h, plan.lat_w)
+        if self._rope_tab is None or self._rope_tab.shape[0] < plan.max_pos:
+            self._rope_tab = ops.rope_table(self._inv_freq, max(plan.max_pos, 1), self.D)
+        self.prefilled = False
+
+    def _pos_rows(self, lat_h: int, lat_w: int) -> torch.Tensor:
+        """``cropped_pos_embed`` (LVM/model.py:268-289) as bf16 rows ``[tokens, hidden]``: gathered
+        from the model's persistent buffer when it is present, else computed for the crop."""
+        hh, ww = lat_h // self.patch, lat_w // self.patch
+        if hh > self.pos_max:
+            raise ValueError(f"Height ({hh}) cannot be greater than `pos_embed_max_size`: {self.pos_max}.")
+        if ww > self.pos_max:
+            raise ValueError(f"Width ({ww}) cannot be greater than `pos_embed_max_size`: {self.pos_max}.")
+        if self.w.pos_embed is not None:
+            top, left = (self.pos_max - hh) // 2, (self.pos_max - ww) // 2
+            pe = self.w.pos_embed.reshape(self.pos_max, self.pos_max, -1)[top:top + hh, left:left + ww]
+            return pe.reshape(hh * ww, -1).to(device=self.device, dtype=torch.bfloat16).contiguous()
+        from .synth import cropped_pos_embed_rows
+        return cropped_pos_embed_rows(self.hs, lat_h, lat_w, self.patch, self.pos_max).to(
+            device=self.device, dtype=torch.bfloat16).contiguous()
+
+    # ---- kernel sequences ----------------------------------------------------------------------
+    def _time_embeddings(self, n: int):
+        """time_token / t_embedder MLPs and the adaLN modulation (LVM/model.py:420, 480, 80)."""
+        w = self.w
+        ops.timestep_sinusoid(self.t[:n], self._t_freqs, self.t_sin[:n])
+        ops.linear_small(self.t_sin[:n], w.time_token[0], w.time_token[1], post_silu=True, out=self.t_h1[:n])
+        ops.linear_small(self.t_h1[:n], w.time_token[2], w.time_token[3], out=self.time_tokens[:n])
+        ops.linear_small(self.t_sin[:n], w.t_embedder[0], w.t_embedder[1], post_silu=True, out=self.t_h1[:n])
+        ops.linear_small(self.t_h1[:n], w.t_embedder[2], w.t_embedder[3], out=self.t_emb[:n])
+        ops.linear_small(self.t_emb[:n], w.ada_w, w.ada_b, pre_silu=True, out=self.mod[:n])
+
+    def _assemble(self, ph: PhaseArrays):
+        w = self.w
+        ops.embed_assemble(self.hidden[:ph.rows], ph.kind, ph.arg_a, ph.arg_b, w.embed_tokens, self.time_tokens,
+                           self.z, self.ctx, self.plan.lat_h, self.plan.lat_w, w.x_w, w.x_b, w.cx_w, w.cx_b,
+                           self.pos_rows)
+
+    def _layers(self, ph: PhaseArrays, kv_only_last: bool):
+        """Phi3DecoderLayer x L (transformers 4.47.1) on the packed rows of one phase."""
+        n, plan = ph.rows, self.plan
+        hidden, xn, qkv, attn, mlp_h = (self.hidden[:n], self.xn[:n], self.qkv[:n], self.attn[:n], self.mlp_h[:n])
+        scale = 1.0 / math.sqrt(self.D)
+        for li, lw in enumerate(self.w.layers):
+            ops.rmsnorm(hidden, lw["ln1"], self.eps, out=xn)
+            ops.gemm(xn, lw["qkv"], out=qkv)
+            ops.rope_kv_append(qkv, ph.row_pos, ph.row_slot, self._rope_tab, self.kv[li, 0], self.kv[li, 1],
+                               self.H, self.D)
+            if kv_only_last and li == self.L - 1:
+                break                     # prefix rows: nothing after the last K/V append is read
+            ops.attention(qkv[:, :self.hs], attn, self.kv[li, 0], self.kv[li, 1], plan.page_table, ph.seqs,
+                          ph.max_q_rows, ph.q_code, plan.k_code, plan.k_tile_minmax, self.H, self.D, scale)
+            ops.gemm(attn, lw["o"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
+            ops.rmsnorm(hidden, lw["ln2"], self.eps, out=xn)
+            ops.gemm(xn, lw["gate_up"], out=mlp_h, epilogue=ops.EPI_SWIGLU)
+            ops.gemm(mlp_h, lw["down"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
+
+    def prefill(self, ctx_latents: Optional[torch.Tensor] = None):
+        """Compute and cache K/V of every prefix (context) row.  ``ctx_latents``: [n_ctx, 4, h, w]."""
+        plan = self.plan
+        if ctx_latents is not None and plan.n_ctx_latents:
+            self.ctx.copy_(ctx_latents.to(self.ctx.dtype).reshape(self.ctx.shape))
+        if plan.prefix.rows:
+            self._assemble(plan.prefix)
+            self._layers(plan.prefix, kv_only_last=True)
+        self.prefilled = True
+
+    def _predict_kernels(self):
+        plan = self.plan
+        st = plan.step
+        self._time_embeddings(plan.n_latents)
+        self._assemble(st)
+        self._layers(st, kv_only_last=False)
+        ops.rmsnorm(self.hidden[:st.rows], self.w.norm, self.eps, out=self.xn[:st.rows])
+        ops.final_layer(self.xn[:st.rows], plan.lat_row0, self.mod[:plan.n_latents], self.w.final_w,
+                        self.w.final_b, self.pred)
+
+    def predict(self) -> torch.Tensor:
+        """One denoising forward of the active rows.  Inputs: ``self.z`` (latents), ``self.t``
+        (one timestep per latent); output ``self.pred`` (raw model prediction per latent)."""
+        if not self.prefilled:
+            raise RuntimeError("prefill() must run before predict()")
+        if not self.use_cuda_graph:
+            self._predict_kernels()
+            return self.pred
+        if self._graph is None:
+            self._predict_kernels()            # warm-up (sets function attributes, fills caches)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._predict_kernels()
+            self._graph = g
+        self._graph.replay()
+        return self.pred
+
+    @property
+    def launches_per_predict(self) -> int:
+        return 6 + 1 + 8 * self.L + 2
+
+    @property
+    def launches_per_prefill(self) -> int:
+        return (1 + 8 * (self.L - 1) + 3) if self.plan.prefix.rows else 0

@@ -1,0 +1,71 @@
+"""Sequence-parallel process-group state, mirroring ``LVM/acceleration/parallel_states.py``.
+
+``hccl_info`` keeps the reference's field names (``group``, ``world_size``, ``rank``;
+parallel_states.py:18-22).  The reference leaves ``world_size`` at 0 until
+``initialize_sequence_parallel_state`` runs (and then divides by it: SURVEY.md quirk q1); here
+0 means "not initialised" and is treated as a single rank.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class COMM_INFO:
+    def __init__(self):
+        self.group = None
+        self.world_size = 0
+        self.rank = -1
+
+
+hccl_info = COMM_INFO()
+_SEQUENCE_PARALLEL_STATE = False
+
+
+def initialize_sequence_parallel_state(sequence_parallel_size: int):
+    """parallel_states.py:24-37."""
+    global _SEQUENCE_PARALLEL_STATE
+    if sequence_parallel_size > 1:
+        _SEQUENCE_PARALLEL_STATE = True
+        initialize_sequence_parallel_group(sequence_parallel_size)
+    else:
+        hccl_info.group, hccl_info.world_size, hccl_info.rank = None, 1, 0
+
+
+def get_sequence_parallel_state() -> bool:
+    return _SEQUENCE_PARALLEL_STATE
+
+
+def initialize_sequence_parallel_group(sequence_parallel_size: int):
+    """Contiguous groups of ``sequence_parallel_size`` ranks (parallel_states.py:40-54)."""
+    rank = int(os.getenv("RANK", "0"))
+    world_size = int(os.getenv("WORLD_SIZE", "1"))
+    assert world_size % sequence_parallel_size == 0, \
+        "world_size must be divisible by sequence_parallel_size"
+    hccl_info.world_size = sequence_parallel_size
+    hccl_info.rank = rank % sequence_parallel_size
+    for i in range(world_size // sequence_parallel_size):
+        ranks = list(range(i * sequence_parallel_size, (i + 1) * sequence_parallel_size))
+        group = dist.new_group(ranks)
+        if rank in ranks:
+            hccl_info.group = group
+
+
+def destroy_sequence_parallel_group():
+    global _SEQUENCE_PARALLEL_STATE
+    hccl_info.group, hccl_info.world_size, hccl_info.rank = None, 0, -1
+    _SEQUENCE_PARALLEL_STATE = False
+
+
+def init_env(sequence_parallel_size: int = 1, backend: str = "nccl"):
+    """``init_npu_env`` (parallel_states.py:66-81) for NVIDIA: bind the local GPU, join the
+    default process group over NCCL (rendezvous from the torchrun environment), build SP groups."""
+    local_rank = int(os.getenv("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    if int(os.getenv("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        dist.init_process_group(backend=backend)
+    initialize_sequence_parallel_state(sequence_parallel_size)
+    return local_rank

@@ -1,0 +1,94 @@
+"""``LVMScheduler``: drop-in for the reference's flow-matching Euler sampler
+(``LVM/scheduler.py:119-208``): same constructor, sigma grid and call signature.
+
+When ``func`` is the ``frame_block_forward_with_cfg`` of a ``videogpt_b200.LVM`` the whole
+loop runs on the engine: latents stay in one device buffer, each step is one CUDA-graph replay
+of the denoising forward plus the fused x1->v / CFG / Euler kernel, and nothing syncs with the
+host.  Any other ``func`` (seam S2 of SURVEY.md 8(b)) goes through the generic loop, which still
+applies the update with the CUDA kernel.  CPU tensors are rejected: there is no CPU path.
+"""
+from __future__ import annotations
+
+import gc
+from typing import Callable, List, Optional
+
+import torch
+
+from . import ops
+
+
+class LVMScheduler:
+    def __init__(self, num_steps: int = 50, time_shifting_factor: int = 1, begin_time=None):
+        self.num_steps = num_steps
+        self.time_shift = time_shifting_factor
+        t = torch.linspace(0 if begin_time is None else begin_time, 1, num_steps + 1)
+        self.sigma = t / (t + time_shifting_factor - time_shifting_factor * t)
+        self.record_velocity: Optional[list] = None     # tests: per-step velocity of the cond half
+
+    # step scalars exactly as the reference forms them (fp32 tensor arithmetic, scheduler.py:178-204)
+    def _scalars(self, i: int):
+        sigma, sigma_next = self.sigma[i], self.sigma[i + 1]
+        return float(1.0 - sigma), float(sigma_next - sigma)
+
+    def __call__(self, z, func: Callable, model_kwargs: dict, use_kv_cache: bool = True,
+                 offload_kv_cache: bool = True, prediction_type: str = "v", vae=None, noise_level=None):
+        if noise_level is not None:
+            z = z * noise_level + torch.randn_like(z) * (1 - noise_level)
+        model = getattr(func, "__self__", None)
+        from .model import LVM
+        if isinstance(model, LVM) and getattr(func, "__name__", "") == "frame_block_forward_with_cfg" \
+                and isinstance(z, list):
+            out = self._run_engine(z, model, model_kwargs, prediction_type)
+        else:
+            out = self._run_generic(z, func, model_kwargs, prediction_type)
+        gc.collect()
+        return out
+
+    # ---- engine loop -----------------------------------------------------------------------------
+    def _run_engine(self, z: List[torch.Tensor], model, mk: dict, prediction_type: str):
+        lat_h, lat_w = z[0].shape[-2:]
+        e = model.prepare_frame_block(mk["input_ids"], mk["input_img_latents"], mk["input_image_sizes"],
+                                      mk["attention_mask"], mk["position_ids"], mk["denoise_image_sizes"],
+                                      mk["time_emb_inx"], lat_h, lat_w)
+        n = e.plan.n_latents
+        assert len(z) == n
+        use_cfg = bool(mk["use_img_cfg"])
+        e.z.copy_(torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0))
+        vel = torch.empty_like(e.z[: n // 2 if use_cfg else n]) if self.record_velocity is not None else None
+        for i in range(self.num_steps):
+            e.t.fill_(float(self.sigma[i]))
+            e.predict()
+            oms, ds = self._scalars(i)
+            ops.cfg_euler(e.z, e.pred, use_cfg, prediction_type == "x1", oms, ds,
+                          float(mk["img_cfg_scale"]), vel_out=vel)
+            if vel is not None:
+                self.record_velocity.append(vel.clone())
+        out = [e.z[i:i + 1].clone() for i in range(n)]
+        for i in range(n):
+            z[i] = out[i]
+        return out
+
+    # ---- generic loop (any func with the reference's callback signature) --------------------------
+    def _run_generic(self, z, func, mk: dict, prediction_type: str):
+        is_list = isinstance(z, list)
+        zs = torch.cat(z, 0) if is_list else z
+        if not zs.is_cuda:
+            raise RuntimeError("videogpt_b200.LVMScheduler needs CUDA latents (no CPU fallback)")
+        zs = zs.to(torch.bfloat16).contiguous().clone()
+        use_cfg = bool(mk.get("use_img_cfg", False))
+        for i in range(self.num_steps):
+            cur = [zs[j:j + 1] for j in range(zs.shape[0])] if is_list else zs
+            timesteps = torch.zeros(size=(len(cur),), device=zs.device) + self.sigma[i]
+            pred, _cache = func(cur, timesteps, past_key_values=None, prediction_type=prediction_type, **mk)
+            pred = (torch.cat(pred, 0) if is_list else pred).to(torch.bfloat16).contiguous()
+            oms, ds = self._scalars(i)
+            if prediction_type == "x1":
+                ops.cfg_euler(zs, pred, use_cfg, True, oms, ds, float(mk.get("img_cfg_scale", 1.0)))
+            else:   # v mode: the model already combined the branches (model.py:554-562)
+                ops.cfg_euler(zs, pred, False, False, oms, ds, 1.0)
+        if is_list:
+            out = [zs[j:j + 1].clone() for j in range(zs.shape[0])]
+            for j in range(len(out)):
+                z[j] = out[j]
+            return out
+        return zs

@@ -158,3 +158,22 @@ def synthetic_latents(n_frames: int, height: int, width: int, seed: int = 42, de
     g = torch.Generator(device=device).manual_seed(seed)
     return [torch.randn(1, channels, height // 8, width // 8, generator=g, device=device).to(dtype)
             for _ in range(n_frames)]
+
+
+class SingleIdTagTokenizer:
+    """Stand-in for the released tokenizer (not in the reference checkout, not downloadable):
+    BOS (1) followed by one id per ``<img>`` / ``</img>`` / ``<|diffusion|>`` tag, which is what
+    ``LVMProcessor`` assumes of the real one (``LVM/processor.py:138-142, 513-515``)."""
+    TAGS = {"<img>": 32001, "</img>": 32002, "<|diffusion|>": 32003}
+    eos_token_id = 2
+
+    class _Out:
+        def __init__(self, ids):
+            self.input_ids = ids
+
+    def __call__(self, text):
+        import re
+        ids = [1]
+        for t in re.findall(r"<img>|</img>|<\|diffusion\|>", text):
+            ids.append(self.TAGS[t])
+        return self._Out(ids)
