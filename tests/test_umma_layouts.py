@@ -18,16 +18,17 @@ def idesc(m, n, a_mn=0, b_mn=0):
 
 
 def kmajor_image(mat: torch.Tensor, swizzle_bytes: int) -> torch.Tensor:
-    """[rows, k] bf16 -> bytes of the K-major swizzled tile TMA would write: each row is
-    `swizzle_bytes` wide, 16-byte chunk c of row r lands at chunk c ^ (r % (swizzle_bytes/16))."""
+    """[rows, k] bf16 -> bytes of the K-major swizzled tile TMA would write.  Rows are
+    `swizzle_bytes` wide and dense; the hardware swizzle XORs byte-address bits [4,7) with bits
+    [7,10), masked to the swizzle width: addr ^= ((addr >> 7) & (swizzle_bytes/16 - 1)) << 4."""
     rows, k = mat.shape
     assert k * 2 == swizzle_bytes
     chunks = swizzle_bytes // 16
-    raw = mat.contiguous().view(torch.uint8).view(rows, chunks, 16)
+    raw = mat.contiguous().view(torch.uint8).view(rows * chunks, 16)
+    addr = torch.arange(rows * chunks) * 16
+    dst = addr ^ (((addr >> 7) & (chunks - 1)) << 4)
     out = torch.empty_like(raw)
-    r = torch.arange(rows)[:, None]
-    c = torch.arange(chunks)[None, :]
-    out[r, c ^ (r % chunks)] = raw
+    out[dst // 16] = raw
     return out.reshape(-1)
 
 

@@ -234,17 +234,16 @@ class LVM(nn.Module):
 
     @staticmethod
     def _identity(*objs):
-        out = []
-        for o in objs:
+        """Cheap identity of (nested) conditioning inputs: tensors by storage + version."""
+        def freeze(o):
             if torch.is_tensor(o):
-                out.append((o.data_ptr(), tuple(o.shape), o._version))
-            elif isinstance(o, (list, tuple)):
-                out.append(tuple((t.data_ptr(), tuple(t.shape), t._version) for t in o))
-            elif isinstance(o, dict):
-                out.append(tuple((k, tuple(map(tuple, v))) for k, v in o.items()))
-            else:
-                out.append(o)
-        return tuple(out)
+                return (o.data_ptr(), tuple(o.shape), o._version)
+            if isinstance(o, (list, tuple)):
+                return tuple(freeze(x) for x in o)
+            if isinstance(o, dict):
+                return tuple((k, freeze(v)) for k, v in o.items())
+            return o
+        return tuple(freeze(o) for o in objs)
 
     def prepare_frame_block(self, input_ids, input_img_latents, input_image_sizes, attention_mask,
                             position_ids, denoise_image_sizes, time_emb_inx, lat_h, lat_w,
