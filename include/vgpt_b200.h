@@ -63,17 +63,27 @@ int vgpt_rope_table(const float* inv_freq, void* table, int max_pos, int head_di
 int vgpt_rope_kv_append(void* qkv, const int32_t* row_pos, const int32_t* row_slot, const void* table,
                         void* k_pool, void* v_pool, int rows, int H, int D, void* stream);
 
-/* Clip-block-causal flash attention over the paged KV pools; replaces
+/* Clip-block-causal flash attention over the paged KV pools (tcgen05 + TMEM + TMA); replaces
  * F.scaled_dot_product_attention with the dense additive mask (sdpa_transform.py:152-166,
  * OmniGen/transformer.py:128-145).  allowed(q,k) <=> q_code[q] >= k_code[k]; k_code is
  * [num_seqs][max_pages*128], k_tile_minmax [num_seqs][max_k_tiles][2] holds (min,max) of k_code
- * per 64-key tile, page_table [num_seqs][max_pages].  q/out rows are [.., H*D] with leading
- * dimensions q_ld / out_ld (q may point into the fused qkv buffer). */
-int vgpt_attn_clip_causal(const void* q, int q_ld, void* out, int out_ld, const void* k_pool,
-                          const void* v_pool, const int32_t* page_table, int max_pages,
+ * per 64-key tile, page_table [num_seqs][max_pages] indexes pools of total_pages pages.  q/out
+ * rows are [.., H*D] with leading dimensions q_ld / out_ld (q may point into the fused qkv
+ * buffer of q_rows rows). */
+int vgpt_attn_clip_causal(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
+                          const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                           const VgptAttnSeq* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
                           const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H,
                           int D, float scale, void* stream);
+
+/* Same contract on the legacy tensor path (mma.sync, cp.async): the round-1 kernel, kept only as
+ * an independent cross-check of the tcgen05 kernel in the GPU tests. */
+int vgpt_attn_clip_causal_mma_sync(const void* q, int q_ld, int q_rows, void* out, int out_ld,
+                                   const void* k_pool, const void* v_pool, int total_pages,
+                                   const int32_t* page_table, int max_pages, const VgptAttnSeq* seqs,
+                                   int num_seqs, int max_q_rows, const int32_t* q_code, const int32_t* k_code,
+                                   const int32_t* k_tile_minmax, int max_k_tiles, int H, int D, float scale,
+                                   void* stream);
 
 /* Sequence assembly (LVM/model.py:419-454): hidden[row] = embed_tokens[a] | time_tokens[a] |
  * PatchEmbedMR(z[a] or ctx[a]) patch b + pos_rows[b], per row_kind (VGPT_ROW_*).

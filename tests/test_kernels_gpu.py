@@ -306,7 +306,7 @@ def test_mask_from_codes_bit_exact(ops, case):
 # ---------------------------------------------------------------------------------------------
 # attention over the paged cache vs dense-mask SDPA
 # ---------------------------------------------------------------------------------------------
-def _attention_case(ops, n_ctx, n_gen, H_px, W_px, heads, D, phase, seed):
+def _attention_case(ops, n_ctx, n_gen, H_px, W_px, heads, D, phase, seed, impl="tcgen05"):
     from videogpt_b200 import engine as eng
     d = po.frame_block_inputs(n_ctx, n_gen, H_px, W_px, True, 1)
     specs, n_lat, n_c = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
@@ -319,7 +319,7 @@ def _attention_case(ops, n_ctx, n_gen, H_px, W_px, heads, D, phase, seed):
     q = _rand((ph.rows, 3 * heads * D), seed + 3)                     # q lives in the fused qkv buffer
     out = torch.zeros(ph.rows, heads * D, device=DEV, dtype=BF)
     ops.attention(q[:, :heads * D], out, k_pool, v_pool, plan.page_table, ph.seqs, ph.max_q_rows, ph.q_code,
-                  plan.k_code, plan.k_tile_minmax, heads, D, 1.0 / math.sqrt(D))
+                  plan.k_code, plan.k_tile_minmax, heads, D, 1.0 / math.sqrt(D), impl=impl)
     # oracle: gather the logical K/V of each sequence and run dense-mask SDPA in fp32
     row0 = 0
     worst = 0.0
@@ -346,17 +346,29 @@ def _attention_case(ops, n_ctx, n_gen, H_px, W_px, heads, D, phase, seed):
     assert worst < 1e-2, worst
 
 
-@pytest.mark.parametrize("D", [64, 96])
+IMPLS = ["tcgen05", "mma_sync"]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("D", [64, 96, 128])
 @pytest.mark.parametrize("phase", ["step", "prefix"])
-def test_attention_small(ops, D, phase):
-    _attention_case(ops, 2, 2, 64, 96, 2, D, phase, 100)
+def test_attention_small(ops, D, phase, impl):
+    _attention_case(ops, 2, 2, 64, 96, 2, D, phase, 100, impl)
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("phase", ["step", "prefix"])
-def test_attention_cfg2_geometry(ops, phase):
-    _attention_case(ops, 4, 4, 256, 256, 4, 96, phase, 200)
+def test_attention_cfg2_geometry(ops, phase, impl):
+    _attention_case(ops, 4, 4, 256, 256, 4, 96, phase, 200, impl)
 
 
-def test_attention_ragged_blocks(ops):
-    _attention_case(ops, 3, 5, 176, 320, 2, 96, "step", 300)
-    _attention_case(ops, 3, 5, 176, 320, 2, 96, "prefix", 301)
+@pytest.mark.parametrize("impl", IMPLS)
+def test_attention_ragged_blocks(ops, impl):
+    _attention_case(ops, 3, 5, 176, 320, 2, 96, "step", 300, impl)
+    _attention_case(ops, 3, 5, 176, 320, 2, 96, "prefix", 301, impl)
+
+
+def test_attention_long_context_tile_skipping(ops):
+    """8 context clips (32 frames): most KV tiles of a context query tile are fully masked."""
+    _attention_case(ops, 32, 4, 64, 64, 2, 96, "prefix", 400)
+    _attention_case(ops, 32, 4, 64, 64, 2, 96, "step", 401)

@@ -54,3 +54,19 @@ def test_kmajor_sw64_layout():
     d = ops.umma_probe(kmajor_image(a, 64).to(DEV), kmajor_image(b, 64).to(DEV),
                        smem_desc(16, 512, 4), smem_desc(16, 512, 4), idesc(128, 128), 2, 32, 32, 128)
     assert torch.equal(d.cpu(), a.float() @ b.float().t())
+
+
+@pytest.mark.parametrize("d,row_bytes,layout", [(96, 64, 4), (64, 128, 2), (128, 128, 2)])
+def test_mn_major_b_operand_is_v_as_stored(d, row_bytes, layout):
+    """O = P V with V kept as stored in the KV cache, [keys][d] (d contiguous) = an MN-major B
+    operand: chunks of row_bytes/2 d-columns (LBO = chunk stride), 8-key groups (SBO = 8 rows),
+    16 keys per MMA K-step (= 16 rows of start-address advance)."""
+    from videogpt_b200 import ops
+    keys = 64
+    p, v = ints((128, keys), 5), ints((keys, d), 6)
+    cw = row_bytes // 2
+    v_img = torch.cat([kmajor_image(v[:, c * cw:(c + 1) * cw].contiguous(), row_bytes) for c in range(d // cw)])
+    out = ops.umma_probe(kmajor_image(p, 128).to(DEV), v_img.to(DEV), smem_desc(16, 1024, 2),
+                         smem_desc(keys * row_bytes, 8 * row_bytes, layout), idesc(128, d, b_mn=1),
+                         keys // 16, 32, 16 * row_bytes, d)
+    assert torch.equal(out.cpu(), p.float() @ v.float())

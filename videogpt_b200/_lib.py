@@ -22,7 +22,8 @@ SIGNATURES = {
     "vgpt_rmsnorm": [P, P, P, I, I, F, P],
     "vgpt_rope_table": [P, P, I, I, P],
     "vgpt_rope_kv_append": [P, P, P, P, P, P, I, I, I, P],
-    "vgpt_attn_clip_causal": [P, I, P, I, P, P, P, I, P, I, I, P, P, P, I, I, I, F, P],
+    "vgpt_attn_clip_causal": [P, I, I, P, I, P, P, I, P, I, P, I, I, P, P, P, I, I, I, F, P],
+    "vgpt_attn_clip_causal_mma_sync": [P, I, I, P, I, P, P, I, P, I, P, I, I, P, P, P, I, I, I, F, P],
     "vgpt_embed_assemble": [P, I, I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, P],
     "vgpt_timestep_sinusoid": [P, P, P, I, I, P],
     "vgpt_linear_small": [P, P, P, P, I, I, I, I, I, P],

@@ -28,11 +28,22 @@ int vgpt_rope_kv_append(void* qkv, const int32_t* row_pos, const int32_t* row_sl
   return vgpt::rope_kv_append(qkv, row_pos, row_slot, table, k_pool, v_pool, rows, H, D,
                               VGPT_PAGE_TOKENS, S(stream));
 }
-int vgpt_attn_clip_causal(const void* q, int q_ld, void* out, int out_ld, const void* k_pool,
-                          const void* v_pool, const int32_t* page_table, int max_pages,
+int vgpt_attn_clip_causal(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
+                          const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                           const VgptAttnSeq* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
                           const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H,
                           int D, float scale, void* stream) {
+  return vgpt::attn_clip_causal_tc(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,
+                                   max_pages, seqs, num_seqs, max_q_rows, q_code, k_code, k_tile_minmax,
+                                   max_k_tiles, H, D, scale, S(stream));
+}
+int vgpt_attn_clip_causal_mma_sync(const void* q, int q_ld, int q_rows, void* out, int out_ld,
+                                   const void* k_pool, const void* v_pool, int total_pages,
+                                   const int32_t* page_table, int max_pages, const VgptAttnSeq* seqs,
+                                   int num_seqs, int max_q_rows, const int32_t* q_code, const int32_t* k_code,
+                                   const int32_t* k_tile_minmax, int max_k_tiles, int H, int D, float scale,
+                                   void* stream) {
+  (void)q_rows; (void)total_pages;
   return vgpt::attn_clip_causal(q, q_ld, out, out_ld, k_pool, v_pool, page_table, max_pages, seqs,
                                 num_seqs, max_q_rows, q_code, k_code, k_tile_minmax, max_k_tiles, H, D,
                                 scale, S(stream));

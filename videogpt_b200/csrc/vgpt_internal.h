@@ -30,6 +30,11 @@ int attn_clip_causal(const void* q, int q_ld, void* out, int out_ld, const void*
                      int num_seqs, int max_q_rows, const int32_t* q_code, const int32_t* k_code,
                      const int32_t* k_tile_minmax, int max_k_tiles, int H, int D, float scale,
                      cudaStream_t s);
+int attn_clip_causal_tc(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
+                        const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
+                        const void* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
+                        const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H, int D,
+                        float scale, cudaStream_t s);
 int embed_assemble(void* hidden, int rows, int hs, const int32_t* kind, const int32_t* a,
                    const int32_t* b, const void* embed_tokens, const void* time_tokens, const void* z,
                    const void* ctx, int C, int lat_h, int lat_w, const void* wx, const void* bx,

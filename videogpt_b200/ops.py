@@ -96,19 +96,26 @@ def rope_kv_append(qkv, row_pos, row_slot, table, k_pool, v_pool, heads: int, he
               _p(v_pool), rows, heads, head_dim, _stream())
 
 
+ATTN_IMPL = "tcgen05"       # "mma_sync" selects the legacy cross-check kernel (tests only)
+
+
 def attention(q, out, k_pool, v_pool, page_table, seqs, max_q_rows: int, q_code, k_code, k_tile_minmax,
-              heads: int, head_dim: int, scale: float):
-    """q: [rows, >= H*D] (row-strided view allowed, e.g. the q part of qkv); out: [rows, H*D]."""
+              heads: int, head_dim: int, scale: float, impl: str = None):
+    """q: [rows, >= H*D] (row-strided view allowed, e.g. the q part of qkv); out: [rows, H*D];
+    pools: [pages, H, 128, D]."""
     _req(q, BF16, "q", contiguous=False); _req(out, BF16, "out", contiguous=False)
+    _req(k_pool, BF16, "k_pool"); _req(v_pool, BF16, "v_pool")
     _req(page_table, I32, "page_table"); _req(seqs, I32, "seqs"); _req(q_code, I32, "q_code")
     _req(k_code, I32, "k_code"); _req(k_tile_minmax, I32, "k_tile_minmax")
     num_seqs, max_pages = page_table.shape
     assert seqs.shape == (num_seqs, 4) and k_code.shape == (num_seqs, max_pages * PAGE_TOKENS)
     max_k_tiles = k_tile_minmax.shape[1]
     assert k_tile_minmax.shape == (num_seqs, max_k_tiles, 2)
-    _lib.call("vgpt_attn_clip_causal", _p(q), q.stride(0), _p(out), out.stride(0), _p(k_pool), _p(v_pool),
-              _p(page_table), max_pages, _p(seqs), num_seqs, max_q_rows, _p(q_code), _p(k_code),
-              _p(k_tile_minmax), max_k_tiles, heads, head_dim, float(scale), _stream())
+    assert k_pool.shape == v_pool.shape and k_pool.shape[1:] == (heads, PAGE_TOKENS, head_dim)
+    name = "vgpt_attn_clip_causal" if (impl or ATTN_IMPL) == "tcgen05" else "vgpt_attn_clip_causal_mma_sync"
+    _lib.call(name, _p(q), q.stride(0), q.shape[0], _p(out), out.stride(0), _p(k_pool), _p(v_pool),
+              k_pool.shape[0], _p(page_table), max_pages, _p(seqs), num_seqs, max_q_rows, _p(q_code),
+              _p(k_code), _p(k_tile_minmax), max_k_tiles, heads, head_dim, float(scale), _stream())
     return out
 
 
