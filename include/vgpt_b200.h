@@ -43,9 +43,11 @@ const char* vgpt_last_error(void);
  * down_proj of transformers' Phi3MLP.  epilogue: VGPT_EPI_STORE; VGPT_EPI_RESIDUAL
  * (C = bf16(A W^T) + R, R may alias C: the in-place residual stream of Phi3DecoderLayer);
  * VGPT_EPI_SWIGLU (W packed by vgpt_pack_gate_up, C[M,N/2] = up * silu(gate)).
- * K % 64 == 0, N % 64 == 0; block_n 0 = auto (256 or 128). */
+ * K % 64 == 0, N % 64 == 0.  cta_pair 1 = CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles,
+ * block_n 128/192/256), 0 = single CTAs (128 x block_n, block_n 128/256), -1 = tuned default;
+ * block_n 0 = tuned default. */
 int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                   int ldc, int epilogue, int block_n, void* stream);
+                   int ldc, int epilogue, int block_n, int cta_pair, void* stream);
 
 /* gate_up_proj.weight [2I,K] ([gate | up] rows, Phi3MLP chunk(2)) -> block-interleaved rows. */
 int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream);

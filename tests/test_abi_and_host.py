@@ -42,7 +42,7 @@ def test_argument_errors_surface_as_exceptions_without_a_gpu():
     with pytest.raises(_lib.VgptError, match="multiple of 64"):
         buf = ctypes.create_string_buffer(64)
         p = ctypes.cast(buf, ctypes.c_void_p)
-        _lib.call("vgpt_gemm_bf16", p, p, p, None, 8, 64, 100, 104, 64, 0, 0, None)
+        _lib.call("vgpt_gemm_bf16", p, p, p, None, 8, 64, 100, 104, 64, 0, 0, 0, None)
 
 
 def test_no_cpu_fallback():
@@ -140,3 +140,19 @@ def test_scheduler_sigma_and_scalars():
         assert torch.equal(s.sigma, so.sigma_grid(steps, shift))
         oms, ds = s._scalars(steps - 1)
         assert oms == float(1.0 - s.sigma[steps - 1]) and ds == float(s.sigma[steps] - s.sigma[steps - 1])
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 1), (4, 256, 256, 1), (3, 176, 320, 8), (1, 64, 96, 4)])
+def test_single_frame_codes_reproduce_the_reference_mask(case):
+    n_ctx, H, W, sp = case
+    d = po.single_frame_inputs(n_ctx, H, W, True, sp)
+    n_tok = H * W // 256
+    specs, n_lat, n_c = eng.single_frame_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"], n_tok)
+    L = d["position_ids"].shape[1]
+    assert n_lat == 2 and n_c == n_ctx
+    for b, s in enumerate(specs):
+        pad = L - (s.n_prefix + s.n_active)
+        assert np.array_equal(eng.codes_dense_mask(s.codes, pad), d["attention_mask"][b].numpy().astype(bool))
+        assert np.array_equal(s.positions, d["position_ids"][b, pad:].numpy())
+    plan = eng.build_plan(specs, n_lat, n_c, H // 8, W // 8, "cpu")
+    assert plan.step.rows == 2 * (n_tok + 1) and plan.prefix.rows == specs[0].n_prefix + 1

@@ -168,3 +168,18 @@ def test_pipeline_latent_entry_point(dry):
     assert len(out) == 2 and out[0].shape == (1, 4, 8, 8)
     out = pipe.next_clip_latents(lat[:4], 2, num_inference_steps=2, img_guidance_scale=1.0, initial_noise=lat[4:])
     assert len(out) == 2                      # guidance off: single branch, all generated frames returned
+
+
+def test_single_frame_path_dryrun(dry):
+    from videogpt_b200 import LVMScheduler
+    m = _model()
+    d = po.single_frame_inputs(2, 64, 64, True, 1)
+    lat = [x.to(BF) for x in synth.synthetic_latents(3, 64, 64)]
+    mk = dict(input_ids=d["input_ids"], input_img_latents=lat[:2], input_image_sizes=d["input_image_sizes"],
+              attention_mask=d["attention_mask"], position_ids=d["position_ids"], img_cfg_scale=1.5,
+              use_img_cfg=True, use_kv_cache=False, offload_model=False)
+    z = torch.cat([lat[2], lat[2]], 0)
+    out = LVMScheduler(num_steps=2)(z, m.forward_with_cfg, mk, prediction_type="v")
+    assert out.shape == (2, 4, 8, 8)
+    pred, cache = m.forward_with_cfg(z, torch.full((2,), 0.5), past_key_values=None, prediction_type="v", **mk)
+    assert cache is None and pred.shape == (2, 4, 8, 8)

@@ -41,10 +41,10 @@ def _rel(a, b):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (16, 512, 3072), (2064, 1536, 512),
                                    (300, 3072, 1024), (1032, 9216, 3072)])
-@pytest.mark.parametrize("block_n", [256, 128])
-def test_gemm_store(ops, M, N, K, block_n):
+@pytest.mark.parametrize("block_n,cta_pair", [(256, 0), (192, 0), (128, 0), (256, 1), (192, 1), (128, 1)])
+def test_gemm_store(ops, M, N, K, block_n, cta_pair):
     a, w = _rand((M, K), 1), _rand((N, K), 2, 0.05)
-    c = ops.gemm(a, w, block_n=block_n)
+    c = ops.gemm(a, w, block_n=block_n, cta_pair=cta_pair)
     ref = a.float() @ w.float().t()
     # fp32 accumulation of exact bf16 products, one final rounding: <= 2^-8 of the row scale
     err = (c.float() - ref).abs().max().item()
@@ -52,30 +52,33 @@ def test_gemm_store(ops, M, N, K, block_n):
     assert _rel(c, ref) < 4e-3
 
 
-def test_gemm_identity_layout(ops):
-    """W = I picks out columns of A exactly: catches any operand layout / swizzle mix-up."""
-    M, K = 256, 256
+@pytest.mark.parametrize("block_n,cta_pair", [(256, 0), (192, 0), (256, 1), (192, 1), (128, 1)])
+def test_gemm_identity_layout(ops, block_n, cta_pair):
+    """W = I picks out columns of A exactly: catches any operand layout / swizzle / pair-split mix-up."""
+    M, K = 520, 384
     a = _rand((M, K), 3)
     w = torch.eye(K, device=DEV, dtype=BF)
-    c = ops.gemm(a, w)
+    c = ops.gemm(a, w, block_n=block_n, cta_pair=cta_pair)
     assert torch.equal(c, a)
     perm = torch.randperm(K, generator=torch.Generator().manual_seed(0)).to(DEV)
-    c = ops.gemm(a, w[perm])
+    c = ops.gemm(a, w[perm], block_n=block_n, cta_pair=cta_pair)
     assert torch.equal(c, a[:, perm])
 
 
+@pytest.mark.parametrize("cta_pair,block_n", [(0, 0), (1, 256), (1, 192)])
 @pytest.mark.parametrize("M,N,K", [(2064, 512, 1024), (130, 3072, 8192)])
-def test_gemm_residual_in_place(ops, M, N, K):
+def test_gemm_residual_in_place(ops, M, N, K, cta_pair, block_n):
     a, w, r = _rand((M, K), 4), _rand((N, K), 5, 0.03), _rand((M, N), 6)
     want = (a.float() @ w.float().t()).to(BF).float() + r.float()     # bf16(o_proj) + residual, rounded
     out = r.clone()
-    ops.gemm(a, w, out=out, residual=out, epilogue=ops.EPI_RESIDUAL)
+    ops.gemm(a, w, out=out, residual=out, epilogue=ops.EPI_RESIDUAL, block_n=block_n, cta_pair=cta_pair)
     assert (out.float() - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
     assert _rel(out, want) < 4e-3
 
 
+@pytest.mark.parametrize("cta_pair,block_n", [(0, 0), (0, 192), (1, 256), (1, 192)])
 @pytest.mark.parametrize("M,I,K", [(2064, 1024, 512), (257, 8192, 3072)])
-def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K):
+def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K, cta_pair, block_n):
     """gate_up GEMM + SwiGLU epilogue on the packed weight == Phi3MLP's chunk / silu / mul."""
     x, wgu = _rand((M, K), 7), _rand((2 * I, K), 8, 0.03)
     packed = ops.pack_gate_up(wgu)
@@ -83,7 +86,7 @@ def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K):
     blk = torch.arange(2 * I, device=DEV).view(-1, 64)
     src = torch.where(blk % 64 < 32, (blk // 64) * 32 + blk % 64, I + (blk // 64) * 32 + blk % 64 - 32)
     assert torch.equal(packed, wgu[src.view(-1)])
-    h = ops.gemm(x, packed, epilogue=ops.EPI_SWIGLU)
+    h = ops.gemm(x, packed, epilogue=ops.EPI_SWIGLU, block_n=block_n, cta_pair=cta_pair)
     gu = (x.float() @ wgu.float().t()).to(BF)
     gate, up = gu.chunk(2, dim=-1)
     want = (up * torch.nn.functional.silu(gate)).float()

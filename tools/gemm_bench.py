@@ -20,10 +20,10 @@ for name, (N, K, epi) in shapes.items():
     a = torch.randn(M, K, device=dev).to(torch.bfloat16)
     n_out = N // 2 if epi == ops.EPI_SWIGLU else N
     out = torch.zeros(M, n_out, device=dev, dtype=torch.bfloat16)
-    for bn in (256, 128):
+    for bn, pair in ((256, 0), (192, 0), (256, 1), (192, 1)):
         def run():
             for w in ws:
-                ops.gemm(a, w, out=out, residual=out if epi == ops.EPI_RESIDUAL else None, epilogue=epi, block_n=bn)
+                ops.gemm(a, w, out=out, residual=out if epi == ops.EPI_RESIDUAL else None, epilogue=epi, block_n=bn, cta_pair=pair)
         run(); torch.cuda.synchronize()
         s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -31,5 +31,5 @@ for name, (N, K, epi) in shapes.items():
             run()
         t.record(); torch.cuda.synchronize()
         us = s.elapsed_time(t) * 1e3 / (5 * L)
-        print(f"{name:8s} M={M} N={N} K={K} block_n={bn}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:8.1f} TFLOP/s", flush=True)
+        print(f"{name:8s} M={M} N={N} K={K} block_n={bn} pair={pair}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:8.1f} TFLOP/s", flush=True)
     del ws

@@ -17,7 +17,7 @@ P, I, F = c_void_p, c_int, c_float
 SIGNATURES = {
     "vgpt_abi_version": [],
     "vgpt_last_error": [],
-    "vgpt_gemm_bf16": [P, P, P, P, I, I, I, I, I, I, I, P],
+    "vgpt_gemm_bf16": [P, P, P, P, I, I, I, I, I, I, I, I, P],
     "vgpt_pack_gate_up": [P, P, I, I, P],
     "vgpt_rmsnorm": [P, P, P, I, I, F, P],
     "vgpt_rope_table": [P, P, I, I, P],

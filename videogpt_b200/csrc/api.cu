@@ -11,8 +11,8 @@ int vgpt_abi_version(void) { return VGPT_ABI_VERSION; }
 const char* vgpt_last_error(void) { return vgpt::last_error(); }
 
 int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                   int ldc, int epilogue, int block_n, void* stream) {
-  return vgpt::gemm_bf16(A, W, C, R, M, N, K, lda, ldc, epilogue, block_n, S(stream));
+                   int ldc, int epilogue, int block_n, int cta_pair, void* stream) {
+  return vgpt::gemm_bf16(A, W, C, R, M, N, K, lda, ldc, epilogue, block_n, cta_pair, S(stream));
 }
 int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream) {
   return vgpt::pack_gate_up(w, packed, I, K, S(stream));

@@ -1,0 +1,340 @@
+// bf16 GEMM on CTA pairs (tcgen05 cta_group::2): C[M,N] = A[M,K] * W[N,K]^T, same contract and
+// epilogues as gemm_tcgen05.cu.
+//
+// Why a second kernel: with one CTA per 128 x 256 tile every SM pulls (128 + 256) x 64 bf16 per
+// 512 tensor cycles = 96 B/clk from L2, and the measured ~60 % tensor-pipe activity of that kernel
+// is the L2 -> SMEM fabric limit (profiles/r01a_gemm_1cta_ncu.txt).  A CTA pair computes a
+// 256 x BN tile: each CTA loads its own 128 rows of A and only HALF of the W tile, and one
+// tcgen05.mma.cta_group::2 (M = 256) reads both halves from the two SMs' shared memory, so the
+// per-SM fill rate drops to (128 + BN/2) x 128 B per k-block (64 B/clk at BN = 256).
+//
+// Pair protocol (cluster of 2 along M; rank 0 = leader):
+//   * both CTAs' TMA loads are .cta_group::2 and complete_tx on the LEADER's full barrier
+//     (the leader's arrive.expect_tx accounts for both halves),
+//   * the leader's elected thread issues the MMAs and commits with .multicast::cluster to the
+//     empty / tmem-full barriers of BOTH CTAs,
+//   * each CTA's epilogue warps drain their own TMEM half (128 rows) and arrive on the leader's
+//     tmem-empty barrier,
+//   * cluster barriers fence set-up and tear-down (the peer's smem / TMEM must outlive the
+//     leader's last MMA).
+#include "common.cuh"
+#include "vgpt_internal.h"
+
+#include <cuda.h>
+
+namespace vgpt {
+
+constexpr int kG2BlockM = 128;     // rows per CTA (256 per pair)
+constexpr int kG2BlockK = 64;
+constexpr int kG2Threads = 192;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = kG2BlockM * kG2BlockK * 2;         // 16 KB
+  static constexpr int kBBytes = (BN / 2) * kG2BlockK * 2;          // this CTA's half of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;     // two accumulator stages
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+};
+
+enum : int { kG2Store = 0, kG2Residual = 1, kG2SwiGLU = 2 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+// TMA load issued by either CTA of a pair; bytes are credited to the LEADER's barrier
+// (peer bit 24 of the shared::cluster address cleared, as CUTLASS' SM100_TMA_2SM_LOAD does).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// One 32-column chunk of one accumulator row -> global memory (same as the 1-CTA kernel).
+template <int EPI>
+__device__ __forceinline__ void store_chunk2(const uint32_t (&acc)[32], __nv_bfloat16* __restrict__ out,
+                                             const __nv_bfloat16* __restrict__ res) {
+  uint4 r[4];
+  if constexpr (EPI == kG2Residual) {
+    const uint4* rp = reinterpret_cast<const uint4*>(res);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = rp[i];
+  }
+  uint4* op = reinterpret_cast<uint4*>(out);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = __uint_as_float(acc[i * 8 + j * 2]);
+      float b = __uint_as_float(acc[i * 8 + j * 2 + 1]);
+      if constexpr (EPI == kG2Residual) {
+        uint32_t rv = (&r[i].x)[j];
+        a = rbf(a) + bf16lo(rv);
+        b = rbf(b) + bf16hi(rv);
+      }
+      w[j] = pack_bf16x2(a, b);
+    }
+    op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                              __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ R, int M, int N,
+                              int K, int ldc, int flags) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int m_tiles = (M + 2 * kG2BlockM - 1) / (2 * kG2BlockM);
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = K / kG2BlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);          // leader producer's arrive.expect_tx covers both CTAs' bytes
+      mbar_init(empty_bar(s), 1);         // leader's multicast commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar(s), 1);     // leader's multicast commit
+      mbar_init(tmem_empty_bar(s), 8);    // 4 epilogue warps x 2 CTAs (used in the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();                     // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile % m_tiles) * 2 * kG2BlockM + rank * kG2BlockM;
+        const int n0 = (tile / m_tiles) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          if (flags & 1) {                 // debug: MMA-bound ceiling, operands not refreshed
+            if (leader) mbar_arrive(full_bar(stage));
+          } else {
+            // The peer only issues its loads: its bytes are credited to the leader's barrier, whose
+            // phase cannot complete before the leader's own arrive.expect_tx (count 1).  (A remote
+            // mbarrier.arrive.release.cluster here serialised the peer's loads: profiles/r01c.)
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &tmap_a, full_bar(stage), kb * kG2BlockK, m0);
+            tma_load_2d_pair(sb, &tmap_b, full_bar(stage), kb * kG2BlockK, n0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader only) ================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kG2BlockM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(sb, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kG2BlockK / 16; ++k)
+            umma_f16_ss_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(tmem_full_bar(as));
+      }
+    }
+  } else {
+    // ================================ epilogue (both CTAs, own 128 rows) ================================
+    const int quad = warp & 3;
+    int local = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      const int m0 = (tile % m_tiles) * 2 * kG2BlockM + rank * kG2BlockM;
+      const int n0 = (tile / m_tiles) * BN;
+      const int row = m0 + quad * 32 + lane;
+      mbar_wait(tmem_full_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+      if constexpr (EPI == kG2SwiGLU) {
+        __nv_bfloat16* crow = C + (size_t)row * ldc + n0 / 2;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t g[32], u[32];
+          tmem_ld_32x32b_x32(taddr + c * 64, g);
+          tmem_ld_32x32b_x32(taddr + c * 64 + 32, u);
+          tmem_ld_wait();
+          if (row < M && n0 + c * 64 < N) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float gv = rbf(__uint_as_float(g[i]));
+              float uv = rbf(__uint_as_float(u[i]));
+              g[i] = __float_as_uint(uv * rbf(silu_f(gv)));
+            }
+            store_chunk2<kG2Store>(g, crow + c * 32, nullptr);
+          }
+        }
+      } else {
+        __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+        const __nv_bfloat16* rrow = (EPI == kG2Residual) ? R + (size_t)row * ldc + n0 : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          if (row < M && n0 + c * 32 < N) store_chunk2<EPI>(acc, crow + c * 32, rrow + c * 32);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                     // nobody frees smem / TMEM while the pair still works
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm2(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
+                        int ldc, int num_sms, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t box[2] = {kG2BlockK, kG2BlockM}, estr[2] = {1, 1};
+    int rc = encode_tensor_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(A), dims, strides, box,
+                               estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {kG2BlockK, BN / 2}, estr[2] = {1, 1};
+    int rc = encode_tensor_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box,
+                               estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  auto kern = gemm_bf16_tcgen05_pair_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + 2 * kG2BlockM - 1) / (2 * kG2BlockM)) * ((N + BN - 1) / BN);
+  const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  kern<<<2 * clusters, kG2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C),
+                                                             static_cast<const __nv_bfloat16*>(R), M, N, K, ldc,
+                                                             debug_gemm_flags());
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
+int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
+                   int epilogue, int block_n, cudaStream_t stream) {
+  const int sms = device_sm_count();
+#define VGPT_GEMM2_CASE(BN_, EPI_) \
+  if (block_n == BN_ && epilogue == EPI_) return launch_gemm2<BN_, EPI_>(A, W, C, R, M, N, K, lda, ldc, sms, stream);
+  VGPT_GEMM2_CASE(256, kG2Store)
+  VGPT_GEMM2_CASE(256, kG2Residual)
+  VGPT_GEMM2_CASE(256, kG2SwiGLU)
+  VGPT_GEMM2_CASE(192, kG2Store)
+  VGPT_GEMM2_CASE(192, kG2Residual)
+  VGPT_GEMM2_CASE(192, kG2SwiGLU)
+  VGPT_GEMM2_CASE(128, kG2Store)
+  VGPT_GEMM2_CASE(128, kG2Residual)
+  VGPT_GEMM2_CASE(128, kG2SwiGLU)
+#undef VGPT_GEMM2_CASE
+  set_last_error("vgpt_gemm_bf16: no CTA-pair kernel for block_n=%d epilogue=%d", block_n, epilogue);
+  return -1;
+}
+
+}  // namespace vgpt

@@ -17,6 +17,7 @@
 #include "vgpt_internal.h"
 
 #include <cuda.h>
+#include <cstdlib>
 
 namespace vgpt {
 
@@ -27,16 +28,36 @@ constexpr int kGemmThreads = 192;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two: 256 / 512)
+  static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;  // two accumulator stages
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: alignment
 };
 
 enum GemmEpilogue : int { kEpiStore = 0, kEpiResidual = 1, kEpiSwiGLU = 2 };
+// defaults used when the caller passes block_n = 0 / cta_pair = -1 (tuned on B200, profiles/)
+constexpr int kDefaultCtaPair = 1;
+
+// Tile width for the CTA-pair kernel: fewest (waves x tile width), with the narrower tile charged
+// for its higher L2 -> SMEM fill rate per MMA cycle (profiles/r01c_gemm_sweep_pair.txt: qkv and
+// gate_up prefer 256, the N = 3072 projections prefer 192 at M = 2064).
+static int pick_pair_block_n(int M, int N, int num_sms) {
+  const int clusters = num_sms / 2;
+  const int m_tiles = (M + 255) / 256;
+  double best = 0;
+  int best_bn = 256;
+  const int cand[2] = {256, 192};
+  const double eff[2] = {1.0, 0.92};
+  for (int i = 0; i < 2; ++i) {
+    const int tiles = m_tiles * ((N + cand[i] - 1) / cand[i]);
+    const double cost = (double)((tiles + clusters - 1) / clusters) * cand[i] / eff[i];
+    if (i == 0 || cost < best - 1e-9) { best = cost; best_bn = cand[i]; }
+  }
+  return best_bn;
+}
 
 // One 32-column chunk of one accumulator row -> global memory.
 template <int EPI>
@@ -73,7 +94,7 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                          const __grid_constant__ CUtensorMap tmap_b, __nv_bfloat16* __restrict__ C,
-                         const __nv_bfloat16* __restrict__ R, int M, int N, int K, int ldc) {
+                         const __nv_bfloat16* __restrict__ R, int M, int N, int K, int ldc, int flags) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B atoms: 1 KB aligned
@@ -124,9 +145,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m0);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
+          if (flags & 1) {                 // debug: MMA-bound ceiling, operands not refreshed
+            mbar_arrive(full_bar(stage));
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m0);
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBlockK, n0);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -224,6 +249,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+int debug_gemm_flags() {   // VGPT_DEBUG_GEMM_FLAGS=1: skip the TMA loads (profiling experiments only)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VGPT_DEBUG_GEMM_FLAGS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
                         CUtensorMapSwizzle swz) {
@@ -256,13 +290,14 @@ static int launch_gemm(const void* A, const void* W, void* C, const void* R, int
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
-      ta, tb, static_cast<__nv_bfloat16*>(C), static_cast<const __nv_bfloat16*>(R), M, N, K, ldc);
+      ta, tb, static_cast<__nv_bfloat16*>(C), static_cast<const __nv_bfloat16*>(R), M, N, K, ldc,
+      debug_gemm_flags());
   VGPT_CHECK_LAUNCH();
   return 0;
 }
 
 int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-              int ldc, int epilogue, int block_n, cudaStream_t stream) {
+              int ldc, int epilogue, int block_n, int cta_pair, cudaStream_t stream) {
   VGPT_CHECK_ARG(A && W && C, "vgpt_gemm_bf16: null pointer");
   VGPT_CHECK_ARG(M > 0 && N > 0 && K > 0, "vgpt_gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   VGPT_CHECK_ARG(K % kBlockK == 0, "vgpt_gemm_bf16: K=%d must be a multiple of %d", K, kBlockK);
@@ -273,10 +308,15 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
                  "vgpt_gemm_bf16: pointers must be 16-byte aligned");
   VGPT_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "vgpt_gemm_bf16: unknown epilogue %d", epilogue);
   VGPT_CHECK_ARG(epilogue != kEpiResidual || R, "vgpt_gemm_bf16: residual epilogue needs R");
-  if (block_n == 0) block_n = (N % 256 == 0) ? 256 : 128;
-  VGPT_CHECK_ARG((block_n == 128 || block_n == 256), "vgpt_gemm_bf16: block_n must be 128 or 256");
-  VGPT_CHECK_ARG(N % block_n == 0 || epilogue != kEpiSwiGLU,
-                 "vgpt_gemm_bf16: SwiGLU epilogue needs N %% block_n == 0");
+  if (cta_pair < 0) cta_pair = kDefaultCtaPair;
+  if (block_n == 0) block_n = cta_pair ? pick_pair_block_n(M, N, device_sm_count()) : ((N % 256 == 0) ? 256 : 128);
+  if (cta_pair) {
+    VGPT_CHECK_ARG(block_n == 128 || block_n == 192 || block_n == 256,
+                   "vgpt_gemm_bf16: CTA-pair block_n must be 128, 192 or 256");
+    return gemm_bf16_pair(A, W, C, R, M, N, K, lda, ldc, epilogue, block_n, stream);
+  }
+  VGPT_CHECK_ARG((block_n == 128 || block_n == 192 || block_n == 256),
+                 "vgpt_gemm_bf16: block_n must be 128, 192 or 256");
   const int sms = device_sm_count();
 #define VGPT_GEMM_CASE(BN_, EPI_)                                                         \
   if (block_n == BN_ && epilogue == EPI_)                                                  \
@@ -284,6 +324,9 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
   VGPT_GEMM_CASE(256, kEpiStore)
   VGPT_GEMM_CASE(256, kEpiResidual)
   VGPT_GEMM_CASE(256, kEpiSwiGLU)
+  VGPT_GEMM_CASE(192, kEpiStore)
+  VGPT_GEMM_CASE(192, kEpiResidual)
+  VGPT_GEMM_CASE(192, kEpiSwiGLU)
   VGPT_GEMM_CASE(128, kEpiStore)
   VGPT_GEMM_CASE(128, kEpiResidual)
   VGPT_GEMM_CASE(128, kEpiSwiGLU)

@@ -19,7 +19,10 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
 const char* last_error();
 
 int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-              int ldc, int epilogue, int block_n, cudaStream_t stream);
+              int ldc, int epilogue, int block_n, int cta_pair, cudaStream_t stream);
+int debug_gemm_flags();
+int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
+                   int epilogue, int block_n, cudaStream_t stream);
 int pack_gate_up(const void* w, void* packed, int I, int K, cudaStream_t s);
 int rmsnorm(const void* x, const void* w, void* y, int rows, int hidden, float eps, cudaStream_t s);
 int rope_table(const float* inv_freq, void* tab, int max_pos, int head_dim, cudaStream_t s);

@@ -170,6 +170,51 @@ def frame_block_specs(input_ids, position_ids, input_image_sizes, denoise_image_
     return specs, lat_counter, ctx_counter
 
 
+def single_frame_specs(input_ids, position_ids, input_image_sizes, n_out_tokens: int):
+    """Sequence specs of the one-frame-at-a-time layout of ``pipeline.__call__``
+    (``LVMCollator.__call__``, ``LVM/processor.py:943-962``; assembled in ``LVM.forward``,
+    ``LVM/model.py:345-362``): row b = [pad | condition tokens with context-image ranges | time
+    token | n_out_tokens noisy image tokens].  Prefix = condition tokens, active = time + image.
+
+    Codes reproduce ``create_mask`` + ``adjust_attention_for_input_images``
+    (processor.py:536-573, 776-781): condition tokens are causal (code = index), the tokens of one
+    context image share the code of its last token (bidirectional block), the time token is
+    causal, output-image tokens carry the largest code (they see everything; nothing earlier
+    sees them)."""
+    ids = input_ids.cpu().numpy()
+    pos = position_ids.cpu().numpy()
+    B, Lt = ids.shape
+    L = Lt + 1 + n_out_tokens
+    assert pos.shape == (B, L), "position_ids must cover condition + time + image tokens"
+    pads = (Lt + n_out_tokens + 1) - (pos.max(axis=1) + 1)          # create_position: pos = idx - pad
+    specs, ctx_counter = [], 0
+    for b in range(B):
+        pad = int(pads[b])
+        t_real = Lt - pad
+        T = t_real + 1 + n_out_tokens
+        kinds = np.full(T, ops.ROW_TOKEN, np.int32)
+        arg_a = np.zeros(T, np.int32)
+        arg_b = np.zeros(T, np.int32)
+        arg_a[:t_real] = ids[b, pad:]
+        codes = np.arange(T, dtype=np.int32)
+        for s_, e_ in input_image_sizes.get(b, []):
+            kinds[s_ - pad:e_ - pad] = ops.ROW_CONTEXT_PATCH
+            arg_a[s_ - pad:e_ - pad] = ctx_counter
+            arg_b[s_ - pad:e_ - pad] = np.arange(e_ - s_)
+            codes[s_ - pad:e_ - pad] = e_ - pad - 1
+            ctx_counter += 1
+        kinds[t_real] = ops.ROW_TIME
+        arg_a[t_real] = b
+        kinds[t_real + 1:] = ops.ROW_NOISY_PATCH
+        arg_a[t_real + 1:] = b
+        arg_b[t_real + 1:] = np.arange(n_out_tokens)
+        codes[t_real + 1:] = T
+        specs.append(SequenceSpec(n_prefix=t_real, n_active=1 + n_out_tokens,
+                                  positions=pos[b, pad:].astype(np.int32), codes=codes, kinds=kinds,
+                                  arg_a=arg_a, arg_b=arg_b, latent_rows=[(b, t_real + 1)]))
+    return specs, B, ctx_counter
+
+
 def codes_dense_mask(spec_codes: np.ndarray, pad: int) -> np.ndarray:
     """Dense bool mask (with ``pad`` left-pad tokens) implied by a code array -- host mirror of
     ``vgpt_mask_from_codes``, used to validate a caller-supplied ``attention_mask``."""

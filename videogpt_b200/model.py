@@ -337,6 +337,60 @@ class LVM(nn.Module):
             out = cond + cond
         return out, None
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("LVM.forward (pipeline.__call__ path) is served by "
-                                  "forward_with_cfg; see DESIGN.md")
+    # ---- pipeline.__call__ path (one output frame, batched tensor x) --------------------------------
+    def prepare_single_frame(self, input_ids, input_img_latents, input_image_sizes, attention_mask,
+                             position_ids, lat_h, lat_w, check_mask: bool = True):
+        e = self.engine()
+        ident = self._identity("single", input_ids, position_ids, input_img_latents, input_image_sizes,
+                               attention_mask, lat_h, lat_w)
+        if ident == self._plan_key and e.plan is not None and e.prefilled:
+            return e
+        ids_host, pos_host = input_ids.cpu(), position_ids.cpu()
+        layout = ("single", ids_host.numpy().tobytes(), pos_host.numpy().tobytes(), tuple(ids_host.shape),
+                  self._identity(input_image_sizes), lat_h, lat_w)
+        n_tok = (lat_h // self.patch_size) * (lat_w // self.patch_size)
+        n_ctx = sum(len(v) for v in input_image_sizes.values())
+        assert n_ctx == len(input_img_latents or [])                                   # model.py:358
+        for lat in (input_img_latents or []):
+            if tuple(lat.shape[-2:]) != (lat_h, lat_w):
+                raise NotImplementedError("context and output frames must have the same size "
+                                          "(use_input_image_size_as_output=True)")
+        if layout != self._layout_key or e.plan is None:
+            specs, n_lat, n_ctx = eng.single_frame_specs(ids_host, pos_host, input_image_sizes, n_tok)
+            if check_mask and attention_mask is not None:
+                self._check_mask(attention_mask, specs, e.device)
+            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device))
+            self._layout_key = layout
+        ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
+        e.prefill(ctx)
+        self._plan_key = ident
+        return e
+
+    @torch.no_grad()
+    def forward(self, x, timestep, input_ids, input_img_latents, input_image_sizes, attention_mask,
+                position_ids, padding_latent=None, past_key_values=None, return_past_key_values=True,
+                offload_model: bool = False):
+        """``LVM.forward`` (model.py:330-397) for a batched tensor ``x`` ``[B,4,h,w]``."""
+        if isinstance(x, list) or padding_latent is not None:
+            raise NotImplementedError("multi-resolution lists are not supported on this path")
+        lat_h, lat_w = x.shape[-2:]
+        e = self.prepare_single_frame(input_ids, input_img_latents, input_image_sizes, attention_mask,
+                                      position_ids, lat_h, lat_w)
+        assert x.shape[0] == e.plan.n_latents and timestep.numel() == x.shape[0]
+        e.z.copy_(x)
+        e.t.copy_(timestep.to(device=e.device, dtype=torch.float32))
+        out = e.predict().clone()
+        return (out, None) if return_past_key_values else out
+
+    @torch.no_grad()
+    def forward_with_cfg(self, x, timestep, input_ids, input_img_latents, input_image_sizes, attention_mask,
+                         position_ids, use_img_cfg, img_cfg_scale, past_key_values, use_kv_cache,
+                         offload_model, prediction_type: str = "v"):
+        """``LVM.forward_with_cfg`` (model.py:503-516)."""
+        self.llm.config.use_cache = use_kv_cache
+        out, _ = self.forward(x, timestep, input_ids, input_img_latents, input_image_sizes, attention_mask,
+                              position_ids)
+        if use_img_cfg and prediction_type == "v":
+            ops.cfg_combine(self._engine.pred, img_cfg_scale)
+            out = self._engine.pred.clone()
+        return out, None

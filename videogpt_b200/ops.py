@@ -41,7 +41,7 @@ def _req(t: torch.Tensor, dtype, name: str, contiguous: bool = True):
     return t
 
 
-def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int = 0):
+def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int = 0, cta_pair: int = -1):
     """``out[M,N(/2)] = a[M,K] @ w[N,K]^T`` (+ epilogue).  ``a`` may be row-strided."""
     _req(a, BF16, "a", contiguous=False)
     _req(w, BF16, "w")
@@ -57,7 +57,7 @@ def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int 
         _req(residual, BF16, "residual", contiguous=False)
         assert residual.shape == out.shape and residual.stride(0) == out.stride(0)
     _lib.call("vgpt_gemm_bf16", _p(a), _p(w), _p(out), _p(residual), M, N, K, a.stride(0),
-              out.stride(0), epilogue, block_n, _stream())
+              out.stride(0), epilogue, block_n, cta_pair, _stream())
     return out
 
 

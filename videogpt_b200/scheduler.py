@@ -36,8 +36,10 @@ class LVMScheduler:
             z = z * noise_level + torch.randn_like(z) * (1 - noise_level)
         model = getattr(func, "__self__", None)
         from .model import LVM
-        if isinstance(model, LVM) and getattr(func, "__name__", "") == "frame_block_forward_with_cfg" \
-                and isinstance(z, list):
+        name = getattr(func, "__name__", "")
+        if isinstance(model, LVM) and name == "frame_block_forward_with_cfg" and isinstance(z, list):
+            out = self._run_engine(z, model, model_kwargs, prediction_type)
+        elif isinstance(model, LVM) and name == "forward_with_cfg" and torch.is_tensor(z):
             out = self._run_engine(z, model, model_kwargs, prediction_type)
         else:
             out = self._run_generic(z, func, model_kwargs, prediction_type)
@@ -45,15 +47,20 @@ class LVMScheduler:
         return out
 
     # ---- engine loop -----------------------------------------------------------------------------
-    def _run_engine(self, z: List[torch.Tensor], model, mk: dict, prediction_type: str):
+    def _run_engine(self, z, model, mk: dict, prediction_type: str):
+        is_list = isinstance(z, list)
         lat_h, lat_w = z[0].shape[-2:]
-        e = model.prepare_frame_block(mk["input_ids"], mk["input_img_latents"], mk["input_image_sizes"],
-                                      mk["attention_mask"], mk["position_ids"], mk["denoise_image_sizes"],
-                                      mk["time_emb_inx"], lat_h, lat_w)
+        if is_list:
+            e = model.prepare_frame_block(mk["input_ids"], mk["input_img_latents"], mk["input_image_sizes"],
+                                          mk["attention_mask"], mk["position_ids"], mk["denoise_image_sizes"],
+                                          mk["time_emb_inx"], lat_h, lat_w)
+        else:
+            e = model.prepare_single_frame(mk["input_ids"], mk["input_img_latents"], mk["input_image_sizes"],
+                                           mk["attention_mask"], mk["position_ids"], lat_h, lat_w)
         n = e.plan.n_latents
         assert len(z) == n
         use_cfg = bool(mk["use_img_cfg"])
-        e.z.copy_(torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0))
+        e.z.copy_(torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0) if is_list else z)
         vel = torch.empty_like(e.z[: n // 2 if use_cfg else n]) if self.record_velocity is not None else None
         for i in range(self.num_steps):
             e.t.fill_(float(self.sigma[i]))
@@ -63,6 +70,8 @@ class LVMScheduler:
                           float(mk["img_cfg_scale"]), vel_out=vel)
             if vel is not None:
                 self.record_velocity.append(vel.clone())
+        if not is_list:
+            return e.z.clone()
         out = [e.z[i:i + 1].clone() for i in range(n)]
         for i in range(n):
             z[i] = out[i]
