@@ -220,12 +220,37 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    cfg_split = args.parallelism == "cfg" and world > 1
+    if cfg_split:
+        from oracle import processor_oracle as _po   # index dicts only (host ints), not on the timed path
+        from videogpt_b200 import parallel
+        grp = parallel.CfgBranchGroup()
+        lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42 + grp.video_group)
+        ctx_dev = [x.to(dev, torch.bfloat16) for x in lat[:n_ctx]]
+        noise_dev = [x.to(dev, torch.bfloat16) for x in lat[n_ctx:]]
+        proc = LVMProcessor(FakeTokenizer())
+        from videogpt_b200.pipeline import frame_block_prompts
+        p, p_ = frame_block_prompts(n_ctx, n_gen)
+        d = proc.prompt_condition_frame_block_inference(
+            [p, p_], [[torch.empty(3, H, W, device="meta")] * n_ctx, []], height=H, width=W, use_img_cfg=True,
+            use_input_image_size_as_output=True, frame_blocks=[n_ctx, n_gen], build_dense_mask=False)
+        mk = dict(input_ids=d["input_ids"], input_img_latents=ctx_dev, input_image_sizes=d["input_image_sizes"],
+                  attention_mask=None, position_ids=d["position_ids"], denoise_image_sizes=d["denoise_image_sizes"],
+                  time_emb_inx=d["time_emb_inx"], img_cfg_scale=GUIDANCE, use_img_cfg=True)
+
     def clip_device():
+        if cfg_split:
+            return parallel.sample_cfg_split(model, LVMScheduler(euler), [x.clone() for x in noise_dev] * 2, mk, grp, "x1")
         # a fresh context tensor list every clip => the engine re-runs the prefill (as a new clip would)
         return pipe.next_clip_latents([x.clone() for x in ctx_dev], n_gen, initial_noise=noise_dev, **kw)
 
     def clip_host():
-        out = pipe.next_clip_latents(ctx_host, n_gen, initial_noise=noise_host, **kw)
+        if cfg_split:
+            mk["input_img_latents"] = [x.to(dev, non_blocking=True) for x in ctx_host]
+            out = parallel.sample_cfg_split(model, LVMScheduler(euler), [x.to(dev, non_blocking=True) for x in noise_host] * 2,
+                                            mk, grp, "x1")
+        else:
+            out = pipe.next_clip_latents(ctx_host, n_gen, initial_noise=noise_host, **kw)
         return [x.to("cpu", non_blocking=False) for x in out]
 
     for _ in range(max(args.warmup, 3)):
@@ -259,8 +284,9 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     tokens_per_clip = 2 * n_gen * block * euler
-    value = world * tokens_per_clip * args.steps / dt
-    e2e = world * tokens_per_clip * args.steps / dt_e2e
+    videos = world // 2 if cfg_split else world
+    value = videos * tokens_per_clip * args.steps / dt
+    e2e = videos * tokens_per_clip * args.steps / dt_e2e
     step_fl, prefill_fl, clip_fl = algorithmic_flops(dims, n_ctx, n_gen, block, euler)
     e = model.engine()
     launches = args.steps * (e.launches_per_prefill + euler * (e.launches_per_predict + 1))
@@ -291,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": args.config, "model": "Phi-3-mini-class random-init" if kind == "full" else "2 layers / hidden 512",
                        "context_frames": n_ctx, "generated_frames": n_gen, "height": H, "width": W,
                        "euler_steps": euler, "cfg": True, "guidance": GUIDANCE, "prediction_type": "x1",
-                       "parallelism": f"dp{world} (independent videos)",
+                       "parallelism": (f"cfg-branch pairs x dp{world // 2}" if cfg_split else f"dp{world} (independent videos)"),
                        "l2": "weights 7.2 GB streamed every Euler step (> 126 MB L2); no explicit flush"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "tokens/s", "s_per_clip": dt_e2e / args.steps,
@@ -308,6 +334,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--parallelism", default="dp", choices=["dp", "cfg"],
+                    help="N>1: dp = independent videos per rank; cfg = CFG branches split over rank pairs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

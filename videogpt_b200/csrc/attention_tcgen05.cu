@@ -8,14 +8,15 @@
 //     chunks, head_dim 64 / 128 as 64-element SW128 chunks.
 //   * S = Q K^T is a tcgen05.mma (M=128, N=128) into TMEM, double buffered so the tensor core
 //     computes S(j+1) while the softmax warps work on S(j).
-//   * Softmax: 4 warps, one thread per query row (TMEM lane == row), exp2 domain, code predicate
-//     only on boundary tiles.  P is written to shared memory as a bf16 K-major SW128 A operand.
+//   * Softmax: 8 warps, two threads per query row (TMEM lane == row, 64 key columns each),
+//     exp2 domain, code predicate only on boundary tiles.  P is written to shared memory as a bf16 K-major SW128 A operand.
 //   * O += P V is a tcgen05.mma with V consumed exactly as it lies in the cache ([key][d] =
 //     MN-major B operand), accumulating in TMEM; when a row maximum grows, the owning thread
 //     rescales its O row in TMEM (tcgen05.ld / st) before the next P V is issued.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = softmax / correction / epilogue (TMEM lane quadrant = warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = softmax / correction / epilogue (TMEM lane quadrant = warp_idx % 4; the two warps
+// of a quadrant split the key columns and the output columns in halves).
 #include "common.cuh"
 #include "vgpt_internal.h"
 
@@ -25,7 +26,7 @@ namespace vgpt {
 
 constexpr int kTcBM = 128;          // queries per CTA
 constexpr int kTcBN = 128;          // keys per tile = one KV page
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;    // TMA warp + MMA warp + 8 softmax warps
 
 struct AttnSeqTc { int32_t q_row0, n_q, kv_len, reserved; };
 
@@ -53,6 +54,28 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -69,6 +92,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   constexpr int kTcStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_qmin, s_qmax;
+  __shared__ float s_rowmax[2][2][128];
+  __shared__ float s_rowsum[2][128];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t s_q = base;
@@ -105,7 +130,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     mbar_init(bar_q, 1);
     for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), 1); }
     mbar_init(bar_s_full(0), 1); mbar_init(bar_s_full(1), 1);
-    mbar_init(bar_p_full, 128);
+    mbar_init(bar_p_full, 256);
     mbar_init(bar_o_full, 1);
     fence_barrier_init();
   }
@@ -207,66 +232,78 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else {
     // ========================= softmax / correction / epilogue =========================
+    // 8 warps: two per TMEM lane quadrant; the pair splits the 128 key columns of a row (and the
+    // D output columns) in halves, so every SM sub-partition has two softmax warps to interleave.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;                       // row of the Q tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int qc = (row < rows_here) ? q_code[sq.q_row0 + q0 + row] : (int)0x80000000;
-    const int32_t* kc = k_code + (size_t)seq_id * max_pages * kTcBN;
+    const int32_t* kc = k_code + (size_t)seq_id * max_pages * kTcBN + half * 64;
+    constexpr int kOUnits = D / 32;                         // 16-column units of O per thread
+    const uint32_t o_addr = tmem_o + lane_addr + half * (D / 2);
     float m_run = -INFINITY, l_run = 0.f;
     int j = 0;
     for (int kt = next_tile(0); kt < n_kt; kt = next_tile(kt + 1), ++j) {
       mbar_wait(bar_s_full(j & 1), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t s[128];
+      uint32_t s[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tmem_s0 + lane_addr + (j & 1) * 128 + c * 32,
+      for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(tmem_s0 + lane_addr + (j & 1) * 128 + half * 64 + c * 32,
                                                       *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
       tmem_ld_wait();
       const bool need_mask = tile_max(kt) > q_min || (kt + 1) * kTcBN > sq.kv_len;
       if (need_mask) {
-        const int32_t* kcode = kc + kt * kTcBN;
+        const int4* kcode = reinterpret_cast<const int4*>(kc + kt * kTcBN);
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (qc < __ldg(kcode + i)) s[i] = 0xff800000u;      // -inf
+        for (int i = 0; i < 16; ++i) {
+          const int4 c4 = __ldg(kcode + i);
+          if (qc < c4.x) s[4 * i + 0] = 0xff800000u;          // -inf
+          if (qc < c4.y) s[4 * i + 1] = 0xff800000u;
+          if (qc < c4.z) s[4 * i + 2] = 0xff800000u;
+          if (qc < c4.w) s[4 * i + 3] = 0xff800000u;
+        }
       }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
-      const float m_new = fmaxf(m_run, mx);
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      s_rowmax[j & 1][half][row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 softmax warps only
+      const float m_new = fmaxf(m_run, fmaxf(mx, s_rowmax[j & 1][half ^ 1][row]));
       const float sub = (m_new == -INFINITY) ? 0.f : m_new * scale_log2;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run * scale_log2 - sub);
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * scale_log2 - sub);
       // O(j-1) must be complete before it is rescaled and before P is overwritten
       if (j > 0) {
         mbar_wait(bar_o_full, (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
+          for (int u = 0; u < kOUnits; ++u) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(o_addr + u * 16, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(tmem_o + lane_addr + c * 32, o);
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x16(o_addr + u * 16, o);
           }
           tmem_st_wait();
         }
       }
       m_run = m_new;
       float sum = 0.f;
-      // P row -> smem, K-major SW128: chunk = 64 keys (128 B per row), 16-byte units XOR (row & 7)
+      // P half-row -> smem, K-major SW128 chunk `half` (64 keys = 128 B per row), 16-byte units
+      // XOR (row & 7)
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+      for (int u = 0; u < 8; ++u) {
         uint32_t w[4];
 #pragma unroll
         for (int h2 = 0; h2 < 4; ++h2) {
-          const float p0 = exp2f(__uint_as_float(s[u * 8 + h2 * 2]) * scale_log2 - sub);
-          const float p1 = exp2f(__uint_as_float(s[u * 8 + h2 * 2 + 1]) * scale_log2 - sub);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[u * 8 + h2 * 2]), scale_log2, -sub));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[u * 8 + h2 * 2 + 1]), scale_log2, -sub));
           sum += p0 + p1;
           w[h2] = pack_bf16x2(p0, p1);
         }
-        const int chunk = u >> 3, unit = u & 7;
-        *reinterpret_cast<uint4*>(p_gen + chunk * 16384 + row * 128 + ((unit ^ (row & 7)) << 4)) =
+        *reinterpret_cast<uint4*>(p_gen + half * 16384 + row * 128 + ((u ^ (row & 7)) << 4)) =
             make_uint4(w[0], w[1], w[2], w[3]);
       }
       l_run = l_run * alpha + sum;
@@ -275,30 +312,33 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_arrive(bar_p_full);
     }
     // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------
+    s_rowsum[half][row] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_run + s_rowsum[half ^ 1][row];
     if (j > 0) {
       mbar_wait(bar_o_full, (j - 1) & 1);
       tc_fence_after();
     }
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    __nv_bfloat16* orow = out + (size_t)(sq.q_row0 + q0 + row) * out_ld + head * D;
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    __nv_bfloat16* orow = out + (size_t)(sq.q_row0 + q0 + row) * out_ld + head * D + half * (D / 2);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t o[32];
+    for (int u = 0; u < kOUnits; ++u) {
+      uint32_t o[16];
       if (j > 0) {
-        tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
+        tmem_ld_32x32b_x16(o_addr + u * 16, o);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0u;
+        for (int i = 0; i < 16; ++i) o[i] = 0u;
       }
       if (row < rows_here) {
 #pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {
+        for (int v4 = 0; v4 < 2; ++v4) {
           uint32_t w[4];
 #pragma unroll
           for (int h2 = 0; h2 < 4; ++h2)
             w[h2] = pack_bf16x2(__uint_as_float(o[v4 * 8 + h2 * 2]) * inv, __uint_as_float(o[v4 * 8 + h2 * 2 + 1]) * inv);
-          reinterpret_cast<uint4*>(orow + c * 32)[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+          reinterpret_cast<uint4*>(orow + u * 16)[v4] = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     }

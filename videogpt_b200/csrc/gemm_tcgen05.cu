@@ -50,7 +50,7 @@ static int pick_pair_block_n(int M, int N, int num_sms) {
   double best = 0;
   int best_bn = 256;
   const int cand[2] = {256, 192};
-  const double eff[2] = {1.0, 0.92};
+  const double eff[2] = {1.0, 0.88};
   for (int i = 0; i < 2; ++i) {
     const int tiles = m_tiles * ((N + cand[i] - 1) / cand[i]);
     const double cost = (double)((tiles + clusters - 1) / clusters) * cand[i] / eff[i];

@@ -73,3 +73,64 @@ def max_over_ranks(seconds: float, device=None) -> float:
     t = torch.tensor([seconds], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# CFG-branch parallel sampling: two ranks per video, one 32 KB all-gather per Euler step
+# ------------------------------------------------------------------------------------------------
+def branch_spec(specs, branch: int):
+    """Sequence spec of one CFG branch with latent / context numbering local to its rank.
+    ``specs`` = [cond, uncond] from ``engine.frame_block_specs``."""
+    import copy
+    import numpy as np
+    from . import ops
+    sp = copy.deepcopy(specs[branch])
+    lat_ids = sorted(l for l, _ in sp.latent_rows)
+    base = lat_ids[0]
+    uses_latent = (sp.kinds == ops.ROW_TIME) | (sp.kinds == ops.ROW_NOISY_PATCH)
+    sp.arg_a = np.where(uses_latent, sp.arg_a - base, sp.arg_a).astype(np.int32)
+    sp.latent_rows = [(l - base, r) for l, r in sp.latent_rows]
+    n_ctx = int((sp.kinds == ops.ROW_CONTEXT_PATCH).any()) and int(sp.arg_a[sp.kinds == ops.ROW_CONTEXT_PATCH].max()) + 1
+    if n_ctx:
+        ctx0 = int(sp.arg_a[sp.kinds == ops.ROW_CONTEXT_PATCH].min())
+        sp.arg_a = np.where(sp.kinds == ops.ROW_CONTEXT_PATCH, sp.arg_a - ctx0, sp.arg_a).astype(np.int32)
+        n_ctx -= ctx0
+    return sp, len(lat_ids), n_ctx
+
+
+@torch.no_grad()
+def sample_cfg_split(model, scheduler, z: List[torch.Tensor], model_kwargs: dict, grp: CfgBranchGroup,
+                     prediction_type: str = "x1") -> List[torch.Tensor]:
+    """``LVMScheduler`` loop with the conditional and unconditional branch on different GPUs.
+
+    ``z`` and ``model_kwargs`` are the same objects the single-GPU path takes (both rows present on
+    both ranks; the host work is replicated like in the reference's SP ranks).
+    Returns the ``n_gen`` generated latents (identical on both ranks)."""
+    from . import engine as eng, ops
+    mk = model_kwargs
+    assert mk["use_img_cfg"], "CFG-branch parallelism needs guidance on"
+    lat_h, lat_w = z[0].shape[-2:]
+    specs, n_lat, n_ctx_total = eng.frame_block_specs(mk["input_ids"], mk["position_ids"], mk["input_image_sizes"],
+                                                     mk["denoise_image_sizes"], mk["time_emb_inx"])
+    assert len(specs) == 2 and n_lat % 2 == 0
+    n_gen = n_lat // 2
+    sp, n_local, n_ctx = branch_spec(specs, grp.branch)
+    e = model.engine()
+    layout = ("cfg-split", grp.branch, sp.codes.tobytes(), sp.positions.tobytes(), sp.kinds.tobytes(),
+              sp.arg_a.tobytes(), lat_h, lat_w)
+    if model._layout_key != layout or e.plan is None:    # same geometry as the last clip: keep plan + graph
+        e.set_plan(eng.build_plan([sp], n_local, n_ctx, lat_h, lat_w, e.device))
+        model._layout_key = layout
+    model._plan_key = None                               # the engine does not hold a 2-row plan
+    ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in mk["input_img_latents"]], 0) if n_ctx else None
+    e.prefill(ctx)
+    z_all = torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0).to(e.device, torch.bfloat16).contiguous()
+    pred_all = torch.empty_like(z_all)
+    for i in range(scheduler.num_steps):
+        e.z.copy_(z_all[:n_gen])                         # both halves of z_all are identical (quirk q7)
+        e.t.fill_(float(scheduler.sigma[i]))
+        e.predict()
+        grp.exchange_predictions(e.pred, pred_all)
+        oms, ds = scheduler._scalars(i)
+        ops.cfg_euler(z_all, pred_all, True, prediction_type == "x1", oms, ds, float(mk["img_cfg_scale"]))
+    return [z_all[i:i + 1].clone() for i in range(n_gen)]
