@@ -133,6 +133,11 @@ int vgpt_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int
                           uint32_t a_step_bytes, uint32_t b_step_bytes, float* d_out, int n_cols,
                           void* stream);
 
+/* Test hook: same with the A operand in tensor memory (a_words[128][a_cols] packed bf16x2). */
+int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes,
+                             uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t b_step_bytes,
+                             float* d_out, int n_cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

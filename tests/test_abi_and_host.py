@@ -173,3 +173,16 @@ def test_branch_spec_renumbers_latents_locally():
     assert plan.prefix.rows == 0 and plan.step.rows == 2 * 18 and plan.lat_row0[:2].tolist() == [2, 20]
     plan = eng.build_plan([cond], n0, c0, 8, 8, "cpu")
     assert plan.prefix.rows == 3 * 18 and plan.step.seqs.tolist() == [[0, 36, 90, 0]]
+
+
+@pytest.mark.parametrize("case", [(3, 2, 64, 64, 1), (2, 3, 64, 96, 8)])
+def test_codes_from_mask_recovers_block_causal_masks(case):
+    from videogpt_b200.transform import codes_from_mask
+    n_ctx, n_gen, H, W, sp = case
+    for d in (po.frame_block_inputs(n_ctx, n_gen, H, W, True, sp), po.single_frame_inputs(n_ctx, H, W, True, sp)):
+        for b in range(d["attention_mask"].shape[0]):
+            m = d["attention_mask"][b].bool()
+            qc, kc = codes_from_mask(m)
+            assert torch.equal(qc[:, None] >= kc[None, :], m)
+    with pytest.raises(ValueError):
+        codes_from_mask(torch.eye(5, dtype=torch.bool).flip(0))

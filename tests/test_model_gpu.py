@@ -195,3 +195,37 @@ def test_pipeline_next_clip_latents_host_to_host():
     assert len(out) == 2 and all(torch.equal(a, b) for a, b in zip(out, want[:2]))
     seeded = pipe.next_clip_latents(ctx, 2, num_inference_steps=2, img_guidance_scale=1.0, seed=7)
     assert len(seeded) == 2 and all(torch.isfinite(x.float()).all() for x in seeded)
+
+
+def test_replace_attention_operator_seam():
+    """Seam S1: an HF Phi-3 attention module patched by ``replace_attention`` returns what the
+    reference's ``new_forward`` computes (oracle ``attention``: qkv, RoPE, dense-mask SDPA, o_proj)."""
+    from transformers import Phi3Config
+    import transformers.models.phi3.modeling_phi3 as mp
+    from videogpt_b200 import replace_attention
+    dims = synth.REDUCED
+    cfg = Phi3Config(**dims.phi3_kwargs())
+    holder = torch.nn.Module()
+    holder.attn = mp.Phi3Attention(cfg, layer_idx=0)
+    sd = synth.init_state_dict(dims, seed=0, with_pos_embed=False)
+    holder.attn.qkv_proj.weight.data.copy_(sd["llm.layers.0.self_attn.qkv_proj.weight"])
+    holder.attn.o_proj.weight.data.copy_(sd["llm.layers.0.self_attn.o_proj.weight"])
+    holder.to(DEV, BF)
+    replace_attention(holder)
+    d = po.frame_block_inputs(3, 2, 64, 96, True, 4)
+    B, L = d["input_ids"].shape
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(B, L, dims.hidden_size, generator=g, device=DEV).to(BF)
+    add = mo.additive_mask(d["attention_mask"].to(DEV), BF)
+    pos = d["position_ids"].to(DEV)
+    out, w, cache = holder.attn(x, attention_mask=add, position_ids=pos, past_key_value=None)
+    assert w is None and cache is None and out.shape == x.shape
+    ocfg = _oracle_cfg(dims)
+    wts = {k: v.to(DEV, BF) for k, v in sd.items() if "layers.0.self_attn" in k}
+    cos, sin = mo.rope_cos_sin(pos, ocfg.head_dim, ocfg.rope_theta, BF)
+    want = mo.attention(wts, 0, x, add, cos, sin, ocfg)
+    assert rel_l2(out, want) < 1e-2                           # all rows, pad rows included
+    anti = torch.eye(L, device=DEV).flip(0).bool()            # not of the form code_q >= code_k
+    bad = mo.additive_mask(anti[None].expand(B, L, L), BF)
+    with pytest.raises(ValueError):
+        holder.attn(x, attention_mask=bad, position_ids=pos)

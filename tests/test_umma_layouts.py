@@ -70,3 +70,19 @@ def test_mn_major_b_operand_is_v_as_stored(d, row_bytes, layout):
                          smem_desc(keys * row_bytes, 8 * row_bytes, layout), idesc(128, d, b_mn=1),
                          keys // 16, 32, 16 * row_bytes, d)
     assert torch.equal(out.cpu(), p.float() @ v.float())
+
+
+@pytest.mark.parametrize("d,row_bytes,layout", [(96, 64, 4), (64, 128, 2)])
+def test_a_operand_in_tensor_memory(d, row_bytes, layout):
+    """O = P V with P read from TMEM (lane = row, 32-bit column c = elements 2c | 2c+1 << 16) and V
+    MN-major from shared memory: the layout the attention kernel writes P in."""
+    from videogpt_b200 import ops
+    keys = 64
+    p, v = ints((128, keys), 7), ints((keys, d), 8)
+    words = p.contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
+    a_words = (words[:, 0::2] | (words[:, 1::2] << 16)).to(torch.int32).contiguous()
+    cw = row_bytes // 2
+    v_img = torch.cat([kmajor_image(v[:, c * cw:(c + 1) * cw].contiguous(), row_bytes) for c in range(d // cw)])
+    out = ops.umma_probe_ts(a_words.to(DEV), v_img.to(DEV), smem_desc(keys * row_bytes, 8 * row_bytes, layout),
+                            idesc(128, d, b_mn=1), keys // 16, 16 * row_bytes, d)
+    assert torch.equal(out.cpu(), p.float() @ v.float())

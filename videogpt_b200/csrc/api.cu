@@ -91,4 +91,11 @@ int vgpt_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int
                           a_step_bytes, b_step_bytes, d_out, n_cols, S(stream));
 }
 
+int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes,
+                             uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t b_step_bytes,
+                             float* d_out, int n_cols, void* stream) {
+  return vgpt::umma_probe_ts(a_words, a_cols, b_img, b_bytes, b_desc_base, idesc, k_steps, b_step_bytes,
+                             d_out, n_cols, S(stream));
+}
+
 }  // extern "C"

@@ -9,7 +9,8 @@
 //   * S = Q K^T is a tcgen05.mma (M=128, N=128) into TMEM, double buffered so the tensor core
 //     computes S(j+1) while the softmax warps work on S(j).
 //   * Softmax: 8 warps, two threads per query row (TMEM lane == row, 64 key columns each),
-//     exp2 domain, code predicate only on boundary tiles.  P is written to shared memory as a bf16 K-major SW128 A operand.
+//     exp2 domain, code predicate only on boundary tiles.  P is written back to TENSOR MEMORY
+//     (bf16 pairs, double buffered) and consumed from there as the A operand of O += P V.
 //   * O += P V is a tcgen05.mma with V consumed exactly as it lies in the cache ([key][d] =
 //     MN-major B operand), accumulating in TMEM; when a row maximum grows, the owning thread
 //     rescales its O row in TMEM (tcgen05.ld / st) before the next P V is issued.
@@ -38,22 +39,10 @@ struct TcCfg {
   static constexpr int kChunks = D / kCW;
   static constexpr int kChunkBytes = 128 * kRowBytes;         // 128 rows per chunk
   static constexpr int kTileBytes = kChunks * kChunkBytes;    // Q, K or V tile = 128 * D * 2
-  static constexpr int kPBytes = 2 * 128 * 128;               // P: two SW128 chunks of 64 keys
-  static constexpr int kStages = (D == 128) ? 2 : 3;          // K/V ring depth (smem budget)
-  static constexpr int kSmem = kTileBytes * (1 + 2 * kStages) + kPBytes + 256 + 1024;
+  static constexpr int kStages = (D == 128) ? 2 : 4;          // K/V ring depth (smem budget)
+  static constexpr int kSmem = kTileBytes * (1 + 2 * kStages) + 256 + 1024;
 };
 
-__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -76,10 +65,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void tmem_st_wait() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
 template <int D>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -98,9 +83,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t s_q = base;
   const uint32_t s_kv = s_q + C::kTileBytes;                  // stage s: K at s_kv + 2*s*tile, V right after
-  const uint32_t s_p = s_kv + 2 * kTcStages * C::kTileBytes;
-  uint8_t* p_gen = gen + (s_p - base);
-  const uint32_t bars = s_p + C::kPBytes;
+  const uint32_t bars = s_kv + 2 * kTcStages * C::kTileBytes;
   const uint32_t bar_q = bars;                                 // Q landed
   auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + kTcStages + s); };
@@ -139,7 +122,9 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tmem_s0 = tmem, tmem_o = tmem + 256;          // S[0]: cols 0..127, S[1]: 128..255, O: 256..
+  // TMEM columns: S[0] 0..127, S[1] 128..255, O 256..(256+D), P[0] 384..447, P[1] 448..511
+  // (P = bf16 probabilities, two per 32-bit column: the A operand of O += P V)
+  const uint32_t tmem_s0 = tmem, tmem_o = tmem + 256, tmem_p0 = tmem + 384;
   const int q_min = s_qmin, q_max = s_qmax;
 
   const int n_kt = (sq.kv_len + kTcBN - 1) / kTcBN;
@@ -213,12 +198,11 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint32_t sv = s_kv + 2 * stage_o * C::kTileBytes + C::kTileBytes;
 #pragma unroll
         for (int ks = 0; ks < kTcBN / 16; ++ks) {
-          const uint64_t da = make_smem_desc(s_p + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, kLayoutSW128);
           const uint64_t db = make_smem_desc(sv + ks * 16 * C::kRowBytes, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);
-          umma_f16_ss(tmem_o, da, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          umma_f16_ts(tmem_o, tmem_p0 + (j & 1) * 64 + ks * 8, db, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(bar_kv_empty(stage_o));        // K(j), V(j) no longer needed
-        umma_commit(bar_o_full);                   // O includes tile j; P buffer reusable
+        umma_commit(bar_o_full);                   // O includes tile j; P[j&1] reusable
         if (++stage_o == kTcStages) stage_o = 0;
         if (kt_s < n_kt) {                         // S(j+2) into the buffer softmax(j) just released
           mbar_wait(bar_kv_full(stage_s), phase_s);
@@ -272,7 +256,20 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float m_new = fmaxf(m_run, fmaxf(mx, s_rowmax[j & 1][half ^ 1][row]));
       const float sub = (m_new == -INFINITY) ? 0.f : m_new * scale_log2;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * scale_log2 - sub);
-      // O(j-1) must be complete before it is rescaled and before P is overwritten
+      // P half-row -> TMEM buffer j&1 (last read by P V of tile j-2, whose completion every thread
+      // observed in iteration j-1), overlapping the P V of tile j-1 on the tensor pipe
+      float sum = 0.f;
+      uint32_t w[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), scale_log2, -sub));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), scale_log2, -sub));
+        sum += p0 + p1;
+        w[i] = pack_bf16x2(p0, p1);
+      }
+      tmem_st_32x32b_x32(tmem_p0 + lane_addr + (j & 1) * 64 + half * 32, w);
+      l_run = l_run * alpha + sum;
+      // O(j-1) must be complete before it is rescaled (and before P V(j) may be issued)
       if (j > 0) {
         mbar_wait(bar_o_full, (j - 1) & 1);
         tc_fence_after();
@@ -286,28 +283,10 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_32x32b_x16(o_addr + u * 16, o);
           }
-          tmem_st_wait();
         }
       }
       m_run = m_new;
-      float sum = 0.f;
-      // P half-row -> smem, K-major SW128 chunk `half` (64 keys = 128 B per row), 16-byte units
-      // XOR (row & 7)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        uint32_t w[4];
-#pragma unroll
-        for (int h2 = 0; h2 < 4; ++h2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[u * 8 + h2 * 2]), scale_log2, -sub));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[u * 8 + h2 * 2 + 1]), scale_log2, -sub));
-          sum += p0 + p1;
-          w[h2] = pack_bf16x2(p0, p1);
-        }
-        *reinterpret_cast<uint4*>(p_gen + half * 16384 + row * 128 + ((u ^ (row & 7)) << 4)) =
-            make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      l_run = l_run * alpha + sum;
-      fence_proxy_async_smem();                   // generic-proxy P writes -> async proxy (UMMA)
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_p_full);
     }

@@ -59,6 +59,77 @@ umma_probe_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* __r
   }
 }
 
+// Same probe with the A operand in tensor memory: a_words[128][k_steps * 8] are the packed bf16x2
+// words of each row (thread r stores row r with tcgen05.st), B from a raw smem image.
+__global__ void __launch_bounds__(128, 1)
+umma_probe_ts_kernel(const uint32_t* __restrict__ a_words, int a_cols, const uint4* __restrict__ b_img,
+                     int b_bytes, uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t b_step_bytes,
+                     float* __restrict__ d_out, int n_cols) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(gen)[i] = b_img[i];
+  fence_proxy_async_smem();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_a = tmem + 256;
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < a_cols; c += 32) {
+    uint32_t v[32];
+    for (int j = 0; j < 32; ++j) v[j] = (c + j < a_cols) ? a_words[(size_t)row * a_cols + c + j] : 0u;
+    tmem_st_32x32b_x32(tmem_a + ((uint32_t)(warp * 32) << 16) + c, v);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < k_steps; ++k) {
+      const uint64_t db = b_desc_base + (uint64_t)(((base + k * b_step_bytes) >> 4) & 0x3fffu);
+      umma_f16_ts(tmem, tmem_a + k * 8, db, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  for (int c = 0; c < n_cols; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32 && c + j < n_cols; ++j) d_out[(size_t)row * n_cols + c + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+int umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes, uint64_t b_desc_base,
+                  uint32_t idesc, int k_steps, uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s) {
+  VGPT_CHECK_ARG(a_words && b_img && d_out, "vgpt_debug_umma_probe_ts: null pointer");
+  VGPT_CHECK_ARG(a_cols > 0 && a_cols <= 128 && b_bytes > 0 && b_bytes % 16 == 0 && b_bytes <= 96 * 1024 &&
+                     n_cols > 0 && n_cols <= 256 && k_steps > 0 && k_steps * 8 <= a_cols,
+                 "vgpt_debug_umma_probe_ts: bad sizes");
+  const int smem = ((b_bytes + 1023) & ~1023) + 1024;
+  VGPT_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_probe_ts_kernel<<<1, 128, smem, s>>>((const uint32_t*)a_words, a_cols, (const uint4*)b_img, b_bytes,
+                                            b_desc_base, idesc, k_steps, b_step_bytes, d_out, n_cols);
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
 int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t a_desc_base,
                uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t a_step_bytes,
                uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s) {

@@ -212,3 +212,13 @@ def umma_probe(a_img, b_img, a_desc_base: int, b_desc_base: int, idesc: int, k_s
               ctypes.c_uint64(a_desc_base), ctypes.c_uint64(b_desc_base), ctypes.c_uint32(idesc), k_steps,
               ctypes.c_uint32(a_step_bytes), ctypes.c_uint32(b_step_bytes), _p(out), n_cols, _stream())
     return out
+
+
+def umma_probe_ts(a_words, b_img, b_desc_base: int, idesc: int, k_steps: int, b_step_bytes: int, n_cols: int):
+    """Test hook: A operand in tensor memory.  a_words: int32 CUDA tensor [128, cols] (packed bf16x2)."""
+    assert a_words.is_cuda and a_words.dtype == torch.int32 and a_words.shape[0] == 128 and a_words.is_contiguous()
+    out = torch.zeros(128, n_cols, device=a_words.device, dtype=F32)
+    _lib.call("vgpt_debug_umma_probe_ts", _p(a_words), a_words.shape[1], _p(b_img), b_img.numel(),
+              ctypes.c_uint64(b_desc_base), ctypes.c_uint32(idesc), k_steps, ctypes.c_uint32(b_step_bytes), _p(out),
+              n_cols, _stream())
+    return out
