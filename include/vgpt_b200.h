@@ -65,6 +65,14 @@ int vgpt_rope_table(const float* inv_freq, void* table, int max_pos, int head_di
 int vgpt_rope_kv_append(void* qkv, const int32_t* row_pos, const int32_t* row_slot, const void* table,
                         void* k_pool, void* v_pool, int rows, int H, int D, void* stream);
 
+/* Sequence-parallel form of vgpt_rope_kv_append: the post-RoPE k / v rows are stored into n_pools
+ * pools (this rank's and every peer's, mapped with vgpt_peer_import) -- the K/V all-gather of the
+ * sequence-parallel path fused into the producing kernel as NVLink stores.  Replaces the four
+ * Ulysses all-to-alls per layer of LVM/transform/sdpa_transform.py:126-156.  n_pools <= 8. */
+int vgpt_rope_kv_append_peers(void* qkv, const int32_t* row_pos, const int32_t* row_slot, const void* table,
+                              void* const* k_pools, void* const* v_pools, int n_pools, int rows, int H,
+                              int D, void* stream);
+
 /* Clip-block-causal flash attention over the paged KV pools (tcgen05 + TMEM + TMA); replaces
  * F.scaled_dot_product_attention with the dense additive mask (sdpa_transform.py:152-166,
  * OmniGen/transformer.py:128-145).  allowed(q,k) <=> q_code[q] >= k_code[k]; k_code is
@@ -109,6 +117,33 @@ int vgpt_linear_small(const void* in, const void* W, const void* bias, void* out
 int vgpt_final_layer(const void* hidden, int hidden_size, const int32_t* lat_row0, const void* mod,
                      const void* w, const void* bias, void* pred, int n_lat, int channels, int lat_h,
                      int lat_w, void* stream);
+
+/* Row-driven FinalLayer + unpatchify for row-sharded plans: local row r is an image token of
+ * latent row_a[r], patch row_b[r] when row_kind[r] == VGPT_ROW_NOISY_PATCH (other rows are
+ * skipped); the 16 outputs per row are stored into every destination preds[0..n_preds) (own +
+ * peers), replacing the hidden-state all-gather of LVM/model.py:466-474. */
+int vgpt_final_layer_rows(const void* hidden, int rows, int hidden_size, const int32_t* row_kind,
+                          const int32_t* row_a, const int32_t* row_b, const void* mod, const void* w,
+                          const void* bias, void* const* preds, int n_preds, int channels, int lat_h,
+                          int lat_w, void* stream);
+
+/* Peer memory for the sequence-parallel path (one process per GPU, NVLink/NVSwitch).  These five
+ * are resource management, not data path: vgpt_peer_alloc = zero-filled cudaMalloc (exportable),
+ * vgpt_peer_export writes the 64-byte CUDA IPC handle of an allocation, vgpt_peer_import maps a
+ * peer's allocation into this process (peer access enabled lazily), vgpt_peer_close / _free undo
+ * them.  The reference gets its process groups from torch.distributed / deepspeed
+ * (LVM/acceleration/parallel_states.py:25-60). */
+int vgpt_peer_alloc(void** out, uint64_t bytes);
+int vgpt_peer_free(void* p);
+int vgpt_peer_export(void* p, void* handle64);
+int vgpt_peer_import(const void* handle64, void** out);
+int vgpt_peer_close(void* p);
+
+/* Barrier over n_ranks GPUs through peer-mapped flag words: flag_ptrs[j] -> rank j's uint32[n_ranks]
+ * (flag_ptrs[rank] is local); state = local uint32[2] {epoch, timed_out}.  Enqueued like any other
+ * kernel (graph capturable); every rank must enqueue the same sequence of barriers.  A peer that
+ * never arrives sets state[1] after ~20 s instead of hanging the GPU. */
+int vgpt_peer_barrier(void* const* flag_ptrs, int n_ranks, int rank, uint32_t* state, void* stream);
 
 /* x1 -> velocity, CFG and the Euler update (LVM/scheduler.py:178-204, LVM/model.py:554-562) on
  * z/pred laid out [cond latents | uncond latents] (half_numel elements each; one half if

@@ -1,0 +1,182 @@
+"""Sequence parallelism (sequence axis; reference: LVM/model.py:459-474 chunking +
+LVM/transform/sdpa_transform.py:126-156 Ulysses all-to-alls).
+
+Here a rank owns a contiguous chunk of the rows of every sequence and stores its K/V rows and its
+predictions into every peer (videogpt_b200/peer.py); every row-wise op is independent of the
+partition, so a sharded run must reproduce the single-GPU run BIT FOR BIT:
+
+* CPU: the union of the ranks' row arrays is exactly the unsharded plan (any world size);
+* 1 GPU: ``world`` virtual ranks (LocalPeerGroup, lockstep) == the unsharded engine, bit-exact,
+  through the real kernels (vgpt_rope_kv_append_peers, vgpt_final_layer_rows);
+* 2 GPUs: LVM + LVMScheduler under ``initialize_sequence_parallel_state(2)`` (real IPC peer
+  memory + the barrier kernel, CUDA graphs on) == the single-GPU run, bit-exact.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import processor_oracle as po
+from videogpt_b200 import engine as eng, synth
+
+
+def _specs(n_ctx, n_gen, H, W):
+    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+    specs, n_lat, n_ctx_lat = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
+                                                   d["denoise_image_sizes"], d["time_emb_inx"])
+    return d, specs, n_lat, n_ctx_lat
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("geom", [(4, 4, 256, 256), (3, 2, 64, 96), (1, 1, 64, 64)])
+def test_sharded_plans_partition_the_unsharded_plan(world, geom):
+    n_ctx, n_gen, H, W = geom
+    _, specs, n_lat, n_ctx_lat = _specs(n_ctx, n_gen, H, W)
+    full = eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu")
+    parts = [eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu", shard=(r, world)) for r in range(world)]
+    for p in parts:      # global structures are replicated
+        assert torch.equal(p.page_table, full.page_table) and torch.equal(p.k_code, full.k_code)
+        assert torch.equal(p.k_tile_minmax, full.k_tile_minmax) and p.total_pages == full.total_pages
+    for which in ("prefix", "step"):
+        f = getattr(full, which)
+        ph = [getattr(p, which) for p in parts]
+        assert sum(x.rows for x in ph) == f.rows
+        for name in ("row_pos", "row_slot", "q_code", "kind", "arg_a", "arg_b"):
+            # rows of sequence s on rank r, re-assembled sequence-major, must equal the full plan
+            pieces = []
+            for s in range(len(specs)):
+                for x in ph:
+                    q0, n = int(x.seqs[s, 0]), int(x.seqs[s, 1])
+                    pieces.append(getattr(x, name)[q0:q0 + n])
+            assert torch.equal(torch.cat(pieces), getattr(f, name)), (which, name)
+        for s in range(len(specs)):
+            sizes = [int(x.seqs[s, 1]) for x in ph]
+            assert max(sizes) - min(sizes) <= 1                      # balanced
+            assert all(int(x.seqs[s, 2]) == int(f.seqs[s, 2]) for x in ph)   # every rank sees all keys
+
+
+def test_shard_rows_covers_range():
+    for lo, hi, w in ((0, 1032, 8), (1032, 2064, 3), (5, 7, 4), (0, 0, 2)):
+        chunks = [eng.shard_rows(lo, hi, r, w) for r in range(w)]
+        assert chunks[0][0] == lo and chunks[-1][1] == hi
+        assert all(chunks[i][1] == chunks[i + 1][0] for i in range(w - 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# 1 GPU: virtual ranks in lockstep
+# ------------------------------------------------------------------------------------------------
+def _engine(w, dims, dev, peers=None):
+    return eng.NextClipEngine(w, dims.hidden_size, dims.intermediate_size, dims.num_hidden_layers,
+                              dims.num_attention_heads, dims.rms_norm_eps, dims.rope_theta, dev,
+                              dims.pos_embed_max_size, 2, use_cuda_graph=False, peers=peers)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,geom", [(2, (3, 2, 64, 96)), (3, (2, 2, 64, 64)), (4, (4, 4, 128, 128))])
+def test_virtual_ranks_match_unsharded_engine_bit_exact(world, geom):
+    from videogpt_b200 import ops, peer
+    dev, bf = torch.device("cuda", 0), torch.bfloat16
+    n_ctx, n_gen, H, W = geom
+    dims = synth.REDUCED
+    sd = synth.init_state_dict(dims, seed=0)
+    w = eng.EngineWeights(sd, dims.num_hidden_layers, dev)
+    _, specs, n_lat, n_ctx_lat = _specs(n_ctx, n_gen, H, W)
+    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)
+    ctx = torch.cat(lat[:n_ctx], 0).to(dev, bf)
+    z0 = torch.cat(lat[n_ctx:] * 2, 0).to(dev, bf)
+
+    ref = _engine(w, dims, dev)
+    ref.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev))
+    ref.prefill(ctx)
+    members = peer.LocalPeerGroup.create(world, dev)
+    ranks = [_engine(w, dims, dev, peers=m) for m in members]
+    for r, e in enumerate(ranks):
+        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev, shard=(r, world)))
+    eng.run_lockstep([e.prefill_steps(ctx) for e in ranks])
+    torch.cuda.synchronize()
+    for e in ranks:                                   # every rank ends up with ALL context K/V
+        assert torch.equal(e.kv, ref.kv)
+    ref.z.copy_(z0)
+    for e in ranks:
+        e.z.copy_(z0)
+    for step, t in enumerate((0.0, 0.3, 0.7)):
+        for e in [ref] + ranks:
+            e.t.fill_(t)
+        ref.predict()
+        eng.run_lockstep([e.predict_steps() for e in ranks])
+        torch.cuda.synchronize()
+        for e in ranks:
+            assert torch.equal(e.pred, ref.pred), f"step {step}: prediction differs"
+            assert torch.equal(e.kv, ref.kv)
+        for e in [ref] + ranks:
+            ops.cfg_euler(e.z, e.pred, True, True, 1.0 - t, 0.3, 1.5)
+    assert all(torch.equal(e.z, ref.z) for e in ranks)
+
+
+# ------------------------------------------------------------------------------------------------
+# 2 GPUs: real peer memory
+# ------------------------------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from transformers import Phi3Config
+    from videogpt_b200 import LVM, LVMScheduler, parallel_states as ps
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        dims = synth.REDUCED
+        sd = synth.init_state_dict(dims, seed=0)
+
+        def model():
+            m = LVM(Phi3Config(**dims.phi3_kwargs()), device=dev)
+            m.load_state_dict(sd)
+            return m.to(torch.bfloat16).eval()
+
+        n_ctx, n_gen, H, W, steps = 3, 2, 64, 96, 4
+        d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+        lat = [x.to(dev, torch.bfloat16) for x in synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)]
+        mk = dict(input_ids=d["input_ids"].to(dev), input_img_latents=lat[:n_ctx],
+                  input_image_sizes=d["input_image_sizes"], attention_mask=None, position_ids=d["position_ids"].to(dev),
+                  denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
+                  use_img_cfg=True, use_kv_cache=False, offload_model=False, vae=None)
+        single_model = model()
+        single = {pt: LVMScheduler(steps)([x.clone() for x in lat[n_ctx:]] * 2, single_model.frame_block_forward_with_cfg,
+                                          mk, prediction_type=pt) for pt in ("x1", "v")}
+        ps.initialize_sequence_parallel_state(world)          # the reference's SP switch
+        sp_model = model()
+        out = {}
+        for pt in ("x1", "v"):
+            for rep in range(2):                               # second clip reuses plan + captured graph
+                got = LVMScheduler(steps)([x.clone() for x in lat[n_ctx:]] * 2, sp_model.frame_block_forward_with_cfg,
+                                          mk, prediction_type=pt)
+                torch.cuda.synchronize()
+                out[f"{pt}{rep}"] = all(torch.equal(a, b) for a, b in zip(got, single[pt]))
+        sp_model.engine().peers.check()
+        out["sharded"] = sp_model.engine().plan.shard == (rank, world)
+        ret[rank] = out
+        dist.barrier()
+        sp_model.engine().peers.close()
+    finally:
+        ps.destroy_sequence_parallel_group()
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sequence_parallel_two_gpus_matches_single_gpu():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    want = {"x10": True, "x11": True, "v0": True, "v1": True, "sharded": True}
+    assert dict(ret) == {0: want, 1: want}

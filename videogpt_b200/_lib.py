@@ -22,6 +22,14 @@ SIGNATURES = {
     "vgpt_rmsnorm": [P, P, P, I, I, F, P],
     "vgpt_rope_table": [P, P, I, I, P],
     "vgpt_rope_kv_append": [P, P, P, P, P, P, I, I, I, P],
+    "vgpt_rope_kv_append_peers": [P, P, P, P, P, P, I, I, I, I, P],
+    "vgpt_final_layer_rows": [P, I, I, P, P, P, P, P, P, P, I, I, I, I, P],
+    "vgpt_peer_alloc": [P, c_uint64],
+    "vgpt_peer_free": [P],
+    "vgpt_peer_export": [P, P],
+    "vgpt_peer_import": [P, P],
+    "vgpt_peer_close": [P],
+    "vgpt_peer_barrier": [P, I, I, P, P],
     "vgpt_attn_clip_causal": [P, I, I, P, I, P, P, I, P, I, P, I, I, P, P, P, I, I, I, F, P],
     "vgpt_attn_clip_causal_mma_sync": [P, I, I, P, I, P, P, I, P, I, P, I, I, P, P, P, I, I, I, F, P],
     "vgpt_embed_assemble": [P, I, I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, P],

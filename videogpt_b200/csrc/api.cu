@@ -25,8 +25,31 @@ int vgpt_rope_table(const float* inv_freq, void* table, int max_pos, int head_di
 }
 int vgpt_rope_kv_append(void* qkv, const int32_t* row_pos, const int32_t* row_slot, const void* table,
                         void* k_pool, void* v_pool, int rows, int H, int D, void* stream) {
-  return vgpt::rope_kv_append(qkv, row_pos, row_slot, table, k_pool, v_pool, rows, H, D,
+  void* kp[1] = {k_pool};
+  void* vp[1] = {v_pool};
+  return vgpt::rope_kv_append(qkv, row_pos, row_slot, table, kp, vp, 1, rows, H, D, VGPT_PAGE_TOKENS,
+                              S(stream));
+}
+int vgpt_rope_kv_append_peers(void* qkv, const int32_t* row_pos, const int32_t* row_slot, const void* table,
+                              void* const* k_pools, void* const* v_pools, int n_pools, int rows, int H,
+                              int D, void* stream) {
+  return vgpt::rope_kv_append(qkv, row_pos, row_slot, table, k_pools, v_pools, n_pools, rows, H, D,
                               VGPT_PAGE_TOKENS, S(stream));
+}
+int vgpt_final_layer_rows(const void* hidden, int rows, int hidden_size, const int32_t* row_kind,
+                          const int32_t* row_a, const int32_t* row_b, const void* mod, const void* w,
+                          const void* bias, void* const* preds, int n_preds, int channels, int lat_h,
+                          int lat_w, void* stream) {
+  return vgpt::final_layer_rows(hidden, rows, hidden_size, row_kind, row_a, row_b, mod, w, bias, preds,
+                                n_preds, channels, lat_h, lat_w, S(stream));
+}
+int vgpt_peer_alloc(void** out, uint64_t bytes) { return vgpt::peer_alloc(out, bytes); }
+int vgpt_peer_free(void* p) { return vgpt::peer_free(p); }
+int vgpt_peer_export(void* p, void* handle64) { return vgpt::peer_export(p, handle64); }
+int vgpt_peer_import(const void* handle64, void** out) { return vgpt::peer_import(handle64, out); }
+int vgpt_peer_close(void* p) { return vgpt::peer_close(p); }
+int vgpt_peer_barrier(void* const* flag_ptrs, int n_ranks, int rank, uint32_t* state, void* stream) {
+  return vgpt::peer_barrier(flag_ptrs, n_ranks, rank, state, S(stream));
 }
 int vgpt_attn_clip_causal(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                           const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,

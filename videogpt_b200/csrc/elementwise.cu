@@ -123,8 +123,7 @@ int rope_table(const float* inv_freq, void* tab, int max_pos, int head_dim, cuda
 __global__ void __launch_bounds__(192)
 rope_kv_append_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ row_pos,
                       const int32_t* __restrict__ row_slot, const __nv_bfloat16* __restrict__ tab,
-                      __nv_bfloat16* __restrict__ k_pool, __nv_bfloat16* __restrict__ v_pool, int H,
-                      int D, int page_tokens) {
+                      PeerPtrs k_pools, PeerPtrs v_pools, int n_pools, int H, int D, int page_tokens) {
   const int row = blockIdx.x;
   const int half = D >> 1, hc = half >> 3;           // 16-byte chunks per half head
   const int HD = H * D;
@@ -157,32 +156,43 @@ rope_kv_append_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict
       *reinterpret_cast<uint4*>(p) = vlo;
       *reinterpret_cast<uint4*>(p + half) = vhi;
     } else if (slot >= 0) {
-      __nv_bfloat16* d = k_pool + pool_off + (size_t)h * page_tokens * D + c * 8;
-      *reinterpret_cast<uint4*>(d) = vlo;
-      *reinterpret_cast<uint4*>(d + half) = vhi;
+      const size_t o = pool_off + (size_t)h * page_tokens * D + c * 8;
+      for (int g = 0; g < n_pools; ++g) {            // own pool + every peer's (NVLink stores)
+        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(k_pools.p[g]) + o;
+        *reinterpret_cast<uint4*>(d) = vlo;
+        *reinterpret_cast<uint4*>(d + half) = vhi;
+      }
     }
   }
   if (slot >= 0) {
     const int dc = D >> 3;
     for (int it = threadIdx.x; it < H * dc; it += blockDim.x) {
       const int h = it / dc, c = it % dc;
-      *reinterpret_cast<uint4*>(v_pool + pool_off + (size_t)h * page_tokens * D + c * 8) =
-          *reinterpret_cast<const uint4*>(base + 2 * HD + h * D + c * 8);
+      const uint4 v = *reinterpret_cast<const uint4*>(base + 2 * HD + h * D + c * 8);
+      const size_t o = pool_off + (size_t)h * page_tokens * D + c * 8;
+      for (int g = 0; g < n_pools; ++g)
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(v_pools.p[g]) + o) = v;
     }
   }
 }
 
 int rope_kv_append(void* qkv, const int32_t* row_pos, const int32_t* row_slot, const void* tab,
-                   void* k_pool, void* v_pool, int rows, int H, int D, int page_tokens,
-                   cudaStream_t s) {
-  VGPT_CHECK_ARG(qkv && row_pos && row_slot && tab && k_pool && v_pool,
+                   void* const* k_pools, void* const* v_pools, int n_pools, int rows, int H, int D,
+                   int page_tokens, cudaStream_t s) {
+  VGPT_CHECK_ARG(qkv && row_pos && row_slot && tab && k_pools && v_pools,
                  "vgpt_rope_kv_append: null pointer");
+  VGPT_CHECK_ARG(n_pools >= 1 && n_pools <= kMaxPeers, "vgpt_rope_kv_append: %d pools (1..%d)", n_pools, kMaxPeers);
   VGPT_CHECK_ARG(H > 0 && D > 0 && D % 16 == 0 && page_tokens > 0,
                  "vgpt_rope_kv_append: unsupported H=%d D=%d page_tokens=%d", H, D, page_tokens);
+  PeerPtrs kp, vp;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    kp.p[i] = i < n_pools ? k_pools[i] : nullptr;
+    vp.p[i] = i < n_pools ? v_pools[i] : nullptr;
+    VGPT_CHECK_ARG(i >= n_pools || (kp.p[i] && vp.p[i]), "vgpt_rope_kv_append: null pool pointer %d", i);
+  }
   if (rows <= 0) return 0;
   rope_kv_append_kernel<<<rows, 192, 0, s>>>((__nv_bfloat16*)qkv, row_pos, row_slot,
-                                             (const __nv_bfloat16*)tab, (__nv_bfloat16*)k_pool,
-                                             (__nv_bfloat16*)v_pool, H, D, page_tokens);
+                                             (const __nv_bfloat16*)tab, kp, vp, n_pools, H, D, page_tokens);
   VGPT_CHECK_LAUNCH();
   return 0;
 }
@@ -371,14 +381,22 @@ int linear_small(const void* in, const void* W, const void* bias, void* out, int
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRowThreads)
 final_layer_kernel(const __nv_bfloat16* __restrict__ hidden, int hs,
-                   const int32_t* __restrict__ lat_row0, const __nv_bfloat16* __restrict__ mod,
-                   const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
-                   __nv_bfloat16* __restrict__ pred, int tokens_per_lat, int C, int lat_h,
-                   int lat_w) {
+                   const int32_t* __restrict__ lat_row0, const int32_t* __restrict__ row_kind,
+                   const int32_t* __restrict__ row_a, const int32_t* __restrict__ row_b,
+                   const __nv_bfloat16* __restrict__ mod, const __nv_bfloat16* __restrict__ w,
+                   const __nv_bfloat16* __restrict__ bias, PeerPtrs preds, int n_preds,
+                   int tokens_per_lat, int C, int lat_h, int lat_w) {
   __shared__ float red[32];
   __shared__ float outs[16][kRowThreads / 32];
-  const int j = blockIdx.x / tokens_per_lat, tkn = blockIdx.x % tokens_per_lat;
-  const int row = lat_row0[j] + tkn;
+  int j, tkn, row;
+  if (lat_row0) {                    // latent-driven: CTA = (latent, token), rows contiguous per latent
+    j = blockIdx.x / tokens_per_lat; tkn = blockIdx.x % tokens_per_lat;
+    row = lat_row0[j] + tkn;
+  } else {                           // row-driven (any row partition): CTA = row, image-token rows only
+    row = blockIdx.x;
+    if (row_kind[row] != 2 /* VGPT_ROW_NOISY_PATCH */) return;
+    j = row_a[row]; tkn = row_b[row];
+  }
   const int chunks = hs >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(hidden + (size_t)row * hs);
   float xv[kMaxChunksPerThread][8];
@@ -446,7 +464,9 @@ final_layer_kernel(const __nv_bfloat16* __restrict__ hidden, int hs,
     const int pw = lat_w >> 1;
     const int py = tkn / pw, px = tkn % pw;
     const int p = f / (2 * C), q = (f / C) & 1, c = f % C;     // feature order (p, q, c)
-    pred[(((size_t)j * C + c) * lat_h + 2 * py + p) * lat_w + 2 * px + q] = __float2bfloat16_rn(v);
+    const size_t o = (((size_t)j * C + c) * lat_h + 2 * py + p) * lat_w + 2 * px + q;
+    const __nv_bfloat16 r = __float2bfloat16_rn(v);
+    for (int g = 0; g < n_preds; ++g) static_cast<__nv_bfloat16*>(preds.p[g])[o] = r;
   }
 }
 
@@ -459,9 +479,35 @@ int final_layer(const void* hidden, int hs, const int32_t* lat_row0, const void*
                  "vgpt_final_layer: unsupported hs=%d C=%d latent %dx%d", hs, C, lat_h, lat_w);
   if (n_lat <= 0) return 0;
   const int tokens = (lat_h / 2) * (lat_w / 2);
+  PeerPtrs pp = {};
+  pp.p[0] = pred;
   final_layer_kernel<<<n_lat * tokens, kRowThreads, 0, s>>>(
-      (const __nv_bfloat16*)hidden, hs, lat_row0, (const __nv_bfloat16*)mod,
-      (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (__nv_bfloat16*)pred, tokens, C, lat_h,
+      (const __nv_bfloat16*)hidden, hs, lat_row0, nullptr, nullptr, nullptr, (const __nv_bfloat16*)mod,
+      (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, pp, 1, tokens, C, lat_h, lat_w);
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
+// Row-driven variant for row-sharded (sequence-parallel) plans: `rows` local rows described by the
+// plan's (kind, a = latent, b = token) arrays; the prediction is stored into every rank's pred
+// buffer (preds[0..n_preds), NVLink stores), so no gather follows.
+int final_layer_rows(const void* hidden, int rows, int hs, const int32_t* kind, const int32_t* a,
+                     const int32_t* b, const void* mod, const void* w, const void* bias, void* const* preds,
+                     int n_preds, int C, int lat_h, int lat_w, cudaStream_t s) {
+  VGPT_CHECK_ARG(hidden && kind && a && b && mod && w && bias && preds, "vgpt_final_layer_rows: null pointer");
+  VGPT_CHECK_ARG(n_preds >= 1 && n_preds <= kMaxPeers, "vgpt_final_layer_rows: %d destinations (1..%d)", n_preds, kMaxPeers);
+  VGPT_CHECK_ARG(hs % 8 == 0 && hs <= kRowThreads * kMaxChunksPerThread * 8 && C == 4 &&
+                     lat_h % 2 == 0 && lat_w % 2 == 0,
+                 "vgpt_final_layer_rows: unsupported hs=%d C=%d latent %dx%d", hs, C, lat_h, lat_w);
+  PeerPtrs pp;
+  for (int i = 0; i < kMaxPeers; ++i) {
+    pp.p[i] = i < n_preds ? preds[i] : nullptr;
+    VGPT_CHECK_ARG(i >= n_preds || pp.p[i], "vgpt_final_layer_rows: null destination %d", i);
+  }
+  if (rows <= 0) return 0;
+  final_layer_kernel<<<rows, kRowThreads, 0, s>>>(
+      (const __nv_bfloat16*)hidden, hs, nullptr, kind, a, b, (const __nv_bfloat16*)mod,
+      (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, pp, n_preds, (lat_h / 2) * (lat_w / 2), C, lat_h,
       lat_w);
   VGPT_CHECK_LAUNCH();
   return 0;

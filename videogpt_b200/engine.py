@@ -109,6 +109,7 @@ class ClipPlan:
     step: PhaseArrays
     lat_row0: torch.Tensor
     max_pos: int
+    shard: Optional[tuple] = None      # (rank, world) of a row-sharded (sequence-parallel) plan
 
 
 def frame_block_specs(input_ids, position_ids, input_image_sizes, denoise_image_sizes, time_emb_inx):
@@ -225,9 +226,27 @@ def codes_dense_mask(spec_codes: np.ndarray, pad: int) -> np.ndarray:
     return qc[:, None] >= kc[None, :]
 
 
+def shard_rows(lo: int, hi: int, rank: int, world: int):
+    """Rows [lo, hi) dealt to ``world`` ranks as contiguous chunks (sizes differ by at most one),
+    like the reference's ``input_emb[:, r*L/P:(r+1)*L/P]`` (``LVM/model.py:459-464``) but without
+    its divisibility requirement: every row-wise op is independent of the partition and attention
+    sees all keys, so any partition gives the same numbers."""
+    n = hi - lo
+    a = lo + (n * rank) // world
+    b = lo + (n * (rank + 1)) // world
+    return a, b
+
+
 def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int, lat_h: int,
-               lat_w: int, device) -> ClipPlan:
+               lat_w: int, device, shard: Optional[tuple] = None) -> ClipPlan:
+    """``shard=(rank, world)``: row-sharded plan of one rank of a sequence-parallel group -- the
+    page table, key codes and tile classification describe the WHOLE sequences (every rank holds
+    all K/V), the per-phase row arrays only this rank's chunk of every sequence."""
     S = len(specs)
+    if shard is not None:
+        s_rank, s_world = shard
+        if not (0 <= s_rank < s_world):
+            raise ValueError(f"bad shard {shard}")
     for sp in specs:
         T = sp.n_prefix + sp.n_active
         assert all(len(a) == T for a in (sp.positions, sp.codes, sp.kinds, sp.arg_a, sp.arg_b))
@@ -260,12 +279,15 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
         row0, max_q = 0, 0
         for s, sp in enumerate(specs):
             lo, hi = (0, sp.n_prefix) if which == "prefix" else (sp.n_prefix, sp.n_prefix + sp.n_active)
+            kv_len = hi                        # every key up to the end of this phase's rows
+            if shard is not None:
+                lo, hi = shard_rows(lo, hi, s_rank, s_world)
             n = hi - lo
             logical = np.arange(lo, hi)
             pos.append(sp.positions[lo:hi])
             slot.append(page_table[s, logical // PAGE_TOKENS] * PAGE_TOKENS + logical % PAGE_TOKENS)
             qc.append(sp.codes[lo:hi]); kd.append(sp.kinds[lo:hi]); aa.append(sp.arg_a[lo:hi]); ab.append(sp.arg_b[lo:hi])
-            seqs.append([row0, n, hi, 0])      # kv_len = everything up to the end of these rows
+            seqs.append([row0, n, kv_len, 0])
             row0 += n
             max_q = max(max_q, n)
         cat = lambda xs: torch.from_numpy(np.concatenate(xs).astype(np.int32) if xs else np.zeros(0, np.int32)).to(device)
@@ -286,7 +308,7 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
                     k_code=torch.from_numpy(k_code).to(device),
                     k_tile_minmax=torch.from_numpy(minmax).to(device), total_pages=base,
                     prefix=prefix, step=step, lat_row0=torch.from_numpy(lat_row0).to(device),
-                    max_pos=max_pos)
+                    max_pos=max_pos, shard=shard)
 
 
 # --------------------------------------------------------------------------------------------
@@ -295,7 +317,10 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
 class NextClipEngine:
     def __init__(self, weights: EngineWeights, hidden_size: int, intermediate_size: int, num_layers: int,
                  num_heads: int, rms_eps: float, rope_theta: float, device, pos_embed_max_size: int = 192,
-                 patch_size: int = 2, use_cuda_graph: bool = True):
+                 patch_size: int = 2, use_cuda_graph: bool = True, peers=None):
+        """``peers``: a ``peer.PeerGroup`` (one process per GPU) or ``peer.LocalPeerGroup`` member
+        when this engine is one rank of a sequence-parallel group; plans must then be built with
+        ``shard=(peers.rank, peers.world)``."""
         if not torch.cuda.is_available():
             raise RuntimeError("videogpt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.w = weights
@@ -305,6 +330,8 @@ class NextClipEngine:
         self.device = torch.device(device)
         self.pos_max, self.patch = pos_embed_max_size, patch_size
         self.use_cuda_graph = use_cuda_graph
+        self.peers = peers
+        self._kv_shared = self._pred_shared = None
         self.plan: Optional[ClipPlan] = None
         self._graph = None
         self._rope_tab = None
@@ -324,10 +351,32 @@ class NextClipEngine:
         self.attn = torch.empty(rows, self.hs, device=dev, dtype=bf)
         self.mlp_h = torch.empty(rows, self.inter, device=dev, dtype=bf)
         # paged KV pools: [layer][k|v][page][H][128][D]
-        self.kv = torch.zeros(self.L, 2, plan.total_pages, self.H, PAGE_TOKENS, self.D, device=dev, dtype=bf)
         n = max(plan.n_latents, 1)
         self.z = torch.zeros(n, 4, plan.lat_h, plan.lat_w, device=dev, dtype=bf)
-        self.pred = torch.zeros_like(self.z)
+        kv_shape = (self.L, 2, plan.total_pages, self.H, PAGE_TOKENS, self.D)
+        if self.peers is None:
+            if plan.shard is not None:
+                raise ValueError("a row-sharded plan needs an engine with a peer group")
+            self.kv = torch.zeros(kv_shape, device=dev, dtype=bf)
+            self.pred = torch.zeros_like(self.z)
+            self._kv_ptrs = None
+        else:
+            # sequence parallel: pools and prediction live in peer-mapped memory; every rank holds
+            # ALL K/V (the producers store into every peer) and the full prediction
+            if plan.shard != (self.peers.rank, self.peers.world):
+                raise ValueError(f"plan shard {plan.shard} does not match the peer group "
+                                 f"({self.peers.rank}, {self.peers.world})")
+            kv_bytes, pred_bytes = 2 * math.prod(kv_shape), 2 * self.z.numel()
+            if self._kv_shared is None or self._kv_shared.local.numel() < kv_bytes:
+                self._kv_shared = self.peers.alloc(kv_bytes)
+            if self._pred_shared is None or self._pred_shared.local.numel() < pred_bytes:
+                self._pred_shared = self.peers.alloc(pred_bytes)
+            self.kv = self._kv_shared.local[:kv_bytes].view(bf).view(kv_shape)
+            self.pred = self._pred_shared.local[:pred_bytes].view(bf).view(self.z.shape)
+            pool_bytes = 2 * math.prod(kv_shape[2:])
+            self._kv_ptrs = [(self._kv_shared.ptr_array((2 * li) * pool_bytes),
+                              self._kv_shared.ptr_array((2 * li + 1) * pool_bytes)) for li in range(self.L)]
+            self._pred_ptrs = self._pred_shared.ptr_array()
         self.ctx = torch.zeros(max(plan.n_ctx_latents, 1), 4, plan.lat_h, plan.lat_w, device=dev, dtype=bf)
         self.t = torch.zeros(n, device=dev, dtype=torch.float32)
         self.t_sin = torch.empty(n, 256, device=dev, dtype=bf)
@@ -375,17 +424,28 @@ class NextClipEngine:
                            self.pos_rows)
 
     def _layers(self, ph: PhaseArrays, kv_only_last: bool):
-        """Phi3DecoderLayer x L (transformers 4.47.1) on the packed rows of one phase."""
+        """Phi3DecoderLayer x L (transformers 4.47.1) on the packed rows of one phase.  Generator:
+        yields at every point where, in a sequence-parallel group, the peers' stores must have
+        landed before the next kernel (once per layer, after the K/V append)."""
         n, plan = ph.rows, self.plan
         hidden, xn, qkv, attn, mlp_h = (self.hidden[:n], self.xn[:n], self.qkv[:n], self.attn[:n], self.mlp_h[:n])
         scale = 1.0 / math.sqrt(self.D)
         for li, lw in enumerate(self.w.layers):
-            ops.rmsnorm(hidden, lw["ln1"], self.eps, out=xn)
-            ops.gemm(xn, lw["qkv"], out=qkv)
-            ops.rope_kv_append(qkv, ph.row_pos, ph.row_slot, self._rope_tab, self.kv[li, 0], self.kv[li, 1],
-                               self.H, self.D)
+            if n:
+                ops.rmsnorm(hidden, lw["ln1"], self.eps, out=xn)
+                ops.gemm(xn, lw["qkv"], out=qkv)
+                if self.peers is None:
+                    ops.rope_kv_append(qkv, ph.row_pos, ph.row_slot, self._rope_tab, self.kv[li, 0], self.kv[li, 1],
+                                       self.H, self.D)
+                else:                 # RoPE + K/V append + all-gather: stores into every rank's pool
+                    ops.rope_kv_append_peers(qkv, ph.row_pos, ph.row_slot, self._rope_tab, self._kv_ptrs[li][0],
+                                             self._kv_ptrs[li][1], self.peers.world, self.H, self.D)
+            if self.peers is not None:
+                yield "kv"
             if kv_only_last and li == self.L - 1:
                 break                     # prefix rows: nothing after the last K/V append is read
+            if not n:
+                continue
             ops.attention(qkv[:, :self.hs], attn, self.kv[li, 0], self.kv[li, 1], plan.page_table, ph.seqs,
                           ph.max_q_rows, ph.q_code, plan.k_code, plan.k_tile_minmax, self.H, self.D, scale)
             ops.gemm(attn, lw["o"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
@@ -393,48 +453,97 @@ class NextClipEngine:
             ops.gemm(xn, lw["gate_up"], out=mlp_h, epilogue=ops.EPI_SWIGLU)
             ops.gemm(mlp_h, lw["down"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
 
-    def prefill(self, ctx_latents: Optional[torch.Tensor] = None):
-        """Compute and cache K/V of every prefix (context) row.  ``ctx_latents``: [n_ctx, 4, h, w]."""
+    def _drive(self, gen):
+        """Run a kernel-sequence generator; at its sync points enqueue the cross-GPU barrier."""
+        for _ in gen:
+            self.peers.barrier()
+
+    def prefill_steps(self, ctx_latents: Optional[torch.Tensor] = None):
+        """Generator form of ``prefill`` (``run_lockstep`` interleaves the virtual ranks of a
+        ``LocalPeerGroup`` with it)."""
         plan = self.plan
         if ctx_latents is not None and plan.n_ctx_latents:
             self.ctx.copy_(ctx_latents.to(self.ctx.dtype).reshape(self.ctx.shape))
-        if plan.prefix.rows:
-            self._assemble(plan.prefix)
-            self._layers(plan.prefix, kv_only_last=True)
+        if any(sp.n_prefix for sp in plan.specs):
+            if plan.prefix.rows:
+                self._assemble(plan.prefix)
+            yield from self._layers(plan.prefix, kv_only_last=True)
         self.prefilled = True
+
+    def prefill(self, ctx_latents: Optional[torch.Tensor] = None):
+        """Compute and cache K/V of every prefix (context) row.  ``ctx_latents``: [n_ctx, 4, h, w]."""
+        self._drive(self.prefill_steps(ctx_latents))
 
     def _predict_kernels(self):
         plan = self.plan
         st = plan.step
         self._time_embeddings(plan.n_latents)
-        self._assemble(st)
-        self._layers(st, kv_only_last=False)
-        ops.rmsnorm(self.hidden[:st.rows], self.w.norm, self.eps, out=self.xn[:st.rows])
-        ops.final_layer(self.xn[:st.rows], plan.lat_row0, self.mod[:plan.n_latents], self.w.final_w,
-                        self.w.final_b, self.pred)
+        if st.rows:
+            self._assemble(st)
+        yield from self._layers(st, kv_only_last=False)
+        if st.rows:
+            ops.rmsnorm(self.hidden[:st.rows], self.w.norm, self.eps, out=self.xn[:st.rows])
+        if self.peers is None:
+            ops.final_layer(self.xn[:st.rows], plan.lat_row0, self.mod[:plan.n_latents], self.w.final_w,
+                            self.w.final_b, self.pred)
+        else:                             # prediction stored into every rank's pred buffer
+            if st.rows:
+                ops.final_layer_rows(self.xn[:st.rows], st.kind, st.arg_a, st.arg_b, self.mod[:plan.n_latents],
+                                     self.w.final_w, self.w.final_b, self._pred_ptrs, self.peers.world,
+                                     plan.lat_h, plan.lat_w)
+            yield "pred"
+
+    def predict_steps(self):
+        """Generator form of ``predict`` without CUDA-graph capture (lockstep execution)."""
+        if not self.prefilled:
+            raise RuntimeError("prefill() must run before predict()")
+        yield from self._predict_kernels()
 
     def predict(self) -> torch.Tensor:
         """One denoising forward of the active rows.  Inputs: ``self.z`` (latents), ``self.t``
-        (one timestep per latent); output ``self.pred`` (raw model prediction per latent)."""
+        (one timestep per latent); output ``self.pred`` (raw model prediction per latent; in a
+        sequence-parallel group the complete prediction, on every rank)."""
         if not self.prefilled:
             raise RuntimeError("prefill() must run before predict()")
+        if self.peers is not None and self.peers.lockstep:
+            raise RuntimeError("virtual ranks (LocalPeerGroup) run through engine.run_lockstep")
         if not self.use_cuda_graph:
-            self._predict_kernels()
+            self._drive(self._predict_kernels())
             return self.pred
         if self._graph is None:
-            self._predict_kernels()            # warm-up (sets function attributes, fills caches)
+            self._drive(self._predict_kernels())   # warm-up (sets function attributes, fills caches)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._predict_kernels()
+                self._drive(self._predict_kernels())
             self._graph = g
         self._graph.replay()
         return self.pred
 
     @property
     def launches_per_predict(self) -> int:
-        return 6 + 1 + 8 * self.L + 2
+        sync = (self.L + 1) if self.peers is not None and not self.peers.lockstep else 0
+        return 6 + 1 + 8 * self.L + 2 + sync
 
     @property
     def launches_per_prefill(self) -> int:
         return (1 + 8 * (self.L - 1) + 3) if self.plan.prefix.rows else 0
+
+
+def run_lockstep(generators):
+    """Advance the kernel-sequence generators of several virtual ranks (``LocalPeerGroup``) phase by
+    phase on the current stream: everything every rank does before sync point k is enqueued before
+    anything any rank does after it, which is what the cross-GPU barrier guarantees between real
+    ranks."""
+    live = list(generators)
+    while live:
+        nxt = []
+        for g in live:
+            try:
+                next(g)
+                nxt.append(g)
+            except StopIteration:
+                pass
+        if nxt and len(nxt) != len(live):
+            raise RuntimeError("virtual ranks disagree on the number of sync points")
+        live = nxt

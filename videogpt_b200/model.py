@@ -153,6 +153,7 @@ class LVM(nn.Module):
         self._engine_key = None
         self._plan_key = None
         self._layout_key = None
+        self._peers = None
         self.use_cuda_graph = True
 
     # ---- construction / weights ---------------------------------------------------------------
@@ -221,16 +222,37 @@ class LVM(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("videogpt_b200.LVM runs on CUDA (sm_100a) only: move the model with "
                                ".to('cuda'); there is no CPU fallback")
-        key = (dev, tuple(p._version for p in self.parameters()), self.use_cuda_graph)
+        peers = self.sequence_parallel_peers()
+        key = (dev, tuple(p._version for p in self.parameters()), self.use_cuda_graph, id(peers))
         if self._engine is None or self._engine_key != key:
             d = self.dims()
             sd = {k: v for k, v in self.state_dict().items()}
             w = eng.EngineWeights(sd, d.num_hidden_layers, dev)
             self._engine = eng.NextClipEngine(w, d.hidden_size, d.intermediate_size, d.num_hidden_layers,
                                               d.num_attention_heads, d.rms_norm_eps, d.rope_theta, dev,
-                                              self.pos_embed_max_size, self.patch_size, self.use_cuda_graph)
+                                              self.pos_embed_max_size, self.patch_size, self.use_cuda_graph,
+                                              peers=peers)
             self._engine_key, self._plan_key, self._layout_key = key, None, None
         return self._engine
+
+    def sequence_parallel_peers(self):
+        """Peer group of this rank when ``initialize_sequence_parallel_state(P > 1)`` ran (the
+        reference's switch for sequence parallelism, ``LVM/model.py:459``): the ranks of
+        ``hccl_info.group`` then share every video -- each computes a contiguous chunk of the rows
+        of every sequence and stores its K/V and predictions into all peers (``peer.py``)."""
+        if hccl_info.world_size in (0, 1, None):
+            return None
+        if self._peers is None:
+            import torch.distributed as dist
+            from . import peer
+            ranks = dist.get_process_group_ranks(hccl_info.group) if hccl_info.group is not None else \
+                list(range(dist.get_world_size()))
+            self._peers = peer.PeerGroup(ranks, group=hccl_info.group)
+        return self._peers
+
+    def _shard(self):
+        e = self._engine
+        return None if e is None or e.peers is None else (e.peers.rank, e.peers.world)
 
     @staticmethod
     def _identity(*objs):
@@ -254,10 +276,7 @@ class LVM(nn.Module):
         Euler step of one clip) -> nothing to do; (2) same token layout (next clip of the same
         geometry) -> keep plan, workspaces and the captured CUDA graph, redo only the prefill;
         (3) new layout -> new plan."""
-        if hccl_info.world_size not in (0, 1) and hccl_info.world_size is not None:
-            # sequence-parallel entry (the reference chunks here: model.py:459-464)
-            raise NotImplementedError("use videogpt_b200.parallel for multi-GPU execution")
-        e = self.engine()
+        e = self.engine()             # sequence parallel (model.py:459-464) when hccl_info says so
         ident = self._identity(input_ids, position_ids, input_img_latents, input_image_sizes,
                                denoise_image_sizes, time_emb_inx, attention_mask, lat_h, lat_w)
         if ident == self._plan_key and e.plan is not None and e.prefilled:
@@ -273,7 +292,7 @@ class LVM(nn.Module):
                                                        denoise_image_sizes, time_emb_inx)
             if check_mask and attention_mask is not None:
                 self._check_mask(attention_mask, specs, e.device)
-            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device))
+            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device, shard=self._shard()))
             self._layout_key = layout
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)
@@ -359,7 +378,7 @@ class LVM(nn.Module):
             specs, n_lat, n_ctx = eng.single_frame_specs(ids_host, pos_host, input_image_sizes, n_tok)
             if check_mask and attention_mask is not None:
                 self._check_mask(attention_mask, specs, e.device)
-            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device))
+            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device, shard=self._shard()))
             self._layout_key = layout
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)

@@ -96,6 +96,16 @@ def rope_kv_append(qkv, row_pos, row_slot, table, k_pool, v_pool, heads: int, he
               _p(v_pool), rows, heads, head_dim, _stream())
 
 
+def rope_kv_append_peers(qkv, row_pos, row_slot, table, k_pool_ptrs, v_pool_ptrs, n_pools: int, heads: int,
+                         head_dim: int):
+    """``k_pool_ptrs`` / ``v_pool_ptrs``: ctypes ``void*[n_pools]`` (``peer.SharedBuffer.ptr_array``)."""
+    _req(qkv, BF16, "qkv"); _req(row_pos, I32, "row_pos"); _req(row_slot, I32, "row_slot"); _req(table, BF16, "table")
+    rows = qkv.shape[0]
+    assert qkv.shape[1] == 3 * heads * head_dim and row_pos.numel() >= rows and row_slot.numel() >= rows
+    _lib.call("vgpt_rope_kv_append_peers", _p(qkv), _p(row_pos), _p(row_slot), _p(table), k_pool_ptrs,
+              v_pool_ptrs, n_pools, rows, heads, head_dim, _stream())
+
+
 ATTN_IMPL = "tcgen05"       # "mma_sync" selects the legacy cross-check kernel (tests only)
 
 
@@ -172,6 +182,17 @@ def final_layer(hidden, lat_row0, mod, w, bias, pred):
     _lib.call("vgpt_final_layer", _p(hidden), hidden.shape[1], _p(lat_row0), _p(mod), _p(w), _p(bias),
               _p(pred), n_lat, c, lat_h, lat_w, _stream())
     return pred
+
+
+def final_layer_rows(hidden, row_kind, row_a, row_b, mod, w, bias, pred_ptrs, n_preds: int, lat_h: int, lat_w: int):
+    """Row-driven final layer; ``pred_ptrs``: ctypes ``void*[n_preds]`` of ``[n_lat,4,lat_h,lat_w]`` buffers."""
+    _req(hidden, BF16, "hidden"); _req(mod, BF16, "mod"); _req(w, BF16, "w"); _req(bias, BF16, "bias")
+    rows = hidden.shape[0]
+    for n, t in (("row_kind", row_kind), ("row_a", row_a), ("row_b", row_b)):
+        _req(t, I32, n)
+        assert t.numel() >= rows
+    _lib.call("vgpt_final_layer_rows", _p(hidden), rows, hidden.shape[1], _p(row_kind), _p(row_a), _p(row_b),
+              _p(mod), _p(w), _p(bias), pred_ptrs, n_preds, 4, lat_h, lat_w, _stream())
 
 
 def cfg_euler(z, pred, use_cfg: bool, x1_mode: bool, one_minus_sigma: float = 1.0, dsigma: float = 0.0,
