@@ -16,7 +16,10 @@ steps with CFG (50 at full size), synthetic latents, random-init weights.  Print
 * ``cpu_baseline`` / ``--impl reference``: the oracle restatement of the reference's own
                 PyTorch path (no cache, padded unconditional row, dense mask) on the host cores,
                 bounded sample, extrapolated and labelled as such.
-N > 1 (torchrun): independent videos data-parallel across ranks (weak scaling, no collective).
+N > 1 (torchrun): --parallelism dp = independent videos data-parallel across ranks (weak scaling,
+no collective; the default); cfg = CFG branches on rank pairs; sp = sequence parallel, groups of
+--sp ranks share one video (rows sharded, K/V stored into the peers over NVLink: strong scaling
+of one video inside a group, weak across groups).
 """
 from __future__ import annotations
 
@@ -36,6 +39,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (dims, n_ctx, n_gen, height, width, euler_steps)
     "cfg2": ("full", 4, 4, 256, 256, 50),   # BASELINE.json configs[1]: the config the metric is quoted on
+    "cfg3": ("full", 32, 4, 256, 256, 50),  # configs[2]: 8 context clips, KV cache (sequence parallel at N>1)
     "cfg5": ("full", 4, 4, 512, 512, 50),   # configs[4]
     "cfg1": ("reduced", 4, 4, 256, 256, 4),  # configs[0] (the reference's CPU-runnable case)
 }
@@ -205,10 +209,15 @@ def run_ours(args, rank, world, local_rank):
     dims = _dims(kind)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    sp_size = 1
+    if args.parallelism == "sp" and world > 1:
+        from videogpt_b200 import parallel_states
+        sp_size = args.sp or world
+        parallel_states.initialize_sequence_parallel_state(sp_size)   # the reference's SP switch
     model = build_model(dims, dev)
     pipe = LVMPipeline(None, model, LVMProcessor(FakeTokenizer()), device=dev)
     block = H * W // 256 + 2
-    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42 + rank)
+    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42 + rank // sp_size)
     ctx_host = [x.to(torch.bfloat16).pin_memory() for x in lat[:n_ctx]]
     noise_host = [x.to(torch.bfloat16).pin_memory() for x in lat[n_ctx:]]
     ctx_dev = [x.to(dev) for x in ctx_host]
@@ -284,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     tokens_per_clip = 2 * n_gen * block * euler
-    videos = world // 2 if cfg_split else world
+    videos = world // 2 if cfg_split else world // sp_size
     value = videos * tokens_per_clip * args.steps / dt
     e2e = videos * tokens_per_clip * args.steps / dt_e2e
     step_fl, prefill_fl, clip_fl = algorithmic_flops(dims, n_ctx, n_gen, block, euler)
@@ -298,9 +307,10 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops", 1590.0)
-    sec, fl, n_launch = gemm_roofline(model, 2 * n_gen * block)
+    gemm_rows = e.plan.step.rows
+    sec, fl, n_launch = gemm_roofline(model, gemm_rows)
     achieved = fl / sec / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (qkv/o/gate_up/down, M=%d)" % (2 * n_gen * block),
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_pair_kernel (qkv/o/gate_up/down, M=%d)" % gemm_rows,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if peaks else "fallback 1590",
                 "traffic": None, "avg_launch_us": sec * 1e6, "launches_timed": n_launch,
@@ -312,12 +322,15 @@ def run_ours(args, rank, world, local_rank):
     lat_bytes = 4 * (H // 8) * (W // 8) * 2
     line = {"metric": "next_clip_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
-            "s_per_clip": dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "s_per_clip": dt / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sp_size == world and world > 1 else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.config, "model": "Phi-3-mini-class random-init" if kind == "full" else "2 layers / hidden 512",
                        "context_frames": n_ctx, "generated_frames": n_gen, "height": H, "width": W,
                        "euler_steps": euler, "cfg": True, "guidance": GUIDANCE, "prediction_type": "x1",
-                       "parallelism": (f"cfg-branch pairs x dp{world // 2}" if cfg_split else f"dp{world} (independent videos)"),
+                       "parallelism": (f"cfg-branch pairs x dp{world // 2}" if cfg_split else
+                                       f"sp{sp_size} (rows of one video sharded, K/V pushed to peers over NVLink) x dp{world // sp_size}"
+                                       if sp_size > 1 else f"dp{world} (independent videos)"),
                        "l2": "weights 7.2 GB streamed every Euler step (> 126 MB L2); no explicit flush"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "tokens/s", "s_per_clip": dt_e2e / args.steps,
@@ -334,8 +347,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--parallelism", default="dp", choices=["dp", "cfg"],
-                    help="N>1: dp = independent videos per rank; cfg = CFG branches split over rank pairs")
+    ap.add_argument("--parallelism", default="dp", choices=["dp", "cfg", "sp"],
+                    help="N>1: dp = independent videos per rank; cfg = CFG branches split over rank pairs; "
+                         "sp = sequence parallel groups of --sp ranks per video")
+    ap.add_argument("--sp", type=int, default=0, help="ranks per sequence-parallel group (default: all)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -351,6 +366,8 @@ def main():
         run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
+            from videogpt_b200 import parallel_states
+            parallel_states.destroy_sequence_parallel_group()
             import torch.distributed as dist
             dist.destroy_process_group()
 

@@ -142,7 +142,8 @@ int vgpt_peer_close(void* p);
 /* Barrier over n_ranks GPUs through peer-mapped flag words: flag_ptrs[j] -> rank j's uint32[n_ranks]
  * (flag_ptrs[rank] is local); state = local uint32[2] {epoch, timed_out}.  Enqueued like any other
  * kernel (graph capturable); every rank must enqueue the same sequence of barriers.  A peer that
- * never arrives sets state[1] after ~20 s instead of hanging the GPU. */
+ * never arrives sets state[1] after ~10 s instead of hanging the GPU; later barriers then return
+ * at once (fail fast; the host checks state[1]). */
 int vgpt_peer_barrier(void* const* flag_ptrs, int n_ranks, int rank, uint32_t* state, void* stream);
 
 /* x1 -> velocity, CFG and the Euler update (LVM/scheduler.py:178-204, LVM/model.py:554-562) on

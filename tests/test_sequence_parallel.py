@@ -73,14 +73,18 @@ def _engine(w, dims, dev, peers=None):
                               dims.pos_embed_max_size, 2, use_cuda_graph=False, peers=peers)
 
 
+WIDE = synth.BackboneDims(num_hidden_layers=2)       # full width (32 heads x 96), two layers
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,geom", [(2, (3, 2, 64, 96)), (3, (2, 2, 64, 64)), (4, (4, 4, 128, 128))])
-def test_virtual_ranks_match_unsharded_engine_bit_exact(world, geom):
+@pytest.mark.parametrize("world,geom,dims", [(2, (3, 2, 64, 96), synth.REDUCED), (3, (2, 2, 64, 64), synth.REDUCED),
+                                             (4, (4, 4, 128, 128), synth.REDUCED), (2, (4, 4, 256, 256), WIDE),
+                                             (3, (4, 4, 256, 256), WIDE), (8, (2, 2, 128, 256), WIDE)])
+def test_virtual_ranks_match_unsharded_engine_bit_exact(world, geom, dims):
     from videogpt_b200 import ops, peer
     dev, bf = torch.device("cuda", 0), torch.bfloat16
     n_ctx, n_gen, H, W = geom
-    dims = synth.REDUCED
-    sd = synth.init_state_dict(dims, seed=0)
+    sd = synth.init_state_dict(dims, seed=0, dtype=bf, with_pos_embed=False)
     w = eng.EngineWeights(sd, dims.num_hidden_layers, dev)
     _, specs, n_lat, n_ctx_lat = _specs(n_ctx, n_gen, H, W)
     lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)

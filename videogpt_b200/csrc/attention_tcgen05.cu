@@ -254,8 +254,14 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       s_rowmax[j & 1][half][row] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 softmax warps only
       const float m_new = fmaxf(m_run, fmaxf(mx, s_rowmax[j & 1][half ^ 1][row]));
-      const float sub = (m_new == -INFINITY) ? 0.f : m_new * scale_log2;
-      const float alpha = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run * scale_log2 - sub);
+      const float sub = (m_new == -INFINITY) ? 0.f : __fmul_rn(m_new, scale_log2);
+      // alpha is EXACTLY 1 for a row whose maximum did not move (no FMA contraction of the
+      // difference), so the warp-uniform "somebody's maximum grew" rescale below leaves such rows
+      // bit-identical whatever rows share their warp: results do not depend on how query rows are
+      // grouped into tiles (sequence parallelism relies on this).
+      const float alpha = (m_run == -INFINITY) ? 0.f
+                          : (m_new == m_run)   ? 1.f
+                                               : ex2_approx(__fsub_rn(__fmul_rn(m_run, scale_log2), sub));
       // P half-row -> TMEM buffer j&1 (last read by P V of tile j-2, whose completion every thread
       // observed in iteration j-1), overlapping the P V of tile j-1 on the tensor pipe
       float sum = 0.f;

@@ -81,7 +81,8 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int n, int rank, uint32_t* _
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
     const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + t;
     const long long t0 = clock64();
-    for (;;) {
+    const bool dead = *reinterpret_cast<volatile uint32_t*>(state + 1) != 0;   // fail fast after a time-out
+    for (; !dead;) {
       uint32_t v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int32_t)(v - epoch) >= 0) break;
@@ -100,7 +101,7 @@ int peer_barrier(void* const* flag_ptrs, int n, int rank, uint32_t* state, cudaS
   PeerPtrs f;
   for (int i = 0; i < kMaxPeers; ++i) f.p[i] = i < n ? flag_ptrs[i] : nullptr;
   for (int i = 0; i < n; ++i) VGPT_CHECK_ARG(f.p[i], "vgpt_peer_barrier: null flag pointer for rank %d", i);
-  peer_barrier_kernel<<<1, 32, 0, s>>>(f, n, rank, state, 40000000000ll /* ~20 s */);
+  peer_barrier_kernel<<<1, 32, 0, s>>>(f, n, rank, state, 20000000000ll /* ~10 s */);
   VGPT_CHECK_LAUNCH();
   return 0;
 }

@@ -389,6 +389,8 @@ class NextClipEngine:
         if self._rope_tab is None or self._rope_tab.shape[0] < plan.max_pos:
             self._rope_tab = ops.rope_table(self._inv_freq, max(plan.max_pos, 1), self.D)
         self.prefilled = False
+        if self.peers is not None:
+            self.peers.host_barrier()         # every rank has finished allocating
 
     def _pos_rows(self, lat_h: int, lat_w: int) -> torch.Tensor:
         """``cropped_pos_embed`` (LVM/model.py:268-289) as bf16 rows ``[tokens, hidden]``: gathered
@@ -464,6 +466,10 @@ class NextClipEngine:
         plan = self.plan
         if ctx_latents is not None and plan.n_ctx_latents:
             self.ctx.copy_(ctx_latents.to(self.ctx.dtype).reshape(self.ctx.shape))
+        if self.peers is not None:
+            # clip boundary: from here to the last kernel of the clip this rank's host never blocks
+            # in the driver (no allocation, no capture) while a peer may be spinning on it
+            self.peers.host_barrier()
         if any(sp.n_prefix for sp in plan.specs):
             if plan.prefix.rows:
                 self._assemble(plan.prefix)
@@ -513,10 +519,14 @@ class NextClipEngine:
         if self._graph is None:
             self._drive(self._predict_kernels())   # warm-up (sets function attributes, fills caches)
             torch.cuda.synchronize()
+            if self.peers is not None:
+                self.peers.host_barrier()          # nobody spins on a peer while anybody captures
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._drive(self._predict_kernels())
             self._graph = g
+            if self.peers is not None:
+                self.peers.host_barrier()
         self._graph.replay()
         return self.pred
 

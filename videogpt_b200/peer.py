@@ -117,6 +117,15 @@ class PeerGroup:
         _lib.call("vgpt_peer_barrier", self._flag_ptrs, self.world, self.rank,
                   ctypes.c_void_p(self._state.data_ptr()), torch.cuda.current_stream().cuda_stream)
 
+    def host_barrier(self):
+        """*collective*: drain this GPU, then rendezvous on the host.  Brackets every region in
+        which a rank may block inside the CUDA driver (allocation, graph capture / instantiation):
+        such calls can wait for a PEER device to go idle, and a peer that is spinning in
+        ``vgpt_peer_barrier`` for kernels this rank has not enqueued yet never does."""
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
     def check(self):
         """Raise if any barrier timed out (a peer died); synchronises the stream."""
         if int(self._state[1].item()) != 0:
@@ -155,6 +164,9 @@ class LocalPeerGroup:
         return SharedBuffer(bufs[self.rank], [b.data_ptr() for b in bufs], self.rank)
 
     def barrier(self):
+        pass
+
+    def host_barrier(self):
         pass
 
     def check(self):
