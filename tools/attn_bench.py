@@ -12,7 +12,7 @@ from oracle import processor_oracle as po  # noqa: E402
 from videogpt_b200 import engine as eng, ops  # noqa: E402
 
 n_ctx, n_gen, H, W = (int(x) for x in (sys.argv[1:5] if len(sys.argv) > 4 else (4, 4, 256, 256)))
-heads, D, dev = 32, 96, "cuda"
+heads, D, dev = (int(sys.argv[5]), int(sys.argv[6]), "cuda") if len(sys.argv) > 6 else (32, 96, "cuda")
 d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
 specs, n_lat, n_c = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
                                           d["denoise_image_sizes"], d["time_emb_inx"])

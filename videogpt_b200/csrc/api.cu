@@ -2,6 +2,8 @@
 #include "../../include/vgpt_b200.h"
 #include "vgpt_internal.h"
 
+#include <cstdlib>
+
 static_assert(VGPT_PAGE_TOKENS == 128, "attention.cu assumes 128-token pages");
 #define S(stream) static_cast<cudaStream_t>(stream)
 
@@ -56,9 +58,15 @@ int vgpt_attn_clip_causal(const void* q, int q_ld, int q_rows, void* out, int ou
                           const VgptAttnSeq* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
                           const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H,
                           int D, float scale, void* stream) {
-  return vgpt::attn_clip_causal_tc(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,
-                                   max_pages, seqs, num_seqs, max_q_rows, q_code, k_code, k_tile_minmax,
-                                   max_k_tiles, H, D, scale, S(stream));
+  // VGPT_ATTN_V1=1 selects the earlier one-query-tile kernel (attention_tcgen05.cu) for A/B timing
+  static const bool v1 = [] { const char* e = getenv("VGPT_ATTN_V1"); return e && e[0] == '1'; }();
+  if (v1)
+    return vgpt::attn_clip_causal_tc(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,
+                                     max_pages, seqs, num_seqs, max_q_rows, q_code, k_code, k_tile_minmax,
+                                     max_k_tiles, H, D, scale, S(stream));
+  return vgpt::attn_clip_causal_pair(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,
+                                     max_pages, seqs, num_seqs, max_q_rows, q_code, k_code, k_tile_minmax,
+                                     max_k_tiles, H, D, scale, S(stream));
 }
 int vgpt_attn_clip_causal_mma_sync(const void* q, int q_ld, int q_rows, void* out, int out_ld,
                                    const void* k_pool, const void* v_pool, int total_pages,
@@ -119,6 +127,11 @@ int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img,
                              float* d_out, int n_cols, void* stream) {
   return vgpt::umma_probe_ts(a_words, a_cols, b_img, b_bytes, b_desc_base, idesc, k_steps, b_step_bytes,
                              d_out, n_cols, S(stream));
+}
+
+int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out,
+                         void* stream) {
+  return vgpt::umma_rate(mode, N, iters, n_acc, commit_every, ctas, out, S(stream));
 }
 
 }  // extern "C"

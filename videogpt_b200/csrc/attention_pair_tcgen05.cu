@@ -1,0 +1,536 @@
+// Clip-block-causal flash attention, production kernel: TWO 128-row query tiles per CTA that
+// ping-pong on the tensor pipe (tcgen05 + TMEM + TMA).
+//
+// Same contract as attention.cu / attention_tcgen05.cu (codes instead of a mask, paged KV pools,
+// tile classification from per-tile code min/max).  What changed against attention_tcgen05.cu
+// (one query tile, 8 softmax warps, 101 us per launch at cfg2) and why:
+//
+//   * One CTA owns query tiles A and B of the same (sequence, head): every K/V tile is loaded once
+//     for 256 queries (half the L2 -> SMEM traffic), and while the softmax warps of A work on
+//     S_A(j) the tensor pipe runs O_B += P_B V(j-1) and S_B(j) -- the MMA issue order is
+//     S_A S_B | PV_A S_A' | PV_B S_B' | ...  so neither pipe waits for the other.
+//   * One softmax THREAD per query row (4 warps per tile, TMEM lane == row): the row maximum and
+//     row sum need no shuffle, no shared memory and no named barrier.
+//   * P overwrites S in tensor memory (bf16 pairs in the first 64 columns of the S region) and is
+//     the A operand of O += P V; S(j+1) is issued behind P V(j) on the in-order tensor pipe, so
+//     the aliasing needs no extra barrier.  TMEM: S_A | S_B | O_A | O_B = 2 x 128 + 2 x D <= 512.
+//   * Lazy rescale: the running maximum only moves when a row's tile maximum exceeds it by more
+//     than 2^8 (in the exp2 domain), so after the first tiles O is almost never rescaled; the
+//     rare rescale is done by the row's own thread (tcgen05.ld / st), warp-uniformly, and rows
+//     whose maximum did not move use alpha == 1 exactly -- results do not depend on which rows
+//     share a tile (sequence parallelism relies on it).
+//   * The code predicate is evaluated only by warps that contain a row that cannot see the whole
+//     tile (the two tag rows at a frame start) and on the ragged last tile.
+//
+// Warp roles (384 threads = 3 warpgroups): warps 0..3 = softmax / epilogue of tile A, warps 4..7 =
+// of tile B (TMEM lane quadrant = warp_idx % 4), warp 8 = TMA producer, warp 9 = TMEM allocator +
+// MMA issuer, warp 10 = tile-table builder, warp 11 idle.  Registers are re-balanced per
+// warpgroup with setmaxnreg (softmax 232, the rest 40): a softmax thread holds a whole 128-key
+// row of S in registers.
+#include "common.cuh"
+#include "vgpt_internal.h"
+
+#include <cuda.h>
+
+#include <cstdlib>
+
+namespace vgpt {
+
+constexpr int kPairBM = 128;         // queries per tile (two tiles per CTA)
+constexpr int kPairBN = 128;         // keys per tile = one KV page
+constexpr int kPairThreads = 384;   // 3 warpgroups: softmax A, softmax B, {TMA, MMA, table, idle}
+
+struct AttnSeqP { int32_t q_row0, n_q, kv_len, reserved; };
+
+template <int D>
+struct PairCfg {
+  static constexpr int kCW = (D == 96) ? 32 : 64;            // elements per swizzled chunk row
+  static constexpr int kRowBytes = kCW * 2;                   // 64 (SW64) or 128 (SW128)
+  static constexpr uint32_t kLayout = (D == 96) ? kLayoutSW64 : kLayoutSW128;
+  static constexpr int kChunks = D / kCW;
+  static constexpr int kChunkBytes = 128 * kRowBytes;
+  static constexpr int kTileBytes = kChunks * kChunkBytes;    // Q, K or V tile = 128 * D * 2
+  static constexpr int kStages = (D == 128) ? 2 : (D == 96 ? 3 : 4);
+  static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + 1024;   // tiles + barriers + tile table + align
+  static constexpr int kTmemO = 256;                          // O_A at 256, O_B at 256 + D
+  // 64 spare TMEM columns (head_dim <= 96): P gets its own buffer, shared by the two tiles, and
+  // S_x(j+1) is issued as soon as the softmax warps have read S_x(j) -- it runs under softmax(j).
+  // Otherwise (head_dim 128) P overwrites S and S_x(j+1) follows P V_x(j) on the tensor pipe.
+  static constexpr bool kEarlyS = 256 + 2 * D + 64 <= 512;
+  static constexpr int kTmemP = 256 + 2 * D;
+};
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// packed fp32x2 math (Blackwell FFMA2 / FADD2): halves the FMA-pipe instruction count of the
+// exponent arguments and of the row sums
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {     // d += a
+  asm("{\n\t.reg .b64 ra, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rd, {%0, %1};\n\t"
+      "add.rn.f32x2 rd, rd, ra;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
+}
+
+constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
+
+template <int D>
+__global__ void __launch_bounds__(kPairThreads, 1)
+attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                         const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int out_ld,
+                         const int32_t* __restrict__ page_table, int max_pages,
+                         const AttnSeqP* __restrict__ seqs, const int32_t* __restrict__ q_code,
+                         const int32_t* __restrict__ k_code, const int32_t* __restrict__ k_tile_minmax,
+                         int max_k_tiles64, int H, float scale_log2, int dbg) {
+  using C = PairCfg<D>;
+  constexpr int kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_qmin, s_qmax, s_nvis;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t s_q = base;                                   // Q_A, Q_B
+  const uint32_t s_kv = s_q + 2 * C::kTileBytes;               // stage s: K at s_kv + 2*s*tile, V right after
+  const uint32_t bars = s_kv + 2 * kStages * C::kTileBytes;
+  const uint32_t bar_q = bars;
+  auto bar_kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto bar_kv_empty = [&](int s) { return bars + 8u * (1 + kStages + s); };
+  auto bar_s_full = [&](int x) { return bars + 8u * (1 + 2 * kStages + x); };
+  auto bar_p_full = [&](int x) { return bars + 8u * (3 + 2 * kStages + x); };
+  auto bar_o_full = [&](int x) { return bars + 8u * (5 + 2 * kStages + x); };
+  auto bar_s_free = [&](int x) { return bars + 8u * (7 + 2 * kStages + x); };
+  const uint32_t tmem_slot = bars + 8u * (9 + 2 * kStages);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen + (tmem_slot - base));
+  // per-CTA table of the KV tiles some query of this CTA can see (built once; every role walks it
+  // from shared memory instead of re-deriving it from global memory inside its loop)
+  int32_t* t_page = reinterpret_cast<int32_t*>(gen + (bars - base) + 256);          // pool page of tile i
+  int32_t* t_tmax = t_page + kPairMaxTiles;                                         // max key code of tile i
+  int32_t* t_kt = t_tmax + kPairMaxTiles;                                           // logical tile index
+
+  const int seq_id = blockIdx.z, head = blockIdx.y;
+  const AttnSeqP sq = seqs[seq_id];
+  const int q0 = blockIdx.x * 2 * kPairBM;
+  if (q0 >= sq.n_q) return;
+  const int rows_cta = min(2 * kPairBM, sq.n_q - q0);          // valid rows of A and B together
+  const bool has_b = rows_cta > kPairBM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- CTA-wide max of the valid query codes (tile classification) -----------------------------
+  if (threadIdx.x == 0) { s_qmin = 0x7fffffff; s_qmax = (int)0x80000000; s_nvis = 0; }
+  __syncthreads();
+  if ((int)threadIdx.x < rows_cta && threadIdx.x < 2 * kPairBM) atomicMax(&s_qmax, q_code[sq.q_row0 + q0 + threadIdx.x]);
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), 1); }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(bar_s_full(x), 1); mbar_init(bar_p_full(x), 4); mbar_init(bar_o_full(x), 1); mbar_init(bar_s_free(x), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int n_kt = (sq.kv_len + kPairBN - 1) / kPairBN;
+  if (warp == 8) {                        // Q does not need the table: start its load now
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(bar_q, (has_b ? 2 : 1) * C::kTileBytes);
+      for (int x = 0; x < (has_b ? 2 : 1); ++x)
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_2d(s_q + x * C::kTileBytes + c * C::kChunkBytes, &tmap_q, bar_q, head * D + c * C::kCW,
+                      sq.q_row0 + q0 + x * kPairBM);
+    }
+    __syncwarp();
+  } else if (warp == 10) {                // ordered compaction of the visible tiles, 32 per step
+    const int q_max = s_qmax;
+    const int32_t* mm = k_tile_minmax + (size_t)seq_id * max_k_tiles64 * 2;   // (min, max) per 64 keys
+    const int32_t* pt = page_table + (size_t)seq_id * max_pages;
+    int n = 0;
+    for (int b0 = 0; b0 < n_kt; b0 += 32) {
+      const int kt = b0 + lane;
+      bool vis = false;
+      int tmax = 0, page = 0;
+      if (kt < n_kt) {
+        const int4 m4 = *reinterpret_cast<const int4*>(mm + 4 * kt);
+        vis = min(m4.x, m4.z) <= q_max;               // else: fully masked for every query of this CTA
+        tmax = max(m4.y, m4.w);
+        page = pt[kt];
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, vis);
+      if (vis) {
+        const int i = n + __popc(bal & ((1u << lane) - 1u));
+        t_page[i] = page; t_tmax[i] = tmax; t_kt[i] = kt;
+      }
+      n += __popc(bal);
+    }
+    if (lane == 0) s_nvis = n;
+  }
+  __syncthreads();
+  const int n_vis = s_nvis;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 8) {
+    // =================================== TMA producer ===================================
+    // (whole warp runs the loop; one elected lane issues)
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < n_vis; ++i) {
+      const int row = (t_page[i] * H + head) * kPairBN;         // pool viewed as [(page*H + head)*128 + tok][D]
+      mbar_wait(bar_kv_empty(stage), phase ^ 1);
+      if ((dbg & 8) && i >= kStages) {                          // timing probe: operands not refreshed
+        if (elect_one_sync()) mbar_arrive(bar_kv_full(stage));
+      } else if (elect_one_sync()) {
+        const uint32_t sk = s_kv + 2 * stage * C::kTileBytes, sv = sk + C::kTileBytes;
+        mbar_arrive_expect_tx(bar_kv_full(stage), 2 * C::kTileBytes);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) tma_load_2d(sk + c * C::kChunkBytes, &tmap_k, bar_kv_full(stage), c * C::kCW, row);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) tma_load_2d(sv + c * C::kChunkBytes, &tmap_v, bar_kv_full(stage), c * C::kCW, row);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 9) {
+    // =================================== MMA issuer ===================================
+    // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, kPairBN);        // S = Q K^T (both K-major)
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O = P V   (V MN-major)
+    auto issue_s = [&](int x, int stage) {
+      if (elect_one_sync()) {
+        const uint32_t sk = s_kv + 2 * stage * C::kTileBytes, sqx = s_q + x * C::kTileBytes;
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+#pragma unroll
+          for (int ks = 0; ks < C::kCW / 16; ++ks) {
+            const uint64_t da = make_smem_desc(sqx + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
+            const uint64_t db = make_smem_desc(sk + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
+            umma_f16_ss(tmem + x * 128, da, db, idesc_s, (c | ks) ? 1u : 0u);
+          }
+        }
+        if (!(dbg & 32)) umma_commit(bar_s_full(x));          // (dbg & 32: timing probe, fewer commits)
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int x, int stage, int j, bool release_kv) {
+      if (elect_one_sync()) {
+        const uint32_t sv = s_kv + 2 * stage * C::kTileBytes + C::kTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < kPairBN / 16; ++ks) {
+          const uint64_t db = make_smem_desc(sv + ks * 16 * C::kRowBytes, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);
+          umma_f16_ts(tmem + C::kTmemO + x * D, tmem + (C::kEarlyS ? C::kTmemP : x * 128) + ks * 8, db, idesc_o,
+                      (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        if (!(dbg & 32) || j == n_vis - 1) umma_commit(bar_o_full(x));
+        if (release_kv) umma_commit(bar_kv_empty(stage));     // K(j), V(j) free once everything issued so far is done
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar_q, 0);
+    int stage_s = 0; uint32_t phase_s = 0;
+    int stage_o = 0;
+    if (n_vis > 0) {                            // prologue: S_A(0), S_B(0)
+      mbar_wait(bar_kv_full(stage_s), phase_s);
+      tc_fence_after();
+      issue_s(0, stage_s);
+      if (has_b) issue_s(1, stage_s);
+      if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+    }
+    if constexpr (C::kEarlyS) {
+      // S_x(j+1) as soon as S_x(j) sits in the softmax warps' registers (s_free), P V_x(j) when
+      // P_x(j) is in the shared P buffer (p_full); fixed order A, B -- the two tiles fall into a
+      // half-period stagger.  (An event loop polling all four barriers was measured slower:
+      // it competes with the softmax warps for issue slots.)
+      for (int j = 0; j < n_vis; ++j) {
+        const bool has_next = j + 1 < n_vis;
+        for (int x = 0; x < (has_b ? 2 : 1); ++x) {
+          if (has_next) {
+            if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
+            if (x == 0) mbar_wait(bar_kv_full(stage_s), phase_s);
+            tc_fence_after();
+            issue_s(x, stage_s);
+          }
+          if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
+          tc_fence_after();
+          issue_pv(x, stage_o, j, x == (has_b ? 1 : 0));
+        }
+        if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+        if (++stage_o == kStages) stage_o = 0;
+      }
+    } else {
+      for (int j = 0; j < n_vis; ++j) {
+        const bool has_next = j + 1 < n_vis;
+        mbar_wait(bar_p_full(0), j & 1);          // P_A(j) in TMEM (and O_A rescaled if it had to be)
+        tc_fence_after();
+        issue_pv(0, stage_o, j, !has_b);
+        if (has_next) {
+          mbar_wait(bar_kv_full(stage_s), phase_s);
+          tc_fence_after();
+          issue_s(0, stage_s);                    // S_A(j+1) overwrites P_A(j): behind P V_A(j) in pipe order
+        }
+        if (has_b) {
+          mbar_wait(bar_p_full(1), j & 1);
+          tc_fence_after();
+          issue_pv(1, stage_o, j, true);
+          if (has_next) issue_s(1, stage_s);
+        }
+        if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+        if (++stage_o == kStages) stage_o = 0;
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ============================ softmax / rescale / epilogue ============================
+    const int x = warp >> 2;                                    // 0 = tile A, 1 = tile B
+    if (x == 0 || has_b) {
+      const int quad = warp & 3;
+      const int row = quad * 32 + lane;                         // row of the tile == TMEM lane
+      const int rows_here = min(kPairBM, rows_cta - x * kPairBM);
+      const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+      const uint32_t t_s = tmem + lane_addr + x * 128;          // S_x (P_x = its first 64 columns)
+      const uint32_t t_o = tmem + lane_addr + C::kTmemO + x * D;
+      const uint32_t t_p = tmem + lane_addr + C::kTmemP;        // shared P buffer (kEarlyS)
+      const int grow = sq.q_row0 + q0 + x * kPairBM + row;
+      const bool valid = row < rows_here;
+      const int qc = valid ? q_code[grow] : 0x7fffffff;         // padding rows: see everything, never stored
+      const int32_t* kc = k_code + (size_t)seq_id * max_pages * kPairBN;
+      const float thresh = 8.0f / scale_log2;                   // lazy rescale: 2^8 head-room
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_vis; ++j) {
+        if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
+        const int tmax = t_tmax[j], kt = t_kt[j];                 // (shared memory, before the wait)
+        mbar_wait(bar_s_full(x), j & 1);
+        tc_fence_after();
+        if (dbg & 1) {                                            // timing probe: tensor-pipe chain only
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (C::kEarlyS) mbar_arrive(bar_s_free(x)); mbar_arrive(bar_p_full(x)); }
+          continue;
+        }
+        if ((kt + 1) * kPairBN > sq.kv_len || __any_sync(0xffffffffu, qc < tmax)) {
+          // Rare (the two tag rows at a frame start, the ragged last tile): apply the code predicate
+          // to S in place in tensor memory, 32 columns at a time, so the hot path below keeps its
+          // registers.
+          const int4* kcode = reinterpret_cast<const int4*>(kc + kt * kPairBN);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(t_s + c * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int4 c4 = __ldg(kcode + c * 8 + i);
+              if (qc < c4.x) t[4 * i + 0] = 0xff800000u;          // -inf
+              if (qc < c4.y) t[4 * i + 1] = 0xff800000u;
+              if (qc < c4.z) t[4 * i + 2] = 0xff800000u;
+              if (qc < c4.w) t[4 * i + 3] = 0xff800000u;
+            }
+            tmem_st_32x32b_x32(t_s + c * 32, t);
+          }
+          tmem_st_wait();
+        }
+        uint32_t s[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tmem_ld_32x32b_x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        tmem_ld_wait();
+        if constexpr (C::kEarlyS) {                                // S_x is free: S_x(j+1) may be issued now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_s_free(x));
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[4 * i + 0]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[4 * i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[4 * i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[4 * i + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const bool grew = mx > m_run + thresh;                   // also true for the first finite maximum
+        const float m_new = grew ? mx : m_run;
+        const float sub = (m_new == -INFINITY) ? 0.f : __fmul_rn(m_new, scale_log2);
+        // alpha == 1 EXACTLY for rows whose reference maximum did not move
+        const float alpha = !grew ? 1.f
+                            : (m_run == -INFINITY) ? 0.f
+                                                   : ex2_ftz(__fsub_rn(__fmul_rn(m_run, scale_log2), sub));
+        float sum0 = 0.f, sum1 = 0.f;
+        const float nsub = -sub;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          float p0, p1;
+          ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), scale_log2, nsub);
+          if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
+          fadd2(sum0, sum1, p0, p1);
+          s[i] = pack_bf16x2(p0, p1);                             // P overwrites the dead half of s[]
+        }
+        if constexpr (C::kEarlyS) {
+          // the P buffer is shared: its previous reader is P V of the other tile (B: tile j of A;
+          // A: tile j-1 of B), or of this tile when it is alone
+          const int y = has_b ? (x ^ 1) : 0;
+          const int need = (x == 1) ? j : j - 1;                   // index of that P V
+          if (need >= 0) {
+            mbar_wait(bar_o_full(y), need & 1);
+            tc_fence_after();
+          }
+          tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        } else {
+          tmem_st_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_st_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        }
+        l_run = l_run * alpha + (sum0 + sum1);
+        m_run = m_new;
+        if (j > 0 && __any_sync(0xffffffffu, grew)) {
+          // rare after the first tiles: O_x(j-1) must be complete, then scale this row
+          mbar_wait(bar_o_full(x), (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int u = 0; u < D / 32; ++u) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_o + u * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + u * 32, o);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 per tile)
+      }
+      // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------
+      if (n_vis > 0) {
+        mbar_wait(bar_o_full(x), (n_vis - 1) & 1);
+        tc_fence_after();
+      }
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* orow = out + (size_t)grow * out_ld + head * D;
+#pragma unroll
+      for (int u = 0; u < D / 32; ++u) {
+        uint32_t o[32];
+        if (n_vis > 0) {
+          tmem_ld_32x32b_x32(t_o + u * 32, o);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (valid) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint32_t ww[4];
+#pragma unroll
+            for (int h2 = 0; h2 < 4; ++h2)
+              ww[h2] = pack_bf16x2(__uint_as_float(o[v4 * 8 + h2 * 2]) * inv, __uint_as_float(o[v4 * 8 + h2 * 2 + 1]) * inv);
+            reinterpret_cast<uint4*>(orow + u * 32)[v4] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int debug_attn_flags() {     // VGPT_DEBUG_ATTN_FLAGS: timing probes only (results are garbage)
+  static const int f = [] { const char* e = getenv("VGPT_DEBUG_ATTN_FLAGS"); return e ? atoi(e) : 0; }();
+  return f;
+}
+
+template <int D>
+static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
+                            const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
+                            const void* seqs, int num_seqs, int q_pairs, const int32_t* q_code,
+                            const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles64, int H,
+                            float scale, cudaStream_t s) {
+  using C = PairCfg<D>;
+  const CUtensorMapSwizzle swz = (D == 96) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUtensorMap tq, tk, tv;
+  cuuint32_t estr[2] = {1, 1};
+  cuuint32_t box[2] = {(cuuint32_t)C::kCW, 128};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)q_ld, (cuuint64_t)q_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)q_ld * 2};
+    int rc = encode_tensor_map(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(q), dims, strides, box, estr, swz);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)total_pages * H * 128};
+    cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+    int rc = encode_tensor_map(&tk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(k_pool), dims, strides, box, estr, swz);
+    if (rc) return rc;
+    rc = encode_tensor_map(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(v_pool), dims, strides, box, estr, swz);
+    if (rc) return rc;
+  }
+  auto kern = attn_pair_tcgen05_kernel<D>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    attr_set = true;
+  }
+  dim3 grid(q_pairs, H, num_seqs);
+  kern<<<grid, kPairThreads, C::kSmem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
+                                            (const AttnSeqP*)seqs, q_code, k_code, k_tile_minmax,
+                                            max_k_tiles64, H, scale * 1.4426950408889634f, debug_attn_flags());
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
+int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
+                          const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
+                          const void* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
+                          const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H, int D,
+                          float scale, cudaStream_t s) {
+  VGPT_CHECK_ARG(q && out && k_pool && v_pool && page_table && seqs && q_code && k_code && k_tile_minmax,
+                 "vgpt_attn_clip_causal: null pointer");
+  VGPT_CHECK_ARG(H > 0 && (D == 64 || D == 96 || D == 128), "vgpt_attn_clip_causal: head_dim %d unsupported (64, 96, 128)", D);
+  VGPT_CHECK_ARG(q_ld % 8 == 0 && out_ld % 8 == 0 && q_ld >= H * D && out_ld >= H * D && q_rows > 0,
+                 "vgpt_attn_clip_causal: bad leading dimensions q_ld=%d out_ld=%d", q_ld, out_ld);
+  VGPT_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)k_pool & 127) == 0 &&
+                     ((uintptr_t)v_pool & 127) == 0,
+                 "vgpt_attn_clip_causal: misaligned pointer");
+  VGPT_CHECK_ARG(max_pages > 0 && total_pages > 0 && max_k_tiles >= 2 * max_pages,
+                 "vgpt_attn_clip_causal: max_k_tiles=%d too small for max_pages=%d", max_k_tiles, max_pages);
+  VGPT_CHECK_ARG(scale > 0.f, "vgpt_attn_clip_causal: scale must be positive");
+  VGPT_CHECK_ARG(max_pages <= kPairMaxTiles, "vgpt_attn_clip_causal: %d pages per sequence (at most %d)", max_pages, kPairMaxTiles);
+  if (num_seqs <= 0 || max_q_rows <= 0) return 0;
+  const int q_pairs = (max_q_rows + 2 * kPairBM - 1) / (2 * kPairBM);
+#define VGPT_ATTN_CASE(D_)                                                                               \
+  if (D == D_)                                                                                            \
+    return launch_attn_pair<D_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,   \
+                                max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,       \
+                                max_k_tiles, H, scale, s);
+  VGPT_ATTN_CASE(64)
+  VGPT_ATTN_CASE(96)
+  VGPT_ATTN_CASE(128)
+#undef VGPT_ATTN_CASE
+  return -1;
+}
+
+}  // namespace vgpt

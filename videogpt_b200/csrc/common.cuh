@@ -51,6 +51,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp (returns non-zero in exactly one lane).  Single-thread instructions
+// (tcgen05.mma / commit, TMA) are issued under `if (elect_one_sync())` inside warp-uniform control
+// flow: the compiler then keeps descriptors and addresses in uniform registers and emits the
+// instruction once, instead of the per-lane ELECT loop + R2UR moves it generates under a
+// divergent `if (lane == 0)` (about 14 instructions and ~100 cycles per tcgen05.mma -- slower than
+// the 48-64 cycles a 128 x 96..128 x 16 MMA takes to execute).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
@@ -75,6 +91,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking phase test (never suspends the thread): for event loops that watch several barriers
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)

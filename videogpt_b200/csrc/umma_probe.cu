@@ -147,4 +147,84 @@ int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, u
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Rate probe: how many SM cycles does one tcgen05.mma (M = 128, cta_group::1) of a given shape and
+// operand form really take when issued back to back?  One CTA per SM, operands resident (zeros),
+// no loads.  mode: 0 = SS, K-major, SW128; 1 = SS, K-major, SW64; 2 = TS (A in TMEM), B MN-major
+// SW128; 3 = TS, B MN-major SW64.  n_acc = 1: every MMA accumulates into the same tile (dependent
+// chain); 2: two tiles alternate.  out[cta] = cycles per MMA (clock64 around issue + completion).
+// Not on the hot path (tools/umma_rate.py; numbers in DESIGN.md).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(int mode, int N, int iters, int n_acc, int commit_every, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  for (int i = threadIdx.x; i < (96 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1 << 20); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  long long t0 = 0, t1 = 0;
+  if (warp == 0) {
+    const uint32_t a_addr = base, b_addr = base + 32 * 1024;
+    const bool ts = mode >= 2;
+    const bool sw64 = (mode & 1) != 0;
+    const uint32_t row_bytes = sw64 ? 64 : 128, layout = sw64 ? kLayoutSW64 : kLayoutSW128;
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, ts ? 1 : 0);
+    const int ksteps_per_chunk = row_bytes / 32;
+    t0 = clock64();
+    for (int it = 0; it < iters; it += 8) {
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = u % ksteps_per_chunk;
+          const uint32_t d = tmem + ((n_acc == 2 && (u & 1)) ? 128u : 0u);
+          if (!ts) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 8 * row_bytes, layout);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 8 * row_bytes, layout);
+            umma_f16_ss(d, da, db, idesc, 1u);
+          } else {
+            const uint64_t db = make_smem_desc(b_addr + (u & 3) * 16 * row_bytes, 128 * row_bytes, 8 * row_bytes, layout);
+            umma_f16_ts(d, tmem + 256 + (u & 7) * 8, db, idesc, 1u);
+          }
+          if (commit_every > 0 && (u + 1) % commit_every == 0) umma_commit(smem_u32(&bar2));   // nobody waits on it
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) umma_commit(smem_u32(&bar));
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)iters;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+int umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out, cudaStream_t s) {
+  VGPT_CHECK_ARG(out && mode >= 0 && mode <= 3 && N >= 16 && N <= 256 && N % 16 == 0 && iters >= 8 && iters % 8 == 0 &&
+                     (n_acc == 1 || (n_acc == 2 && N <= 128)) && ctas >= 1 && iters <= (1 << 19) &&
+                     (commit_every == 0 || 8 % commit_every == 0),
+                 "vgpt_debug_umma_rate: bad arguments");
+  const int smem = 96 * 1024 + 1024;
+  VGPT_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_kernel<<<ctas, 128, smem, s>>>(mode, N, iters, n_acc, commit_every, out);
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace vgpt

@@ -44,6 +44,11 @@ int attn_clip_causal_tc(const void* q, int q_ld, int q_rows, void* out, int out_
                         const void* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
                         const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H, int D,
                         float scale, cudaStream_t s);
+int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
+                          const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
+                          const void* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
+                          const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H, int D,
+                          float scale, cudaStream_t s);
 int embed_assemble(void* hidden, int rows, int hs, const int32_t* kind, const int32_t* a,
                    const int32_t* b, const void* embed_tokens, const void* time_tokens, const void* z,
                    const void* ctx, int C, int lat_h, int lat_w, const void* wx, const void* bx,
@@ -69,6 +74,7 @@ int cfg_combine(void* pred, int half_numel, float guidance, cudaStream_t s);
 int mask_from_codes(const int32_t* qc, const int32_t* kc, void* out, int Lq, int Lk, cudaStream_t s);
 int umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes, uint64_t b_desc_base,
                   uint32_t idesc, int k_steps, uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s);
+int umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out, cudaStream_t s);
 int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t a_desc_base,
                uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t a_step_bytes,
                uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s);

@@ -332,6 +332,11 @@ class NextClipEngine:
         self.use_cuda_graph = use_cuda_graph
         self.peers = peers
         self._kv_shared = self._pred_shared = None
+        # True when the caller guarantees that every latent carries the same timestep (the fused
+        # sampler loop: scheduler.py:171 builds `timesteps` from one sigma): the three small MLPs
+        # then run on ONE row and the result is replicated -- identical numbers, 1/n of the work.
+        self.uniform_t = False
+        self._graph_uniform = None
         self.plan: Optional[ClipPlan] = None
         self._graph = None
         self._rope_tab = None
@@ -412,12 +417,18 @@ class NextClipEngine:
     def _time_embeddings(self, n: int):
         """time_token / t_embedder MLPs and the adaLN modulation (LVM/model.py:420, 480, 80)."""
         w = self.w
+        full_n = n
+        if self.uniform_t:
+            n = 1
         ops.timestep_sinusoid(self.t[:n], self._t_freqs, self.t_sin[:n])
         ops.linear_small(self.t_sin[:n], w.time_token[0], w.time_token[1], post_silu=True, out=self.t_h1[:n])
         ops.linear_small(self.t_h1[:n], w.time_token[2], w.time_token[3], out=self.time_tokens[:n])
         ops.linear_small(self.t_sin[:n], w.t_embedder[0], w.t_embedder[1], post_silu=True, out=self.t_h1[:n])
         ops.linear_small(self.t_h1[:n], w.t_embedder[2], w.t_embedder[3], out=self.t_emb[:n])
         ops.linear_small(self.t_emb[:n], w.ada_w, w.ada_b, pre_silu=True, out=self.mod[:n])
+        if full_n > n:                       # replicate row 0 (device-to-device copies, graph capturable)
+            self.time_tokens[1:full_n].copy_(self.time_tokens[0:1].expand(full_n - 1, -1))
+            self.mod[1:full_n].copy_(self.mod[0:1].expand(full_n - 1, -1))
 
     def _assemble(self, ph: PhaseArrays):
         w = self.w
@@ -516,7 +527,8 @@ class NextClipEngine:
         if not self.use_cuda_graph:
             self._drive(self._predict_kernels())
             return self.pred
-        if self._graph is None:
+        if self._graph is None or self._graph_uniform != self.uniform_t:
+            self._graph_uniform = self.uniform_t
             self._drive(self._predict_kernels())   # warm-up (sets function attributes, fills caches)
             torch.cuda.synchronize()
             if self.peers is not None:
@@ -532,6 +544,8 @@ class NextClipEngine:
 
     @property
     def launches_per_predict(self) -> int:
+        """Kernels of this library per predict() (torch's two replicate copies under uniform_t are
+        not counted)."""
         sync = (self.L + 1) if self.peers is not None and not self.peers.lockstep else 0
         return 6 + 1 + 8 * self.L + 2 + sync
 

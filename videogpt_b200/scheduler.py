@@ -62,14 +62,18 @@ class LVMScheduler:
         use_cfg = bool(mk["use_img_cfg"])
         e.z.copy_(torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0) if is_list else z)
         vel = torch.empty_like(e.z[: n // 2 if use_cfg else n]) if self.record_velocity is not None else None
-        for i in range(self.num_steps):
-            e.t.fill_(float(self.sigma[i]))
-            e.predict()
-            oms, ds = self._scalars(i)
-            ops.cfg_euler(e.z, e.pred, use_cfg, prediction_type == "x1", oms, ds,
-                          float(mk["img_cfg_scale"]), vel_out=vel)
-            if vel is not None:
-                self.record_velocity.append(vel.clone())
+        e.uniform_t = True              # one sigma for every latent (scheduler.py:171)
+        try:
+            for i in range(self.num_steps):
+                e.t.fill_(float(self.sigma[i]))
+                e.predict()
+                oms, ds = self._scalars(i)
+                ops.cfg_euler(e.z, e.pred, use_cfg, prediction_type == "x1", oms, ds,
+                              float(mk["img_cfg_scale"]), vel_out=vel)
+                if vel is not None:
+                    self.record_velocity.append(vel.clone())
+        finally:
+            e.uniform_t = False
         if not is_list:
             return e.z.clone()
         out = [e.z[i:i + 1].clone() for i in range(n)]
