@@ -44,8 +44,10 @@ const char* vgpt_last_error(void);
  * (C = bf16(A W^T) + R, R may alias C: the in-place residual stream of Phi3DecoderLayer);
  * VGPT_EPI_SWIGLU (W packed by vgpt_pack_gate_up, C[M,N/2] = up * silu(gate)).
  * K % 64 == 0, N % 64 == 0.  cta_pair 1 = CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles,
- * block_n 128/192/256), 0 = single CTAs (128 x block_n, block_n 128/256), -1 = tuned default;
- * block_n 0 = tuned default. */
+ * block_n 128/192/256), 0 = single CTAs (128 x block_n, block_n 128/256), -1 = tuned default,
+ * 2 = CTA pairs + the swapped-operand skinny kernel for an M % 256 <= 32 tail (EXPERIMENTAL, not yet
+ * validated on hardware; needs N % 256 == 0 and block_n 0; the tuned default only uses it when
+ * VGPT_GEMM_SKINNY_TAIL=1 is set); block_n 0 = tuned default. */
 int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
                    int ldc, int epilogue, int block_n, int cta_pair, void* stream);
 

@@ -157,10 +157,13 @@ rope_kv_append_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict
       *reinterpret_cast<uint4*>(p + half) = vhi;
     } else if (slot >= 0) {
       const size_t o = pool_off + (size_t)h * page_tokens * D + c * 8;
-      for (int g = 0; g < n_pools; ++g) {            // own pool + every peer's (NVLink stores)
-        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(k_pools.p[g]) + o;
-        *reinterpret_cast<uint4*>(d) = vlo;
-        *reinterpret_cast<uint4*>(d + half) = vhi;
+#pragma unroll
+      for (int g = 0; g < kMaxPeers; ++g) {          // own pool + every peer's (NVLink stores)
+        if (g < n_pools) {                           // (unrolled: the pointers stay in constant memory)
+          __nv_bfloat16* d = static_cast<__nv_bfloat16*>(k_pools.p[g]) + o;
+          *reinterpret_cast<uint4*>(d) = vlo;
+          *reinterpret_cast<uint4*>(d + half) = vhi;
+        }
       }
     }
   }
@@ -170,8 +173,9 @@ rope_kv_append_kernel(__nv_bfloat16* __restrict__ qkv, const int32_t* __restrict
       const int h = it / dc, c = it % dc;
       const uint4 v = *reinterpret_cast<const uint4*>(base + 2 * HD + h * D + c * 8);
       const size_t o = pool_off + (size_t)h * page_tokens * D + c * 8;
-      for (int g = 0; g < n_pools; ++g)
-        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(v_pools.p[g]) + o) = v;
+#pragma unroll
+      for (int g = 0; g < kMaxPeers; ++g)
+        if (g < n_pools) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(v_pools.p[g]) + o) = v;
     }
   }
 }
@@ -466,7 +470,9 @@ final_layer_kernel(const __nv_bfloat16* __restrict__ hidden, int hs,
     const int p = f / (2 * C), q = (f / C) & 1, c = f % C;     // feature order (p, q, c)
     const size_t o = (((size_t)j * C + c) * lat_h + 2 * py + p) * lat_w + 2 * px + q;
     const __nv_bfloat16 r = __float2bfloat16_rn(v);
-    for (int g = 0; g < n_preds; ++g) static_cast<__nv_bfloat16*>(preds.p[g])[o] = r;
+#pragma unroll
+    for (int g = 0; g < kMaxPeers; ++g)
+      if (g < n_preds) static_cast<__nv_bfloat16*>(preds.p[g])[o] = r;
   }
 }
 

@@ -84,6 +84,15 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols)
@@ -280,6 +289,175 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Skinny tail GEMM: the last M % 256 <= T rows of a projection (the 16 tag / time-slot rows that
+// make M = 2064 = 8 x 256 + 16 at cfg2 would otherwise cost a ninth, almost empty row of 256-row
+// tiles -- 11 % of all tiles and, for qkv / gate_up, a whole extra wave).  Operands swapped:
+//     C_tail^T[N, T] = W[N, K] * A_tail[T, K]^T
+// so the WEIGHT tile is the M = 256 operand of tcgen05.mma.cta_group::2 (128 rows per CTA), the T
+// tail rows are the N = T operand (T/2 rows per CTA), and the accumulator holds the tail
+// transposed (TMEM lane = output column, TMEM column = tail row).  The MMAs are tiny (N = 16);
+// the kernel streams W once at the L2 -> SMEM fill rate.  Same epilogues; for SwiGLU the gate and
+// up halves of an output land in neighbouring warps and are exchanged through shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int T>
+struct SkinnyCfg {
+  static constexpr int kABytes = kG2BlockM * kG2BlockK * 2;          // 128 weight rows x 64 k
+  static constexpr int kBBytes = (T / 2) * kG2BlockK * 2;            // this CTA's half of the tail rows
+  static constexpr int kStageBytes = kABytes + ((kBBytes + 1023) / 1024) * 1024;
+  static constexpr int kStages = 8;
+  static constexpr int kTmemCols = (2 * T < 32) ? 32 : 2 * T;
+  static constexpr int kXchgBytes = 2 * T * 32 * 4;                  // SwiGLU: up values of two warp pairs
+  static constexpr int kSmemBytes = kStages * kStageBytes + 512 + kXchgBytes + 1024;
+};
+
+template <int T, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
+gemm_bf16_skinny_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+                             __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ R, int rows, int N,
+                             int K, int ldc) {
+  using Cfg = SkinnyCfg<T>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* xchg = reinterpret_cast<float*>(smem_raw + (bar_base + 512 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = N / (2 * kG2BlockM);          // 256 output columns per tile
+  const int k_blocks = K / kG2BlockK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_a);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar(s), 1); mbar_init(tmem_empty_bar(s), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int n0 = tile * 2 * kG2BlockM + rank * kG2BlockM;         // this CTA's 128 weight rows
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * (Cfg::kABytes + Cfg::kBBytes));
+          tma_load_2d_pair(sa, &tmap_w, full_bar(stage), kb * kG2BlockK, n0);
+          tma_load_2d_pair(sb, &tmap_a, full_bar(stage), kb * kG2BlockK, (int)rank * (T / 2));
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader only) ================================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kG2BlockM, T);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+        const int as = local & 1;
+        mbar_wait(tmem_empty_bar(as), ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * T;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+            const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+            const uint64_t db = make_smem_desc(sa + Cfg::kABytes, 16, 1024, kLayoutSW128);
+#pragma unroll
+            for (int k = 0; k < kG2BlockK / 16; ++k)
+              umma_f16_ss_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(empty_bar(stage));
+            if (kb == k_blocks - 1) umma_commit_pair(tmem_full_bar(as));
+          }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ============== epilogue (both CTAs): TMEM lane = output column, column = tail row ==============
+    const int quad = warp & 3;
+    int local = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
+      const int as = local & 1;
+      mbar_wait(tmem_full_bar(as), (local >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[T];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * T;
+      if constexpr (T == 16) {
+        tmem_ld_32x32b_x16(taddr, acc);
+      } else {
+        tmem_ld_32x32b_x32(taddr, acc);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(as), 0);      // accumulator drained
+      const int n = tile * 2 * kG2BlockM + (int)rank * kG2BlockM + quad * 32 + lane;   // weight row = output column
+      if constexpr (EPI == kG2SwiGLU) {
+        // packed rows: [gate x 32 | up x 32] per 64 -> even warps hold gate, odd warps the matching up
+        float* x = xchg + (quad >> 1) * T * 32;
+        if (quad & 1) {
+#pragma unroll
+          for (int j = 0; j < T; ++j) x[j * 32 + lane] = __uint_as_float(acc[j]);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (quad >> 1)) : "memory");
+        if (!(quad & 1)) {
+          const int oc = (tile * 2 * kG2BlockM + (int)rank * kG2BlockM) / 2 + (quad >> 1) * 32 + lane;
+#pragma unroll
+          for (int j = 0; j < T; ++j) {
+            if (j < rows) {
+              const float gv = rbf(__uint_as_float(acc[j]));
+              const float uv = rbf(x[j * 32 + lane]);
+              C[(size_t)j * ldc + oc] = __float2bfloat16_rn(uv * rbf(silu_f(gv)));
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (quad >> 1)) : "memory");      // x reusable for the next tile
+      } else {
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+          if (j < rows) {
+            float v = __uint_as_float(acc[j]);
+            if constexpr (EPI == kG2Residual) v = rbf(v) + __bfloat162float(R[(size_t)j * ldc + n]);
+            C[(size_t)j * ldc + n] = __float2bfloat16_rn(v);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI>
@@ -316,6 +494,62 @@ static int launch_gemm2(const void* A, const void* W, void* C, const void* R, in
                                                              debug_gemm_flags());
   VGPT_CHECK_LAUNCH();
   return 0;
+}
+
+
+template <int T, int EPI>
+static int launch_skinny(const void* A_tail, const void* W, void* C_tail, const void* R_tail, int rows, int N, int K,
+                         int lda, int ldc, int num_sms, cudaStream_t stream) {
+  using Cfg = SkinnyCfg<T>;
+  CUtensorMap tw, ta;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {kG2BlockK, kG2BlockM}, estr[2] = {1, 1};
+    int rc = encode_tensor_map(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box,
+                               estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};           // rows beyond `rows` are zero-filled
+    cuuint64_t strides[1] = {(cuuint64_t)lda * 2};
+    cuuint32_t box[2] = {kG2BlockK, T / 2}, estr[2] = {1, 1};
+    int rc = encode_tensor_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(A_tail), dims, strides, box,
+                               estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  auto kern = gemm_bf16_skinny_pair_kernel<T, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = N / (2 * kG2BlockM);
+  const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  kern<<<2 * clusters, kG2Threads, Cfg::kSmemBytes, stream>>>(tw, ta, static_cast<__nv_bfloat16*>(C_tail),
+                                                             static_cast<const __nv_bfloat16*>(R_tail), rows, N, K, ldc);
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
+// rows <= 32 tail rows of a projection (A_tail / C_tail / R_tail point at the first tail row).
+int gemm_bf16_skinny(const void* A_tail, const void* W, void* C_tail, const void* R_tail, int rows, int N, int K,
+                     int lda, int ldc, int epilogue, cudaStream_t stream) {
+  VGPT_CHECK_ARG(rows > 0 && rows <= 32 && N % 256 == 0 && K % kG2BlockK == 0,
+                 "vgpt_gemm_bf16: skinny tail needs rows <= 32, N %% 256 == 0 (rows=%d N=%d)", rows, N);
+  const int sms = device_sm_count();
+#define VGPT_SKINNY_CASE(T_, EPI_) \
+  if ((rows <= 16) == (T_ == 16) && epilogue == EPI_) \
+    return launch_skinny<T_, EPI_>(A_tail, W, C_tail, R_tail, rows, N, K, lda, ldc, sms, stream);
+  VGPT_SKINNY_CASE(16, kG2Store)
+  VGPT_SKINNY_CASE(16, kG2Residual)
+  VGPT_SKINNY_CASE(16, kG2SwiGLU)
+  VGPT_SKINNY_CASE(32, kG2Store)
+  VGPT_SKINNY_CASE(32, kG2Residual)
+  VGPT_SKINNY_CASE(32, kG2SwiGLU)
+#undef VGPT_SKINNY_CASE
+  set_last_error("vgpt_gemm_bf16: no skinny kernel for epilogue=%d", epilogue);
+  return -1;
 }
 
 int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,

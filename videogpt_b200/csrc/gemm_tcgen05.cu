@@ -308,7 +308,38 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
                  "vgpt_gemm_bf16: pointers must be 16-byte aligned");
   VGPT_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "vgpt_gemm_bf16: unknown epilogue %d", epilogue);
   VGPT_CHECK_ARG(epilogue != kEpiResidual || R, "vgpt_gemm_bf16: residual epilogue needs R");
+  const bool auto_pair = cta_pair < 0;
   if (cta_pair < 0) cta_pair = kDefaultCtaPair;
+  // Skinny tail, EXPERIMENTAL (written after this round's GPU budget was spent: compiled, never run
+  // on hardware).  Reached only with cta_pair == 2, or from the tuned default when the environment
+  // sets VGPT_GEMM_SKINNY_TAIL=1.  When M = q * 256 + tail with tail <= 32, the tail rows go to the
+  // swapped-operand kernel (gemm2_tcgen05.cu) and the main kernel loses its last, almost empty row
+  // of tiles -- taken when that saves at least one wave of the main kernel.
+  static const bool skinny_opt_in = [] { const char* e = getenv("VGPT_GEMM_SKINNY_TAIL"); return e && e[0] == '1'; }();
+  const int tail = M % 256;
+  if ((cta_pair == 2 || (auto_pair && skinny_opt_in)) && tail > 0 && tail <= 32 && M > 256 && N % 256 == 0 &&
+      block_n == 0) {
+    const int sms = device_sm_count();
+    bool split = cta_pair == 2;
+    if (!split) {
+      const int clusters = sms / 2;
+      auto waves = [&](int rows, int bn) { return (((rows + 255) / 256) * ((N + bn - 1) / bn) + clusters - 1) / clusters; };
+      const int bn_full = pick_pair_block_n(M, N, sms), bn_main = pick_pair_block_n(M - tail, N, sms);
+      const double cost_full = waves(M, bn_full) * bn_full / (bn_full == 256 ? 1.0 : 0.88);
+      const double cost_main = waves(M - tail, bn_main) * bn_main / (bn_main == 256 ? 1.0 : 0.88);
+      split = cost_main + 0.5 * 256 < cost_full;       // the tail kernel costs about half a 256-wide tile
+    }
+    if (split) {
+      const int rows_main = M - tail;
+      int rc = gemm_bf16_pair(A, W, C, R, rows_main, N, K, lda, ldc, epilogue, pick_pair_block_n(rows_main, N, sms), stream);
+      if (rc) return rc;
+      const __nv_bfloat16* a_tail = static_cast<const __nv_bfloat16*>(A) + (size_t)rows_main * lda;
+      __nv_bfloat16* c_tail = static_cast<__nv_bfloat16*>(C) + (size_t)rows_main * ldc;
+      const __nv_bfloat16* r_tail = R ? static_cast<const __nv_bfloat16*>(R) + (size_t)rows_main * ldc : nullptr;
+      return gemm_bf16_skinny(a_tail, W, c_tail, r_tail, tail, N, K, lda, ldc, epilogue, stream);
+    }
+  }
+  if (cta_pair == 2) cta_pair = 1;
   if (block_n == 0) block_n = cta_pair ? pick_pair_block_n(M, N, device_sm_count()) : ((N % 256 == 0) ? 256 : 128);
   if (cta_pair) {
     VGPT_CHECK_ARG(block_n == 128 || block_n == 192 || block_n == 256,

@@ -28,6 +28,8 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
 int debug_gemm_flags();
 int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
                    int epilogue, int block_n, cudaStream_t stream);
+int gemm_bf16_skinny(const void* A_tail, const void* W, void* C_tail, const void* R_tail, int rows, int N, int K,
+                     int lda, int ldc, int epilogue, cudaStream_t stream);
 int pack_gate_up(const void* w, void* packed, int I, int K, cudaStream_t s);
 int rmsnorm(const void* x, const void* w, void* y, int rows, int hidden, float eps, cudaStream_t s);
 int rope_table(const float* inv_freq, void* tab, int max_pos, int head_dim, cudaStream_t s);
