@@ -313,7 +313,11 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_pair_kernel (qkv/o/gate_up/down, M=%d)" % gemm_rows,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, kernel timed alone)" if peaks else "fallback 1590",
-                "traffic": None, "avg_launch_us": sec * 1e6, "launches_timed": n_launch,
+                # DRAM read + write bytes of ONE qkv launch (M=2064, N=9216, K=3072) from the ncu --set full
+                # capture profiles/r01c_gemm_pair_serialised_remote_arrive_ncu.txt (107 MB algorithmic)
+                "traffic": (69363712 + 16023808) if gemm_rows == 2064 else None,
+                "traffic_note": "dram__bytes_read+write of one qkv launch, ncu --set full (profiles/r01c_gemm_pair_*_ncu.txt)",
+                "avg_launch_us": sec * 1e6, "launches_timed": n_launch,
                 "whole_clip_tflops": clip_fl * args.steps / dt / 1e12,
                 "whole_clip_frac_of_sustained": clip_fl * args.steps / dt / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
 

@@ -183,3 +183,51 @@ def test_single_frame_path_dryrun(dry):
     assert out.shape == (2, 4, 8, 8)
     pred, cache = m.forward_with_cfg(z, torch.full((2,), 0.5), past_key_values=None, prediction_type="v", **mk)
     assert cache is None and pred.shape == (2, 4, 8, 8)
+
+
+# ------------------------------------------------------------------------------------------------
+# sequence-parallel host logic, dry (stub kernels, CPU): every rank of a group must enqueue the SAME
+# number of cross-GPU barriers in the same places, whatever the geometry / world size -- a mismatch
+# would dead-lock real ranks.  (BASELINE configs[1], [2], [4] geometries at 2 / 4 / 8 ranks.)
+# ------------------------------------------------------------------------------------------------
+class StubOpsSP(StubOps):
+    def rope_kv_append_peers(self, qkv, row_pos, row_slot, table, k_ptrs, v_ptrs, n_pools, heads, head_dim):
+        self._log("rope_kv_append_peers")
+        assert row_pos.numel() == row_slot.numel() == qkv.shape[0] and len(k_ptrs) == len(v_ptrs) == n_pools
+
+    def final_layer_rows(self, hidden, kind, a, b, mod, w, bias, pred_ptrs, n_preds, lat_h, lat_w):
+        self._log("final_layer_rows")
+        assert kind.numel() == hidden.shape[0] and len(pred_ptrs) == n_preds
+
+
+@pytest.mark.parametrize("geom", [(4, 4, 256, 256), (32, 4, 256, 256), (4, 4, 512, 512), (1, 1, 64, 64)])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sequence_parallel_ranks_agree_on_sync_points(monkeypatch, geom, world):
+    from videogpt_b200 import engine as eng, peer
+    stub = StubOpsSP()
+    monkeypatch.setattr(eng, "ops", stub)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    n_ctx, n_gen, H, W = geom
+    dims = synth.REDUCED
+    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+    specs, n_lat, n_ctx_lat = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
+                                                   d["denoise_image_sizes"], d["time_emb_inx"])
+    sd = {k: v.to(BF) for k, v in synth.init_state_dict(dims, seed=0, with_pos_embed=False).items()}
+    w = eng.EngineWeights(sd, dims.num_hidden_layers, "cpu")
+    members = peer.LocalPeerGroup.create(world, "cpu")
+    traces = []
+    for r, m in enumerate(members):
+        e = eng.NextClipEngine(w, dims.hidden_size, dims.intermediate_size, dims.num_hidden_layers,
+                               dims.num_attention_heads, dims.rms_norm_eps, dims.rope_theta, "cpu",
+                               dims.pos_embed_max_size, 2, use_cuda_graph=False, peers=m)
+        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu", shard=(r, world)))
+        assert e.kv.shape[2] == e.plan.total_pages and e.pred.shape == e.z.shape
+        pre = list(e.prefill_steps(None))
+        step = list(e.predict_steps())
+        traces.append((pre, step, e.plan.prefix.rows, e.plan.step.rows))
+    L = dims.num_hidden_layers
+    for pre, step, _, _ in traces:
+        assert pre == (["kv"] * L if n_ctx else [])                 # one barrier per layer's K/V append
+        assert step == ["kv"] * L + ["pred"]                        # + one for the prediction
+    assert sum(t[2] for t in traces) == sum(sp.n_prefix for sp in specs)
+    assert sum(t[3] for t in traces) == sum(sp.n_active for sp in specs)
