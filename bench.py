@@ -356,6 +356,9 @@ def main():
                          "sp = sequence parallel groups of --sp ranks per video")
     ap.add_argument("--sp", type=int, default=0, help="ranks per sequence-parallel group (default: all)")
     args = ap.parse_args()
+    if os.environ.get("VGPT_FAULT_DUMP"):      # debugging aid: dump every thread's stack after N seconds and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["VGPT_FAULT_DUMP"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
