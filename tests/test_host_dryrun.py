@@ -231,3 +231,32 @@ def test_sequence_parallel_ranks_agree_on_sync_points(monkeypatch, geom, world):
         assert step == ["kv"] * L + ["pred"]                        # + one for the prediction
     assert sum(t[2] for t in traces) == sum(sp.n_prefix for sp in specs)
     assert sum(t[3] for t in traces) == sum(sp.n_active for sp in specs)
+
+
+def test_plan_cache_keeps_its_key_objects_alive(dry):
+    """The per-clip cache key identifies the conditioning tensors by object; the model must hold
+    them, otherwise the allocator hands the freed address to the NEXT clip's context and a stale
+    prefill (old context K/V) would be reused silently."""
+    import gc
+    import weakref
+    from videogpt_b200 import LVMScheduler
+    m = _model()
+    mk, z0 = _mk(2, 2, 64, 64)
+    probe = weakref.ref(mk["input_img_latents"][0])
+    LVMScheduler(num_steps=1)([x.clone() for x in z0] * 2, m.frame_block_forward_with_cfg, mk, prediction_type="x1")
+    n_prefill = dry.calls.count("rope_kv_append")
+    ids, pos = mk["input_ids"], mk["position_ids"]
+    del mk
+    gc.collect()
+    assert probe() is not None                       # still referenced by the model's cache
+    # a new clip with NEW tensor objects (same values, same layout) must prefill again
+    mk2, _ = _mk(2, 2, 64, 64)
+    mk2["input_ids"], mk2["position_ids"] = ids, pos
+    LVMScheduler(num_steps=1)([x.clone() for x in z0] * 2, m.frame_block_forward_with_cfg, mk2, prediction_type="x1")
+    L = 2
+    assert dry.calls.count("rope_kv_append") == n_prefill + L + L      # prefill (L) + one step (L)
+    # the same objects again (every Euler step of one clip through the callback seam): no new prefill
+    before = dry.calls.count("rope_kv_append")
+    m.frame_block_forward_with_cfg([x.clone() for x in z0] * 2, torch.full((4,), 0.5), past_key_values=None,
+                                   prediction_type="x1", **mk2)
+    assert dry.calls.count("rope_kv_append") == before + L

@@ -153,6 +153,7 @@ class LVM(nn.Module):
         self._engine_key = None
         self._plan_key = None
         self._layout_key = None
+        self._plan_refs = None
         self._peers = None
         self.use_cuda_graph = True
 
@@ -256,10 +257,16 @@ class LVM(nn.Module):
 
     @staticmethod
     def _identity(*objs):
-        """Cheap identity of (nested) conditioning inputs: tensors by storage + version."""
+        """Identity of (nested) conditioning inputs: tensors by OBJECT (id + storage + version).
+
+        Valid only while the objects are alive -- an address or id freed by one clip is routinely
+        handed to the next clip's tensors by the allocator -- so whoever stores an identity as a
+        cache key must also keep the objects (``_plan_refs``).  A hit then means "the very same,
+        unmodified tensors", which is also the same decision on every rank of a sequence-parallel
+        group (it does not depend on any rank's allocator state)."""
         def freeze(o):
             if torch.is_tensor(o):
-                return (o.data_ptr(), tuple(o.shape), o._version)
+                return (id(o), o.data_ptr(), tuple(o.shape), o._version)
             if isinstance(o, (list, tuple)):
                 return tuple(freeze(x) for x in o)
             if isinstance(o, dict):
@@ -297,6 +304,7 @@ class LVM(nn.Module):
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)
         self._plan_key = ident
+        self._plan_refs = (input_ids, position_ids, input_img_latents, attention_mask)   # keep the key's objects alive
         return e
 
     @staticmethod
@@ -383,6 +391,7 @@ class LVM(nn.Module):
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)
         self._plan_key = ident
+        self._plan_refs = (input_ids, position_ids, input_img_latents, attention_mask)
         return e
 
     @torch.no_grad()
