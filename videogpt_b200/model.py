@@ -304,7 +304,7 @@ class LVM(nn.Module):
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)
         self._plan_key = ident
-        self._plan_refs = (input_ids, position_ids, input_img_latents, attention_mask)   # keep the key's objects alive
+        self._plan_refs = (input_ids, position_ids, list(input_img_latents or []), attention_mask)   # keep the key's objects alive
         return e
 
     @staticmethod
@@ -391,7 +391,7 @@ class LVM(nn.Module):
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)
         self._plan_key = ident
-        self._plan_refs = (input_ids, position_ids, input_img_latents, attention_mask)
+        self._plan_refs = (input_ids, position_ids, list(input_img_latents or []), attention_mask)
         return e
 
     @torch.no_grad()
