@@ -177,7 +177,8 @@ int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img,
                              float* d_out, int n_cols, void* stream);
 
 /* Test / tuning hook: cycles per back-to-back tcgen05.mma (M = 128, cta_group::1, bf16) of width N.
- * mode 0 = SS K-major SW128, 1 = SS K-major SW64, 2 = TS + MN-major SW128 B, 3 = TS + MN-major SW64 B;
+ * mode 0 = SS K-major SW128, 1 = SS K-major SW64, 2 = TS + MN-major SW128 B, 3 = TS + MN-major SW64 B,
+ * 4 = CTA pairs (cta_group::2, M = 256, SS K-major SW128; `ctas` = clusters; not yet run on hardware);
  * n_acc = 1 dependent chain, 2 alternating accumulators; commit_every = 0 / 1 / 2 / 4 / 8: a tcgen05.commit
  * after every that many MMAs; out[ctas] = cycles per MMA per CTA. */
 int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out,

@@ -215,13 +215,69 @@ umma_rate_kernel(int mode, int N, int iters, int n_acc, int commit_every, float*
   }
 }
 
+// Same probe for CTA pairs (tcgen05.mma.cta_group::2, M = 256 over two SMs, SS form, K-major
+// SW128): the production GEMM's instruction.  out[cluster] = cycles per MMA seen by the leader.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_rate_pair_kernel(int N, int iters, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  for (int i = threadIdx.x; i < (64 * 1024) / 16; i += blockDim.x) reinterpret_cast<uint4*>(gen)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  const int warp = threadIdx.x >> 5;
+  const bool leader = cluster_ctarank() == 0;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc_pair<512>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 0) {
+    long long t0 = clock64();
+    if (leader) {
+      const uint32_t idesc = make_idesc_bf16(256, N);
+      for (int it = 0; it < iters; it += 8) {
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint64_t da = make_smem_desc(base + (u & 3) * 32, 16, 1024, kLayoutSW128);
+            const uint64_t db = make_smem_desc(base + 32 * 1024 + (u & 3) * 32, 16, 1024, kLayoutSW128);
+            umma_f16_ss_pair(tmem, da, db, idesc, 1u);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one_sync()) umma_commit_pair(smem_u32(&bar));
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (leader && threadIdx.x == 0) out[blockIdx.x >> 1] = (float)(t1 - t0) / (float)iters;
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem);
+  }
+}
+
 int umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out, cudaStream_t s) {
-  VGPT_CHECK_ARG(out && mode >= 0 && mode <= 3 && N >= 16 && N <= 256 && N % 16 == 0 && iters >= 8 && iters % 8 == 0 &&
+  VGPT_CHECK_ARG(out && mode >= 0 && mode <= 4 && N >= 16 && N <= 256 && N % 16 == 0 && iters >= 8 && iters % 8 == 0 &&
                      (n_acc == 1 || (n_acc == 2 && N <= 128)) && ctas >= 1 && iters <= (1 << 19) &&
                      (commit_every == 0 || 8 % commit_every == 0),
                  "vgpt_debug_umma_rate: bad arguments");
   const int smem = 96 * 1024 + 1024;
   VGPT_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (mode == 4) {                       // CTA pairs: `ctas` = number of clusters
+    const int smem2 = 64 * 1024 + 1024;
+    VGPT_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    umma_rate_pair_kernel<<<2 * ctas, 128, smem2, s>>>(N, iters, out);
+    VGPT_CHECK_LAUNCH();
+    return 0;
+  }
   umma_rate_kernel<<<ctas, 128, smem, s>>>(mode, N, iters, n_acc, commit_every, out);
   VGPT_CHECK_LAUNCH();
   return 0;
