@@ -10,8 +10,10 @@ on the transformer data path:
   quirk q9, so K/V are never shareable).  Per Euler step the two ranks exchange ONE tensor -- the
   raw prediction, ``n_gen x 4 x h/8 x w/8`` bf16 (32 KB at 256x256) -- with an all-gather, then
   both apply the same x1->v / CFG / Euler update, so their latents stay bit-identical.
-* **sequence** (long contexts): contiguous token chunks per rank like the reference
-  (``LVM/model.py:459-464``) with a per-layer K/V all-gather; planned, see DESIGN.md.
+* **sequence** (long contexts / one video on several GPUs): rows of every sequence are dealt to
+  the ranks of ``hccl_info.group`` (the reference's switch, ``LVM/model.py:459-464``); the K/V
+  all-gather is fused into the producing kernels as NVLink peer stores (``peer.py``,
+  ``csrc/peer.cu``).  It lives in the engine / model, not here: see DESIGN.md section 7.
 
 The reference's own multi-GPU inference is DeepSpeed-Ulysses all-to-all (4 collectives per
 layer, ``LVM/transform/sdpa_transform.py:126-156``).
