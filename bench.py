@@ -176,6 +176,37 @@ def cpu_reference_sample(dims, n_ctx, n_gen, height, width, euler_steps, layers_
     return tokens / (per_step * euler_steps), desc, dt
 
 
+def gpu_eager_oracle(model, dims, n_ctx, n_gen, height, width, dev, reps=3):
+    """The reference's own PyTorch path (oracle restatement: every context row recomputed, padded
+    unconditional row, dense additive mask, cuBLAS + SDPA, bf16 eager) on the SAME GPU with the same
+    weights: seconds per Euler step.  SURVEY.md 8(d) names this, not the CPU number, as the kernel
+    bar.  A baseline that is measured, never the product path."""
+    from oracle import model_oracle as mo, processor_oracle as po
+    from videogpt_b200 import synth
+    bf = torch.bfloat16
+    w = dict(model.state_dict())
+    if w.get("pos_embed") is None:
+        w["pos_embed"] = torch.zeros(1, dims.pos_embed_max_size ** 2, dims.hidden_size, device=dev, dtype=bf)
+    cfg = mo.OracleConfig(hidden_size=dims.hidden_size, intermediate_size=dims.intermediate_size,
+                          num_hidden_layers=dims.num_hidden_layers, num_attention_heads=dims.num_attention_heads)
+    d = po.frame_block_inputs(n_ctx, n_gen, height, width, True, 1)
+    lat = [x.to(dev, bf) for x in synth.synthetic_latents(n_ctx + n_gen, height, width, seed=42)]
+    args = (d["input_ids"].to(dev), lat[:n_ctx], d["input_image_sizes"], d["attention_mask"].to(dev),
+            d["position_ids"].to(dev), d["denoise_image_sizes"], d["time_emb_inx"])
+    z = lat[n_ctx:] * 2
+    t = torch.full((len(z),), 0.5, device=dev)
+    with torch.no_grad():
+        mo.frame_block_forward(w, cfg, z, t, *args)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            mo.frame_block_forward(w, cfg, z, t, *args)
+        e.record()
+        torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e-3 / reps
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -321,6 +352,17 @@ def run_ours(args, rank, world, local_rank):
                 "whole_clip_tflops": clip_fl * args.steps / dt / 1e12,
                 "whole_clip_frac_of_sustained": clip_fl * args.steps / dt / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
 
+    gpu_eager = None
+    if world == 1 and kind == "full":
+        try:      # the reference path as written, eager bf16 on this GPU (reported next to ours)
+            sec_step = gpu_eager_oracle(model, dims, n_ctx, n_gen, H, W, dev)
+            gpu_eager = {"value": 2 * n_gen * block / sec_step, "unit": "tokens/s", "ms_per_euler_step": 1e3 * sec_step,
+                         "s_per_clip_extrapolated": sec_step * euler,
+                         "kind": "oracle port of the reference path, bf16 eager on the same GPU (cuBLAS + SDPA with the "
+                                 "dense mask, no KV cache, padded unconditional row); one Euler step timed x3"}
+        except Exception as exc:                      # a baseline must never cost the bench line
+            gpu_eager = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+        torch.cuda.empty_cache()
     threads = os.cpu_count() or 1
     cpu_v, cpu_desc, _ = cpu_reference_sample(dims, n_ctx, n_gen, H, W, euler, 8 if kind == "full" else dims.num_hidden_layers, threads)
     lat_bytes = 4 * (H // 8) * (W // 8) * 2
@@ -341,6 +383,8 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": (n_ctx + n_gen) * lat_bytes, "d2h_bytes_per_step": n_gen * lat_bytes},
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": cpu_desc}}
+    if gpu_eager is not None:
+        line["gpu_eager_baseline"] = gpu_eager
     print(json.dumps(line), flush=True)
 
 
