@@ -13,6 +13,10 @@ steps with CFG (50 at full size), synthetic latents, random-init weights.  Print
                 memory and the generated latents read back to the host, inside the timed region.
 * ``roofline``: the tcgen05 GEMM (dominant kernel) timed live with CUDA events on the launch
                 stream over all layers' weights (7.2 GB > L2), algorithmic FLOPs / duration.
+* ``gpu_eager_baseline`` (N = 1, full size): the same oracle restatement run in bf16 eager on the
+                same GPU and weights, one Euler step -- the reference's path as written on this
+                hardware (SURVEY.md 8(d) "GPU reference baseline").  A measured baseline only:
+                nothing in ``videogpt_b200`` imports ``oracle``.
 * ``cpu_baseline`` / ``--impl reference``: the oracle restatement of the reference's own
                 PyTorch path (no cache, padded unconditional row, dense mask) on the host cores,
                 bounded sample, extrapolated and labelled as such.
