@@ -266,7 +266,6 @@ def run_ours(args, rank, world, local_rank):
 
     cfg_split = args.parallelism == "cfg" and world > 1
     if cfg_split:
-        from oracle import processor_oracle as _po   # index dicts only (host ints), not on the timed path
         from videogpt_b200 import parallel
         grp = parallel.CfgBranchGroup()
         lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42 + grp.video_group)
