@@ -76,39 +76,68 @@ class PeerGroup:
         """*collective*: zero-filled ``nbytes`` on every rank, mapped into every other rank."""
         import torch.distributed as dist
         nbytes = (int(nbytes) + 255) // 256 * 256
-        with torch.cuda.device(self.device):
-            ptr = _raw_alloc(nbytes)
+        with self._device_ctx():
+            ptr = self._raw_alloc(nbytes)
             self._owned.append(ptr)
-            handle = (ctypes.c_ubyte * 64)()
-            _lib.call("vgpt_peer_export", ctypes.c_void_p(ptr), handle)
+            handle = self._export(ptr)
             gathered: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(gathered, (bytes(handle), nbytes), group=self.group)
-            ptrs = []
-            for r, (h, n) in enumerate(gathered):
+            dist.all_gather_object(gathered, (handle, nbytes), group=self.group)
+            # every rank validates before anybody maps anything (a size mismatch raises everywhere)
+            for r, (_, n) in enumerate(gathered):
                 if n != nbytes:
                     raise RuntimeError(f"PeerGroup.alloc: rank {r} asked for {n} bytes, this rank for {nbytes}")
+            ptrs = []
+            for r, (h, _) in enumerate(gathered):
                 if r == self.rank:
                     ptrs.append(ptr)
                     continue
-                out = ctypes.c_void_p()
-                _lib.call("vgpt_peer_import", (ctypes.c_ubyte * 64).from_buffer_copy(h), ctypes.byref(out))
-                self._imported.append(int(out.value))
-                ptrs.append(int(out.value))
-            local = torch.as_tensor(_Blob(ptr, nbytes, self), device=self.device)
+                mapped = self._import(h)
+                self._imported.append(mapped)
+                ptrs.append(mapped)
+            local = self._wrap(ptr, nbytes)
         dist.barrier(group=self.group)
         return SharedBuffer(local, ptrs, self.rank)
+
+    # ---- the four driver-facing steps (overridden by the CPU test double) -------------------------
+    def _device_ctx(self):
+        return torch.cuda.device(self.device)
+
+    def _raw_alloc(self, nbytes: int) -> int:
+        return _raw_alloc(nbytes)
+
+    def _export(self, ptr: int) -> bytes:
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.call("vgpt_peer_export", ctypes.c_void_p(ptr), handle)
+        return bytes(handle)
+
+    def _import(self, handle: bytes) -> int:
+        out = ctypes.c_void_p()
+        _lib.call("vgpt_peer_import", (ctypes.c_ubyte * 64).from_buffer_copy(handle), ctypes.byref(out))
+        return int(out.value)
+
+    def _wrap(self, ptr: int, nbytes: int) -> torch.Tensor:
+        return torch.as_tensor(_Blob(ptr, nbytes, self), device=self.device)
+
+    def _unmap(self, ptr: int):
+        _lib.call("vgpt_peer_close", ctypes.c_void_p(ptr))
+
+    def _free(self, ptr: int):
+        _lib.call("vgpt_peer_free", ctypes.c_void_p(ptr))
+
+    def _sync(self):
+        torch.cuda.synchronize(self.device)
 
     def close(self):
         """*collective*: unmap the peers' buffers, then free this rank's."""
         import torch.distributed as dist
-        torch.cuda.synchronize(self.device)
+        self._sync()
         dist.barrier(group=self.group)
         for p in self._imported:
-            _lib.call("vgpt_peer_close", ctypes.c_void_p(p))
+            self._unmap(p)
         self._imported = []
-        dist.barrier(group=self.group)
+        dist.barrier(group=self.group)           # nobody frees while a peer still maps it
         for p in self._owned:
-            _lib.call("vgpt_peer_free", ctypes.c_void_p(p))
+            self._free(p)
         self._owned = []
 
     # ---- data path --------------------------------------------------------------------------------
@@ -123,7 +152,7 @@ class PeerGroup:
         such calls can wait for a PEER device to go idle, and a peer that is spinning in
         ``vgpt_peer_barrier`` for kernels this rank has not enqueued yet never does."""
         import torch.distributed as dist
-        torch.cuda.synchronize(self.device)
+        self._sync()
         dist.barrier(group=self.group)
 
     def check(self):
