@@ -7,7 +7,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from videogpt_b200 import parallel
+from videogpt_b200 import parallel, peer as _peer_mod
+
+_REAL_PEER_GROUP = _peer_mod.PeerGroup      # (one test patches peer.PeerGroup with the CPU double)
 
 
 def _free_port():
@@ -85,9 +87,8 @@ def test_layout_errors():
 def _fake_peer_group(world_ranks, group=None):
     import contextlib
     import struct
-    from videogpt_b200 import peer
 
-    class FakePeerGroup(peer.PeerGroup):
+    class FakePeerGroup(_REAL_PEER_GROUP):
         log = []
         _next = 0
 
@@ -165,3 +166,77 @@ def test_peer_groups_of_two_in_world4():
     out = _spawn(4, _peer_subgroups)
     assert [out[r][0] for r in range(4)] == [[0, 1], [0, 1], [2, 3], [2, 3]]
     assert [out[r][1] for r in range(4)] == [0, 1, 0, 1] and all(out[r][2] for r in range(4))
+
+
+# ------------------------------------------------------------------------------------------------
+# The whole sequence-parallel HOST flow on CPU: LVM + LVMScheduler under
+# initialize_sequence_parallel_state(2), kernels stubbed, peer memory faked, but the host
+# rendezvous (PeerGroup.host_barrier = a real gloo barrier) and every decision that changes how
+# many collectives a rank enters (plan cache hits, prefill, re-planning) are the real code.
+# A rank-inconsistent decision dead-locks here (caught by the timeout) exactly as it would on GPUs.
+# ------------------------------------------------------------------------------------------------
+def _sp_host_flow(rank, world):
+    from unittest import mock
+    from transformers import Phi3Config
+    from oracle import processor_oracle as po
+    from test_host_dryrun import StubOpsSP
+    from videogpt_b200 import LVM, LVMScheduler, engine, model, peer, scheduler, synth
+    from videogpt_b200 import parallel_states as ps
+    os.environ["RANK"], os.environ["WORLD_SIZE"] = str(rank), str(world)
+    stub = StubOpsSP()
+    barriers = []
+    bf = torch.bfloat16
+
+    def make_group(ranks, group=None, device=None):
+        g = _fake_peer_group(ranks, group=group)
+        g.barrier = lambda: barriers.append(1)          # the flag-barrier kernel launch
+        return g
+
+    def engine_cpu(self):
+        if self._engine is None:
+            d = self.dims()
+            w = engine.EngineWeights(self.state_dict(), d.num_hidden_layers, "cpu")
+            self._engine = engine.NextClipEngine(w, d.hidden_size, d.intermediate_size, d.num_hidden_layers,
+                                                 d.num_attention_heads, d.rms_norm_eps, d.rope_theta, "cpu",
+                                                 self.pos_embed_max_size, self.patch_size, use_cuda_graph=False,
+                                                 peers=self.sequence_parallel_peers())
+        return self._engine
+
+    ps.initialize_sequence_parallel_state(2)
+    try:
+        with mock.patch.object(engine, "ops", stub), mock.patch.object(model, "ops", stub), \
+                mock.patch.object(scheduler, "ops", stub), mock.patch.object(torch.cuda, "is_available", lambda: True), \
+                mock.patch.object(peer, "PeerGroup", make_group), mock.patch.object(model.LVM, "engine", engine_cpu):
+            m = LVM(Phi3Config(**synth.REDUCED.phi3_kwargs()), device="cpu", materialize_pos_embed=False).to(bf).eval()
+            L = synth.REDUCED.num_hidden_layers
+            n_ctx, n_gen, H, W, steps = 3, 2, 64, 96, 2
+            d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+            lat = [x.to(bf) for x in synth.synthetic_latents(n_ctx + n_gen, H, W)]
+            per_clip = []
+            for clip in range(3):
+                # rank 1 churns its allocator between clips: address reuse must not change any decision
+                junk = [torch.empty(17 * (clip + 1) * (rank + 1), dtype=bf) for _ in range(5 * rank)]
+                mk = dict(input_ids=d["input_ids"].clone(), input_img_latents=[x.clone() for x in lat[:n_ctx]],
+                          input_image_sizes=d["input_image_sizes"], attention_mask=None,
+                          position_ids=d["position_ids"].clone(), denoise_image_sizes=d["denoise_image_sizes"],
+                          time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5, use_img_cfg=True, use_kv_cache=False,
+                          offload_model=False, vae=None)
+                before = len(barriers)
+                LVMScheduler(steps)([x.clone() for x in lat[n_ctx:]] * 2, m.frame_block_forward_with_cfg, mk,
+                                    prediction_type="x1")
+                per_clip.append(len(barriers) - before)
+                del junk, mk
+            e = m._engine
+            return per_clip, e.plan.shard, (e.plan.prefix.rows, e.plan.step.rows), L
+    finally:
+        ps.destroy_sequence_parallel_group()
+
+
+@pytest.mark.timeout(240)
+def test_sequence_parallel_host_flow_world2():
+    out = _spawn(2, _sp_host_flow)
+    L = out[0][3]
+    # every clip: prefill (L barriers) + 2 steps x (L + 1) barriers, on BOTH ranks, every time
+    assert out[0][0] == out[1][0] == [L + 2 * (L + 1)] * 3
+    assert out[0][1] == (0, 2) and out[1][1] == (1, 2)
+    assert out[0][2][0] + out[1][2][0] == 3 * 26 and out[0][2][1] + out[1][2][1] == 2 * 2 * 26
