@@ -1,0 +1,117 @@
+"""Numerical check of the HOST side on CPU: the product's model / scheduler / engine run with the
+torch emulation of the kernels (tests/emu_ops.py, same paged-cache / code / row-array layouts) in
+fp32 and must reproduce the oracle -- the reference's path as written: no cache, padded
+unconditional row, dense mask -- to fp32 rounding.  A wrong K/V slot, token code, RoPE position,
+latent number or cached-prefix decision fails here without a GPU; the kernels' own arithmetic is
+the business of the -m gpu tests."""
+import pytest
+import torch
+
+from oracle import model_oracle as mo, processor_oracle as po, scheduler_oracle as so
+from videogpt_b200 import synth
+
+TOL = 2e-5
+
+
+def _model(dims=synth.REDUCED, seed=0):
+    from transformers import Phi3Config
+    from videogpt_b200 import LVM
+    sd = synth.init_state_dict(dims, seed=seed)
+    m = LVM(Phi3Config(**dims.phi3_kwargs()), device="cpu")
+    m.load_state_dict(sd)
+    return m.float().eval(), {k: v.float() for k, v in sd.items()}
+
+
+def _ocfg(d):
+    return mo.OracleConfig(hidden_size=d.hidden_size, intermediate_size=d.intermediate_size,
+                           num_hidden_layers=d.num_hidden_layers, num_attention_heads=d.num_attention_heads)
+
+
+def _mk(n_ctx, n_gen, H, W, sp=1, seed=42):
+    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, sp)
+    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=seed)
+    mk = dict(input_ids=d["input_ids"], input_img_latents=lat[:n_ctx], input_image_sizes=d["input_image_sizes"],
+              attention_mask=d["attention_mask"], position_ids=d["position_ids"],
+              denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
+              use_img_cfg=True, use_kv_cache=False, offload_model=False, vae=None)
+    return mk, lat[n_ctx:]
+
+
+def _maxerr(a, b):
+    a, b = torch.cat([x.flatten() for x in a]), torch.cat([x.flatten() for x in b])
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize("geom", [(2, 2, 64, 64, 1), (3, 2, 64, 96, 1), (1, 1, 64, 64, 1), (3, 4, 48, 80, 8),
+                                  (5, 2, 64, 96, 8)])
+@pytest.mark.parametrize("pt", ["x1", "v"])
+def test_engine_loop_reproduces_the_oracle_in_fp32(emu, geom, pt):
+    """Fused scheduler loop (prefix cached once, unconditional row unpadded, codes instead of the
+    mask) == the oracle's sampler over the reference path as written, 3 Euler steps with CFG; the
+    left-padded / SP-padded layouts of the reference processor included."""
+    from videogpt_b200 import LVMScheduler
+    n_ctx, n_gen, H, W, sp = geom
+    m, sd = _model()
+    mk, z0 = _mk(n_ctx, n_gen, H, W, sp)
+    with torch.no_grad():
+        want = so.euler_sample([x.clone() for x in z0] * 2,
+                               lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                               mk, num_steps=3, prediction_type=pt)
+    got = LVMScheduler(num_steps=3)([x.clone() for x in z0] * 2, m.frame_block_forward_with_cfg, mk,
+                                    use_kv_cache=False, prediction_type=pt)
+    assert _maxerr(got, want) < TOL
+    assert emu.calls.count("attention") == synth.REDUCED.num_hidden_layers * 3 + (synth.REDUCED.num_hidden_layers - 1)
+
+
+def test_callback_seam_reproduces_the_oracle_in_fp32(emu):
+    """Seam S2: one call of frame_block_forward_with_cfg with per-latent timesteps (not uniform)."""
+    m, sd = _model()
+    mk, z0 = _mk(2, 3, 64, 64)
+    z = [x.clone() for x in z0] * 2
+    t = torch.tensor([0.1, 0.4, 0.7, 0.1, 0.4, 0.7])
+    for pt in ("x1", "v"):
+        with torch.no_grad():
+            want = mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, prediction_type=pt, **mk)
+        got, _ = m.frame_block_forward_with_cfg(z, t, past_key_values=None, prediction_type=pt, **mk)
+        assert _maxerr(got, want) < TOL
+
+
+@pytest.mark.parametrize("geom", [(2, 64, 64, 1), (3, 48, 80, 4), (1, 64, 64, 1)])
+@pytest.mark.parametrize("pt", ["x1", "v"])
+def test_single_frame_path_reproduces_the_oracle_in_fp32(emu, geom, pt):
+    """``pipeline.__call__`` layout (LVM.forward_with_cfg): condition tokens cached as the prefix,
+    [time | image] rows active; the 1-token unconditional row left-padded by the reference."""
+    from videogpt_b200 import LVMScheduler
+    n_ctx, H, W, sp = geom
+    m, sd = _model()
+    d = po.single_frame_inputs(n_ctx, H, W, True, sp)
+    lat = synth.synthetic_latents(n_ctx + 1, H, W, seed=7)
+    mk = dict(input_ids=d["input_ids"], input_img_latents=lat[:n_ctx], input_image_sizes=d["input_image_sizes"],
+              attention_mask=d["attention_mask"], position_ids=d["position_ids"], img_cfg_scale=1.5,
+              use_img_cfg=True, use_kv_cache=False, offload_model=False)
+    z0 = torch.cat([lat[n_ctx]] * 2, 0)
+    with torch.no_grad():
+        want = so.euler_sample(z0.clone(),
+                               lambda z, t, **kw: mo.single_frame_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                               mk, num_steps=3, prediction_type=pt)
+    got = LVMScheduler(num_steps=3)(z0.clone(), m.forward_with_cfg, mk, use_kv_cache=False, prediction_type=pt)
+    assert _maxerr([got], [want]) < TOL
+
+
+def test_next_clip_of_the_same_geometry_reuses_the_plan_and_redoes_the_prefill(emu):
+    """Cache level 2 of LVM.prepare_frame_block: new context tensors, same layout -> same plan
+    object, new context K/V; results equal the oracle for BOTH clips."""
+    from videogpt_b200 import LVMScheduler
+    m, sd = _model()
+    plans = []
+    for seed in (1, 2):
+        mk, z0 = _mk(2, 2, 64, 64, seed=seed)
+        with torch.no_grad():
+            want = so.euler_sample([x.clone() for x in z0] * 2,
+                                   lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                                   mk, num_steps=2, prediction_type="x1")
+        got = LVMScheduler(num_steps=2)([x.clone() for x in z0] * 2, m.frame_block_forward_with_cfg, mk,
+                                        use_kv_cache=False, prediction_type="x1")
+        assert _maxerr(got, want) < TOL
+        plans.append(m._engine.plan)
+    assert plans[0] is plans[1]

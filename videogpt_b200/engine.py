@@ -30,6 +30,10 @@ from . import ops
 from .ops import PAGE_TOKENS, ATTN_KV_TILE
 
 INT_MAX = 2 ** 31 - 1
+# Storage type of activations, weights and the KV pools.  The kernels only take bf16 (ops._req
+# rejects anything else); the name exists so the CPU emulation in tests/emu_ops.py can run this
+# module's host logic in fp32 against the fp32 oracle.
+ACT_DTYPE = torch.bfloat16
 
 
 # --------------------------------------------------------------------------------------------
@@ -42,8 +46,8 @@ class EngineWeights:
     def __init__(self, sd: Dict[str, torch.Tensor], num_layers: int, device):
         def g(name):
             t = sd[name]
-            if t.device != torch.device(device) or t.dtype != torch.bfloat16 or not t.is_contiguous():
-                t = t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+            if t.device != torch.device(device) or t.dtype != ACT_DTYPE or not t.is_contiguous():
+                t = t.detach().to(device=device, dtype=ACT_DTYPE).contiguous()
             return t.detach()
 
         self.embed_tokens = g("llm.embed_tokens.weight")
@@ -348,7 +352,7 @@ class NextClipEngine:
     def set_plan(self, plan: ClipPlan):
         self.plan = plan
         self._graph = None
-        dev, bf = self.device, torch.bfloat16
+        dev, bf = self.device, ACT_DTYPE
         rows = max(plan.prefix.rows, plan.step.rows, 1)
         self.hidden = torch.empty(rows, self.hs, device=dev, dtype=bf)
         self.xn = torch.empty(rows, self.hs, device=dev, dtype=bf)
@@ -408,10 +412,10 @@ class NextClipEngine:
         if self.w.pos_embed is not None:
             top, left = (self.pos_max - hh) // 2, (self.pos_max - ww) // 2
             pe = self.w.pos_embed.reshape(self.pos_max, self.pos_max, -1)[top:top + hh, left:left + ww]
-            return pe.reshape(hh * ww, -1).to(device=self.device, dtype=torch.bfloat16).contiguous()
+            return pe.reshape(hh * ww, -1).to(device=self.device, dtype=ACT_DTYPE).contiguous()
         from .synth import cropped_pos_embed_rows
         return cropped_pos_embed_rows(self.hs, lat_h, lat_w, self.patch, self.pos_max).to(
-            device=self.device, dtype=torch.bfloat16).contiguous()
+            device=self.device, dtype=ACT_DTYPE).contiguous()
 
     # ---- kernel sequences ----------------------------------------------------------------------
     def _time_embeddings(self, n: int):
