@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the next-clip denoising hot path (BASELINE.json: next-clip latency / tokens/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg5|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5|cfg1]
 
 One "step" = one next-clip prediction of the named workload: context prefill + all Euler
 steps with CFG (50 at full size), synthetic latents, random-init weights.  Prints ONE JSON line
@@ -46,7 +46,9 @@ WORKLOADS = {
     "cfg3": ("full", 32, 4, 256, 256, 50),  # configs[2]: 8 context clips, KV cache (sequence parallel at N>1)
     "cfg5": ("full", 4, 4, 512, 512, 50),   # configs[4]
     "cfg1": ("reduced", 4, 4, 256, 256, 4),  # configs[0] (the reference's CPU-runnable case)
+    "cfg4": ("full", 4, 4, 256, 256, 50),   # configs[3]: 32 videos x CFG branches, data-parallel over the ranks
 }
+BATCH_VIDEOS = {"cfg4": 32}                 # total videos of the job (split over the ranks: strong scaling)
 GUIDANCE = 1.5
 
 
@@ -281,13 +283,38 @@ def run_ours(args, rank, world, local_rank):
                   attention_mask=None, position_ids=d["position_ids"], denoise_image_sizes=d["denoise_image_sizes"],
                   time_emb_inx=d["time_emb_inx"], img_cfg_scale=GUIDANCE, use_img_cfg=True)
 
+    # configs[3]: this rank's share of the job's videos, `--batch` videos per pass through the engine
+    # (all rows of those videos and both CFG branches in one [M, hidden] matrix)
+    vids_rank = 0
+    if args.config in BATCH_VIDEOS:
+        total = BATCH_VIDEOS[args.config]
+        if args.parallelism != "dp" or total % world or (total // world) % args.batch:
+            raise SystemExit(f"{args.config}: {total} videos need --parallelism dp, a world size dividing {total} "
+                             f"and --batch dividing {total}//world")
+        vids_rank = total // world
+        vlat = [synth.synthetic_latents(n_ctx + n_gen, H, W, seed=1000 + rank * vids_rank + v) for v in range(vids_rank)]
+        vctx_host = [[x.to(torch.bfloat16).pin_memory() for x in l[:n_ctx]] for l in vlat]
+        vnoise_host = [[x.to(torch.bfloat16).pin_memory() for x in l[n_ctx:]] for l in vlat]
+        vctx_dev = [[x.to(dev) for x in c] for c in vctx_host]
+        vnoise_dev = [[x.to(dev) for x in c] for c in vnoise_host]
+
+    def batch_pass(ctxs, noises):
+        out = []
+        for i in range(0, vids_rank, args.batch):
+            out += pipe.next_clip_latents_batch(ctxs[i:i + args.batch], n_gen, initial_noise=noises[i:i + args.batch], **kw)
+        return out
+
     def clip_device():
+        if vids_rank:
+            return batch_pass([[x.clone() for x in c] for c in vctx_dev], vnoise_dev)
         if cfg_split:
             return parallel.sample_cfg_split(model, LVMScheduler(euler), [x.clone() for x in noise_dev] * 2, mk, grp, "x1")
         # a fresh context tensor list every clip => the engine re-runs the prefill (as a new clip would)
         return pipe.next_clip_latents([x.clone() for x in ctx_dev], n_gen, initial_noise=noise_dev, **kw)
 
     def clip_host():
+        if vids_rank:
+            return [[x.to("cpu") for x in v] for v in batch_pass(vctx_host, vnoise_host)]
         if cfg_split:
             mk["input_img_latents"] = [x.to(dev, non_blocking=True) for x in ctx_host]
             out = parallel.sample_cfg_split(model, LVMScheduler(euler), [x.to(dev, non_blocking=True) for x in noise_host] * 2,
@@ -328,11 +355,15 @@ def run_ours(args, rank, world, local_rank):
         return
     tokens_per_clip = 2 * n_gen * block * euler
     videos = world // 2 if cfg_split else world // sp_size
+    if vids_rank:
+        videos = world * vids_rank
     value = videos * tokens_per_clip * args.steps / dt
     e2e = videos * tokens_per_clip * args.steps / dt_e2e
     step_fl, prefill_fl, clip_fl = algorithmic_flops(dims, n_ctx, n_gen, block, euler)
     e = model.engine()
     launches = args.steps * (e.launches_per_prefill + euler * (e.launches_per_predict + 1))
+    if vids_rank:
+        launches *= vids_rank // args.batch
 
     peaks = {}
     try:
@@ -352,8 +383,8 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": (69363712 + 16023808) if gemm_rows == 2064 else None,
                 "traffic_note": "dram__bytes_read+write of one qkv launch, ncu --set full (profiles/r01c_gemm_pair_*_ncu.txt)",
                 "avg_launch_us": sec * 1e6, "launches_timed": n_launch,
-                "whole_clip_tflops": clip_fl * args.steps / dt / 1e12,
-                "whole_clip_frac_of_sustained": clip_fl * args.steps / dt / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
+                "whole_clip_tflops": max(vids_rank, 1) * clip_fl * args.steps / dt / 1e12,
+                "whole_clip_frac_of_sustained": max(vids_rank, 1) * clip_fl * args.steps / dt / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
 
     gpu_eager = None
     if world == 1 and kind == "full":
@@ -372,18 +403,21 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "next_clip_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
             "s_per_clip": dt / args.steps, "higher_is_better": True,
-            "scaling": "strong" if sp_size == world and world > 1 else "weak", "vs_baseline": None,
+            "scaling": "strong" if (sp_size == world and world > 1) or vids_rank else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.config, "model": "Phi-3-mini-class random-init" if kind == "full" else "2 layers / hidden 512",
                        "context_frames": n_ctx, "generated_frames": n_gen, "height": H, "width": W,
                        "euler_steps": euler, "cfg": True, "guidance": GUIDANCE, "prediction_type": "x1",
-                       "parallelism": (f"cfg-branch pairs x dp{world // 2}" if cfg_split else
+                       "parallelism": (f"dp{world}: {vids_rank} of {world * vids_rank} videos per rank, {args.batch} videos x 2 CFG "
+                                       f"branches per engine pass" if vids_rank else
+                                       f"cfg-branch pairs x dp{world // 2}" if cfg_split else
                                        f"sp{sp_size} (rows of one video sharded, K/V pushed to peers over NVLink) x dp{world // sp_size}"
                                        if sp_size > 1 else f"dp{world} (independent videos)"),
                        "l2": "weights 7.2 GB streamed every Euler step (> 126 MB L2); no explicit flush"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "tokens/s", "s_per_clip": dt_e2e / args.steps,
-                    "h2d_bytes_per_step": (n_ctx + n_gen) * lat_bytes, "d2h_bytes_per_step": n_gen * lat_bytes},
+                    "h2d_bytes_per_step": max(vids_rank, 1) * (n_ctx + n_gen) * lat_bytes,
+                    "d2h_bytes_per_step": max(vids_rank, 1) * n_gen * lat_bytes},
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": cpu_desc}}
     if gpu_eager is not None:
@@ -402,6 +436,7 @@ def main():
                     help="N>1: dp = independent videos per rank; cfg = CFG branches split over rank pairs; "
                          "sp = sequence parallel groups of --sp ranks per video")
     ap.add_argument("--sp", type=int, default=0, help="ranks per sequence-parallel group (default: all)")
+    ap.add_argument("--batch", type=int, default=4, help="cfg4: videos per engine pass on a rank")
     args = ap.parse_args()
     if os.environ.get("VGPT_FAULT_DUMP"):      # debugging aid: dump every thread's stack after N seconds and exit
         import faulthandler

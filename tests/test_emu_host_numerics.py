@@ -115,3 +115,42 @@ def test_next_clip_of_the_same_geometry_reuses_the_plan_and_redoes_the_prefill(e
         assert _maxerr(got, want) < TOL
         plans.append(m._engine.plan)
     assert plans[0] is plans[1]
+
+
+def _pipe(m):
+    from videogpt_b200 import LVMPipeline, LVMProcessor
+    return LVMPipeline(None, m, LVMProcessor(synth.SingleIdTagTokenizer()), device="cpu")
+
+
+@pytest.mark.parametrize("guidance", [1.5, 1.0])
+def test_batched_videos_reproduce_the_oracle_and_the_per_video_runs(emu, guidance):
+    """BASELINE configs[3] (batch of videos x CFG branches in one pass): (a) the batched index
+    dicts fed to the ORACLE -- the reference model as written takes any number of rows
+    (LVM/model.py:436-453) -- give what the product computes from them; (b) video v of the batch
+    equals video v run alone through the single-video API."""
+    from videogpt_b200.pipeline import replicate_frame_block_inputs
+    n_videos, n_ctx, n_gen, H, W, steps = 3, 2, 2, 64, 64, 2
+    m, sd = _model()
+    pipe = _pipe(m)
+    lats = [synth.synthetic_latents(n_ctx + n_gen, H, W, seed=10 + v) for v in range(n_videos)]
+    ctx = [l[:n_ctx] for l in lats]
+    noise = [l[n_ctx:] for l in lats]
+    kw = dict(num_inference_steps=steps, img_guidance_scale=guidance, prediction_type="x1", dtype=torch.float32)
+    got = pipe.next_clip_latents_batch(ctx, n_gen, initial_noise=noise, **kw)
+    assert len(got) == n_videos and all(len(g) == n_gen for g in got)
+    # (b) per-video runs
+    for v in range(n_videos):
+        alone = pipe.next_clip_latents(ctx[v], n_gen, initial_noise=noise[v], **kw)
+        assert _maxerr(got[v], alone) < TOL
+    # (a) the oracle on the batched rows, dense mask
+    use_cfg = guidance != 1.0
+    d = replicate_frame_block_inputs(po.frame_block_inputs(n_ctx, n_gen, H, W, use_cfg, 1), n_videos)
+    mk = dict(input_ids=d["input_ids"], input_img_latents=[x for c in ctx for x in c],
+              input_image_sizes=d["input_image_sizes"], attention_mask=d["attention_mask"],
+              position_ids=d["position_ids"], denoise_image_sizes=d["denoise_image_sizes"],
+              time_emb_inx=d["time_emb_inx"], img_cfg_scale=guidance, use_img_cfg=use_cfg)
+    z0 = [x.clone() for nv in noise for x in nv] * (2 if use_cfg else 1)
+    with torch.no_grad():
+        want = so.euler_sample(z0, lambda z, t, **kw_: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw_),
+                               mk, num_steps=steps, prediction_type="x1")
+    assert _maxerr([x for g in got for x in g], want[:n_videos * n_gen]) < TOL

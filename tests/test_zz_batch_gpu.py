@@ -1,0 +1,41 @@
+"""Batched videos on the GPU (BASELINE.json configs[3]): all rows of several videos and both CFG
+branches in one pass.  Every kernel gives a row the same bits whatever else shares its launch
+(profiles/r01g_row_partition_invariance.txt), so video v of a batch must equal video v run alone
+BIT FOR BIT; the host side of the batched layout is checked against the oracle on CPU
+(tests/test_emu_host_numerics.py).  This file sorts last on purpose: it was written after this
+round's GPU minutes were spent and runs on hardware for the first time in the round-end suite."""
+import pytest
+import torch
+
+from videogpt_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV, BF = "cuda", torch.bfloat16
+
+
+def _pipe(dims):
+    from transformers import Phi3Config
+    from videogpt_b200 import LVM, LVMPipeline, LVMProcessor
+    sd = synth.init_state_dict(dims, seed=0)
+    model = LVM(Phi3Config(**dims.phi3_kwargs()), device=DEV)
+    model.load_state_dict(sd)
+    model.to(BF).eval()
+    return LVMPipeline(None, model, LVMProcessor(synth.SingleIdTagTokenizer()), device=torch.device(DEV))
+
+
+@pytest.mark.parametrize("pt", ["x1", "v"])
+def test_batch_of_videos_equals_the_videos_run_alone(pt):
+    n_videos, n_ctx, n_gen, H, W = 3, 2, 2, 128, 128
+    pipe = _pipe(synth.REDUCED)
+    lats = [synth.synthetic_latents(n_ctx + n_gen, H, W, seed=20 + v) for v in range(n_videos)]
+    ctx = [[x.to(DEV, BF) for x in l[:n_ctx]] for l in lats]
+    noise = [[x.to(DEV, BF) for x in l[n_ctx:]] for l in lats]
+    kw = dict(num_inference_steps=4, img_guidance_scale=1.5, prediction_type=pt)
+    got = pipe.next_clip_latents_batch(ctx, n_gen, initial_noise=noise, **kw)
+    torch.cuda.synchronize()
+    assert len(got) == n_videos
+    for v in range(n_videos):
+        alone = pipe.next_clip_latents(ctx[v], n_gen, initial_noise=noise[v], **kw)
+        for a, b in zip(got[v], alone):
+            assert torch.isfinite(a.float()).all()
+            assert torch.equal(a, b), f"video {v}: batched and single runs differ"

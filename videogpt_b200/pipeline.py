@@ -31,6 +31,25 @@ def frame_block_prompts(n_ctx: int, gen_num: int):
     return prompt, prompt_
 
 
+def replicate_frame_block_inputs(data: dict, n_videos: int) -> dict:
+    """Index dicts of ONE video (rows: conditional [, unconditional]) -> those of ``n_videos`` videos
+    of the same geometry in one batch: rows ``0..n-1`` are the conditional rows, rows ``n..2n-1``
+    the unconditional ones, so that latents and predictions keep the ``[cond..., uncond...]`` order
+    the sampler's CFG expects (``LVM/scheduler.py:186-199``) and the model's running counters
+    over rows (``LVM/model.py:436-453``) number context and noisy latents video by video."""
+    rows = data["input_ids"].shape[0]
+    order = [r for r in range(rows) for _ in range(n_videos)]           # source row of every batch row
+    out = dict(data)
+    for k in ("input_ids", "position_ids", "attention_mask"):
+        if data.get(k) is not None:
+            out[k] = data[k][order].contiguous()
+    for k in ("input_image_sizes", "denoise_image_sizes", "time_emb_inx"):
+        out[k] = {b: list(data[k][src]) for b, src in enumerate(order) if src in data[k]}
+    if "frame_blocks" in data:
+        out["frame_blocks"] = {b: data["frame_blocks"][src] for b, src in enumerate(order)}
+    return out
+
+
 class LVMPipeline:
     def __init__(self, vae, model: LVM, processor: LVMProcessor, device: Union[str, torch.device] = None):
         self.vae = vae
@@ -151,6 +170,65 @@ class LVMPipeline:
                             use_kv_cache=False, offload_kv_cache=False, prediction_type=prediction_type,
                             vae=self.vae)
         return samples[:len(samples) // 2] if use_img_guidance else samples
+
+    @torch.no_grad()
+    def next_clip_latents_batch(self, context_latents: List[List[torch.Tensor]], gen_num: int,
+                                num_inference_steps: int = 50, img_guidance_scale: float = 1.6,
+                                use_img_guidance: bool = True, seed: Optional[int] = None,
+                                time_shifting_factor: float = 1.0, prediction_type: str = "v",
+                                dtype: torch.dtype = torch.bfloat16,
+                                initial_noise: Optional[List[List[torch.Tensor]]] = None,
+                                scheduler: Optional[LVMScheduler] = None) -> List[List[torch.Tensor]]:
+        """``next_clip_latents`` for several independent videos of the same geometry in ONE pass
+        (BASELINE.json configs[3]): ``context_latents[v]`` are the context latents of video ``v``;
+        returns ``gen_num`` generated latents per video.
+
+        The reference's pipeline handles one video per call; its model, however, takes any number
+        of rows (``LVM/model.py:436-453``), and that is what this uses: all rows of all videos
+        and both CFG branches are packed into one ``[M, hidden]`` matrix, so every projection is
+        one GEMM over ``n_videos`` x more rows.  Every row-wise kernel and the attention kernel
+        give a row the same bits whatever else is in the batch, so video ``v`` of a batch equals
+        the same video run alone with the same noise."""
+        n_videos = len(context_latents)
+        if n_videos == 0:
+            return []
+        if img_guidance_scale == 1:
+            use_img_guidance = False
+        n_ctx = len(context_latents[0])
+        lat_h, lat_w = context_latents[0][0].shape[-2:]
+        for ctx in context_latents:
+            if len(ctx) != n_ctx or any(tuple(x.shape[-2:]) != (lat_h, lat_w) for x in ctx):
+                raise ValueError("all videos of a batch must have the same number and size of context frames")
+        height, width = lat_h * 8, lat_w * 8
+        prompt, prompt_ = frame_block_prompts(n_ctx, gen_num)
+        placeholders = [torch.empty(3, height, width, device="meta") for _ in range(n_ctx)]
+        instructions = [prompt, prompt_] if use_img_guidance else [prompt]
+        images = [placeholders, []] if use_img_guidance else [placeholders]
+        self.model.to(dtype)
+        data = replicate_frame_block_inputs(self.processor.prompt_condition_frame_block_inference(
+            instructions, images, height=height, width=width, use_img_cfg=use_img_guidance,
+            use_input_image_size_as_output=True, frame_blocks=[n_ctx, gen_num], build_dense_mask=False), n_videos)
+        if initial_noise is not None:
+            if len(initial_noise) != n_videos or any(len(n) != gen_num for n in initial_noise):
+                raise ValueError("initial_noise must hold gen_num latents for every video")
+            latents = [x.to(self.device, dtype) for video in initial_noise for x in video]
+        else:
+            generator = torch.Generator(device=self.device).manual_seed(seed) if seed is not None else None
+            latents = [torch.randn(1, 4, lat_h, lat_w, device=self.device, generator=generator).to(dtype)
+                       for _ in range(n_videos * gen_num)]
+        latents = latents * (2 if use_img_guidance else 1)
+        ctx = [x.to(self.device, dtype, non_blocking=True) for video in context_latents for x in video]
+        model_kwargs = dict(
+            input_ids=data["input_ids"], input_img_latents=ctx, input_image_sizes=data["input_image_sizes"],
+            attention_mask=None, position_ids=data["position_ids"],
+            denoise_image_sizes=data["denoise_image_sizes"], time_emb_inx=data["time_emb_inx"],
+            img_cfg_scale=img_guidance_scale, use_img_cfg=use_img_guidance, use_kv_cache=False,
+            offload_model=False, vae=self.vae)
+        scheduler = scheduler or LVMScheduler(num_steps=num_inference_steps, time_shifting_factor=time_shifting_factor)
+        samples = scheduler(latents, self.model.frame_block_forward_with_cfg, model_kwargs,
+                            use_kv_cache=False, offload_kv_cache=False, prediction_type=prediction_type,
+                            vae=self.vae)
+        return [samples[v * gen_num:(v + 1) * gen_num] for v in range(n_videos)]
 
     # ---- reference user API --------------------------------------------------------------------
     @torch.no_grad()
