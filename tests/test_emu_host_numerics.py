@@ -154,3 +154,97 @@ def test_batched_videos_reproduce_the_oracle_and_the_per_video_runs(emu, guidanc
         want = so.euler_sample(z0, lambda z, t, **kw_: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw_),
                                mk, num_steps=steps, prediction_type="x1")
     assert _maxerr([x for g in got for x in g], want[:n_videos * n_gen]) < TOL
+
+
+class _FakeVAE:
+    """Stands in for diffusers' AutoencoderKL (outside the hot path): 8x8 average pooling of the
+    three colour channels into 4 latent channels and its nearest-neighbour inverse; records what
+    it is asked to decode."""
+    class config:
+        shift_factor = None
+        scaling_factor = 0.5
+
+    def __init__(self):
+        self.decoded = []
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def encode(self, x):
+        lat = torch.nn.functional.avg_pool2d(x, 8)
+        lat = torch.cat([lat, lat.mean(1, keepdim=True)], 1)
+
+        class _D:
+            class latent_dist:
+                @staticmethod
+                def sample():
+                    return lat.clone()
+        return _D
+
+    def decode(self, lat):
+        self.decoded.append(lat.clone())
+        img = torch.nn.functional.interpolate(lat[:, :3], scale_factor=8, mode="nearest")
+
+        class _S:
+            sample = img
+        return _S
+
+
+def _pil(seed, size=64):
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    return Image.fromarray(rng.integers(0, 256, (size, size, 3), dtype=np.uint8))
+
+
+def test_pipeline_call_one_frame_at_a_time_reproduces_the_oracle(emu):
+    """``LVMPipeline.__call__`` (reference pipeline.py:136-343): two input images, two generated
+    frames; the latent handed to the VAE decoder for every generated frame must be what the
+    oracle's sampler gives for the same context latents and the same seeded noise."""
+    m, sd = _model()
+    pipe = _pipe(m)
+    pipe.vae = vae = _FakeVAE()
+    imgs = [_pil(1), _pil(2)]
+    out = pipe(input_images=imgs, height=64, width=64, gen_num=2, num_inference_steps=2, img_guidance_scale=1.5,
+               use_input_image_size_as_output=True, dtype=torch.float32, seed=5, prediction_type="v",
+               clean_image_noise_level=0.0)
+    assert len(out) == 4 and all(im.size == (64, 64) for im in out)
+    # decode order: 2 context reconstructions, generated frame 1, generated frame 2
+    assert len(vae.decoded) == 4
+    ctx = [pipe.vae_encode(pipe.processor.process_image(im).unsqueeze(0), torch.float32) for im in imgs]
+    for k in range(2):
+        if k == 1:     # the second frame is conditioned on the first one, re-encoded from its PIL image
+            ctx.append(pipe.vae_encode(pipe.processor.process_image(out[2]).unsqueeze(0), torch.float32))
+        d = po.single_frame_inputs(len(ctx), 64, 64, True, 1)
+        mk = dict(input_ids=d["input_ids"], input_img_latents=ctx, input_image_sizes=d["input_image_sizes"],
+                  attention_mask=d["attention_mask"], position_ids=d["position_ids"], img_cfg_scale=1.5,
+                  use_img_cfg=True)
+        noise = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(5))
+        with torch.no_grad():
+            want = so.euler_sample(torch.cat([noise] * 2, 0),
+                                   lambda z, t, **kw: mo.single_frame_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                                   mk, num_steps=2, prediction_type="v")[:1]
+        got = vae.decoded[2 + k] * vae.config.scaling_factor
+        assert _maxerr([got], [want]) < TOL
+
+
+def test_pipeline_call_without_input_images_generates_unconditionally(emu):
+    """No input images: guidance is switched off (pipeline.py:217-218), the sequence is
+    ``[<|diffusion|>, time, image tokens]``; the second frame is conditioned on the first."""
+    m, sd = _model()
+    pipe = _pipe(m)
+    pipe.vae = vae = _FakeVAE()
+    out = pipe(input_images=None, height=64, width=64, gen_num=2, num_inference_steps=2, dtype=torch.float32,
+               seed=3, prediction_type="x1", clean_image_noise_level=0.0)
+    assert len(out) == 2 and len(vae.decoded) == 2      # nothing to reconstruct: the two generated frames
+    d = po.single_frame_inputs(0, 64, 64, False, 1)
+    mk = dict(input_ids=d["input_ids"], input_img_latents=[], input_image_sizes=d["input_image_sizes"],
+              attention_mask=d["attention_mask"], position_ids=d["position_ids"], img_cfg_scale=1.6, use_img_cfg=False)
+    noise = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = so.euler_sample(noise, lambda z, t, **kw: mo.single_frame_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                               mk, num_steps=2, prediction_type="x1")
+    assert _maxerr([vae.decoded[0] * vae.config.scaling_factor], [want]) < TOL

@@ -230,7 +230,101 @@ class LVMPipeline:
                             vae=self.vae)
         return [samples[v * gen_num:(v + 1) * gen_num] for v in range(n_videos)]
 
+    @torch.no_grad()
+    def next_frame_latents(self, context_latents: Optional[List[torch.Tensor]], height: int = None,
+                           width: int = None, num_inference_steps: int = 50, img_guidance_scale: float = 1.6,
+                           use_img_guidance: bool = True, seed: Optional[int] = None,
+                           time_shifting_factor: float = 1.0, prediction_type: str = "v",
+                           dtype: torch.dtype = torch.bfloat16, initial_noise: Optional[torch.Tensor] = None,
+                           use_kv_cache: bool = True) -> torch.Tensor:
+        """One iteration of ``LVMPipeline.__call__`` (pipeline.py:215-296) in latent space: context
+        latents ``[1,4,h,w]`` (or none: unconditional generation of a ``height`` x ``width`` frame)
+        -> ONE generated latent ``[1,4,h,w]``, through the one-frame-at-a-time layout
+        (``LVMProcessor.__call__``, ``LVM.forward_with_cfg``)."""
+        ctx_in = list(context_latents or [])
+        if img_guidance_scale == 1 or not ctx_in:
+            use_img_guidance = False                                                     # 207-208, 217-218
+        if ctx_in and (height is None or width is None):
+            height, width = ctx_in[0].shape[-2] * 8, ctx_in[0].shape[-1] * 8
+        assert height is not None and width is not None and height % 16 == 0 and width % 16 == 0, \
+            "The height and width must be a multiple of 16."
+        lat_h, lat_w = height // 8, width // 8
+        prompt = "".join(f"<img><|image_{i + 1}|></img>" for i in range(len(ctx_in)))    # 222-225
+        images = [[torch.empty(3, x.shape[-2] * 8, x.shape[-1] * 8, device="meta") for x in ctx_in]] if ctx_in else None
+        self.model.to(dtype)
+        data = self.processor([prompt], images, height=height, width=width, use_img_cfg=use_img_guidance,
+                              use_input_image_size_as_output=False)
+        num_cfg = 1 if use_img_guidance else 0
+        if initial_noise is not None:
+            latents = initial_noise.to(self.device).reshape(1, 4, lat_h, lat_w)
+        else:
+            generator = torch.Generator(device=self.device).manual_seed(seed) if seed is not None else None
+            latents = torch.randn(1, 4, lat_h, lat_w, device=self.device, generator=generator)   # 250
+        latents = torch.cat([latents] * (1 + num_cfg), 0).to(dtype)                               # 251
+        model_kwargs = dict(
+            input_ids=self.move_to_device(data["input_ids"]),
+            input_img_latents=[x.to(self.device, dtype, non_blocking=True) for x in ctx_in],
+            input_image_sizes=data["input_image_sizes"],
+            attention_mask=self.move_to_device(data["attention_mask"]),
+            position_ids=self.move_to_device(data["position_ids"]), img_cfg_scale=img_guidance_scale,
+            use_img_cfg=use_img_guidance, use_kv_cache=use_kv_cache, offload_model=False)
+        scheduler = LVMScheduler(num_steps=num_inference_steps, time_shifting_factor=time_shifting_factor)
+        samples = scheduler(latents, self.model.forward_with_cfg, model_kwargs, use_kv_cache=use_kv_cache,
+                            offload_kv_cache=False, prediction_type=prediction_type, vae=self.vae)
+        return samples.chunk(1 + num_cfg, dim=0)[0]                                               # 297
+
     # ---- reference user API --------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, input_images=None, height: int = 1024, width: int = 1024, gen_num: int = 1,
+                 num_inference_steps: int = 50, use_img_guidance: bool = True, img_guidance_scale: float = 1.6,
+                 max_input_image_size: int = 1024, offload_model: bool = False, use_kv_cache: bool = True,
+                 offload_kv_cache: bool = True, use_input_image_size_as_output: bool = False,
+                 dtype: torch.dtype = torch.bfloat16, seed: int = None, output_type: str = "pil",
+                 time_shifting_factor: float = 1.0, prediction_type: str = "v",
+                 clean_image_noise_level: float = None):
+        """``LVMPipeline.__call__`` (pipeline.py:136-343): ``gen_num`` frames, one at a time, each
+        conditioned on the input images plus the frames generated so far (re-encoded through the
+        VAE every iteration and noised by ``clean_image_noise_level``, 256-260).  Returns the PIL
+        list: reconstructions of the input images, then the generated frames.
+
+        The arithmetic between the two VAE passes is ``next_frame_latents``.  As in the reference
+        the output frame takes the size of the (first) input image when
+        ``use_input_image_size_as_output`` is set; context frames of a size other than the output
+        frame's are rejected by the model (the engine's plan assumes one latent geometry)."""
+        if offload_model:
+            raise NotImplementedError("offload_model is out of scope on B200 (SURVEY.md 2b)")
+        prompt_img_len = len(input_images) if input_images is not None else 0
+        if not use_input_image_size_as_output:
+            assert height % 16 == 0 and width % 16 == 0, "The height and width must be a multiple of 16."
+        if max_input_image_size != self.processor.max_image_size:
+            self.processor = LVMProcessor(self.processor.text_tokenizer, max_image_size=max_input_image_size,
+                                          sequence_parallel_size=max(hccl_info.world_size, 1))
+        self.model.to(dtype)
+        frames = list(input_images) if input_images is not None else None               # ori_input_images
+        output_images = []
+        for gen_idx in range(gen_num):
+            if output_images:                                                            # 211-215
+                frames = [output_images[-1]] if frames is None else frames + [output_images[-1]]
+            ctx = []
+            for idx, img in enumerate(frames or []):                                     # 254-260
+                pixels = self.processor.process_image(img)
+                lat = self.vae_encode(pixels.unsqueeze(0).to(self.device), dtype)
+                if idx >= prompt_img_len:
+                    lat = (1 - clean_image_noise_level) * lat + clean_image_noise_level * torch.randn_like(lat)
+                ctx.append(lat)
+            if ctx and use_input_image_size_as_output:                                   # 246-247
+                height, width = ctx[0].shape[-2] * 8, ctx[0].shape[-1] * 8
+            sample = self.next_frame_latents(
+                ctx, height=height, width=width, num_inference_steps=num_inference_steps,
+                img_guidance_scale=img_guidance_scale, use_img_guidance=use_img_guidance, seed=seed,
+                time_shifting_factor=time_shifting_factor, prediction_type=prediction_type, dtype=dtype,
+                use_kv_cache=use_kv_cache)
+            if gen_idx == 0:
+                output_images.extend(self.vae_decode_to_pil(lat) for lat in ctx)         # 305-316
+            output_images.append(self.vae_decode_to_pil(sample))                         # 318-336
+        gc.collect()
+        return output_images
+
     @torch.no_grad()
     def prompt_condition_frame_block_autoregressive_inference(
             self, input_images=None, height: int = 1024, width: int = 1024, gen_nums: list = [1],
