@@ -304,7 +304,13 @@ def run_ours(args, rank, world, local_rank):
             out += pipe.next_clip_latents_batch(ctxs[i:i + args.batch], n_gen, initial_noise=noises[i:i + args.batch], **kw)
         return out
 
+    rounds = max(args.rollout, 1)
+    roll_kw = dict(num_inference_steps=euler, img_guidance_scale=GUIDANCE, prediction_type="x1", seed=7,
+                   max_frame_window=n_ctx + n_gen, persistent_cache=not args.recompute)
+
     def clip_device():
+        if args.rollout:     # `rounds` clips autoregressively, latents and K/V carried forward
+            return pipe.rollout_latents([x.clone() for x in ctx_dev], [n_gen] * rounds, **roll_kw)
         if vids_rank:
             return batch_pass([[x.clone() for x in c] for c in vctx_dev], vnoise_dev)
         if cfg_split:
@@ -313,6 +319,8 @@ def run_ours(args, rank, world, local_rank):
         return pipe.next_clip_latents([x.clone() for x in ctx_dev], n_gen, initial_noise=noise_dev, **kw)
 
     def clip_host():
+        if args.rollout:
+            return [x.to("cpu") for x in pipe.rollout_latents(ctx_host, [n_gen] * rounds, **roll_kw)]
         if vids_rank:
             return [[x.to("cpu") for x in v] for v in batch_pass(vctx_host, vnoise_host)]
         if cfg_split:
@@ -353,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
         dt, dt_e2e = float(tt[0]), float(tt[1])
     if rank != 0:
         return
-    tokens_per_clip = 2 * n_gen * block * euler
+    tokens_per_clip = 2 * n_gen * block * euler * rounds
     videos = world // 2 if cfg_split else world // sp_size
     if vids_rank:
         videos = world * vids_rank
@@ -361,7 +369,7 @@ def run_ours(args, rank, world, local_rank):
     e2e = videos * tokens_per_clip * args.steps / dt_e2e
     step_fl, prefill_fl, clip_fl = algorithmic_flops(dims, n_ctx, n_gen, block, euler)
     e = model.engine()
-    launches = args.steps * (e.launches_per_prefill + euler * (e.launches_per_predict + 1))
+    launches = args.steps * rounds * (e.launches_per_prefill + euler * (e.launches_per_predict + 1))
     if vids_rank:
         launches *= vids_rank // args.batch
 
@@ -386,8 +394,11 @@ def run_ours(args, rank, world, local_rank):
                 "whole_clip_tflops": max(vids_rank, 1) * clip_fl * args.steps / dt / 1e12,
                 "whole_clip_frac_of_sustained": max(vids_rank, 1) * clip_fl * args.steps / dt / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
 
+    if args.rollout:          # the per-clip FLOP model assumes one full prefill per clip
+        roofline["whole_clip_tflops"] = roofline["whole_clip_frac_of_sustained"] = None
+
     gpu_eager = None
-    if world == 1 and kind == "full":
+    if world == 1 and kind == "full" and not args.rollout:
         try:      # the reference path as written, eager bf16 on this GPU (reported next to ours)
             sec_step = gpu_eager_oracle(model, dims, n_ctx, n_gen, H, W, dev)
             gpu_eager = {"value": 2 * n_gen * block / sec_step, "unit": "tokens/s", "ms_per_euler_step": 1e3 * sec_step,
@@ -413,6 +424,9 @@ def run_ours(args, rank, world, local_rank):
                                        f"cfg-branch pairs x dp{world // 2}" if cfg_split else
                                        f"sp{sp_size} (rows of one video sharded, K/V pushed to peers over NVLink) x dp{world // sp_size}"
                                        if sp_size > 1 else f"dp{world} (independent videos)"),
+                       "rollout": ({"rounds": rounds, "window_frames": n_ctx + n_gen,
+                                    "context": "persistent paged K/V cache (each context frame prefilled once)"
+                                    if not args.recompute else "recomputed every round (reference flow)"} if args.rollout else None),
                        "l2": "weights 7.2 GB streamed every Euler step (> 126 MB L2); no explicit flush"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "tokens/s", "s_per_clip": dt_e2e / args.steps,
@@ -437,6 +451,9 @@ def main():
                          "sp = sequence parallel groups of --sp ranks per video")
     ap.add_argument("--sp", type=int, default=0, help="ranks per sequence-parallel group (default: all)")
     ap.add_argument("--batch", type=int, default=4, help="cfg4: videos per engine pass on a rank")
+    ap.add_argument("--rollout", type=int, default=0, help="a step = this many clips generated autoregressively in "
+                    "latent space (window = the workload's context + clip); 0 = one clip per step")
+    ap.add_argument("--recompute", action="store_true", help="--rollout without the persistent K/V cache")
     args = ap.parse_args()
     if os.environ.get("VGPT_FAULT_DUMP"):      # debugging aid: dump every thread's stack after N seconds and exit
         import faulthandler

@@ -248,3 +248,94 @@ def test_pipeline_call_without_input_images_generates_unconditionally(emu):
         want = so.euler_sample(noise, lambda z, t, **kw: mo.single_frame_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
                                mk, num_steps=2, prediction_type="x1")
     assert _maxerr([vae.decoded[0] * vae.config.scaling_factor], [want]) < TOL
+
+
+# ---- latent-space rollout with a persistent paged K/V cache ---------------------
+def _history_mask(d, n_hist, gen, bl, ws_of_frame, ws_now):
+    """The reference mask over the FULL history (cond row), minus what the rollout's window hides:
+    the clip sees context frames >= ws_now, context frame f keeps the view of the round that cached
+    it (frames >= ws_of_frame[f]).  Row 1 (unconditional) is untouched."""
+    mask = d["attention_mask"].clone()
+    frame = torch.arange(mask.shape[-1]) // bl
+    for q in range(mask.shape[-1]):
+        fq = int(frame[q])
+        lo = ws_now if fq >= n_hist else ws_of_frame[fq]
+        mask[0, q, frame < lo] = 0
+    return mask
+
+
+@pytest.mark.parametrize("pt", ["x1", "v"])
+def test_rollout_with_persistent_cache_matches_the_oracle_over_the_full_history(emu, pt):
+    """4 rounds, window 6 frames, 2 frames per clip, 128x128 frames (66-token blocks, so evicted
+    frames release whole 128-token pages): every round's clip equals the oracle's sampler over
+    the full history with absolute positions and the history mask; every context frame goes
+    through the transformer once; from round 2 on the plan is refreshed in place."""
+    from videogpt_b200 import LVMProcessor
+    from videogpt_b200.rollout import LatentRollout, window_start
+    n0, gen, window, H, W, steps, rounds = 2, 2, 6, 128, 128, 2, 4
+    bl = (H // 16) * (W // 16) + 2
+    m, sd = _model()
+    lat = synth.synthetic_latents(n0 + gen * rounds, H, W, seed=3)
+    history = [x.clone() for x in lat[:n0]]
+    noises = [lat[n0 + gen * r:n0 + gen * (r + 1)] for r in range(rounds)]
+    ro = LatentRollout(m, LVMProcessor(synth.SingleIdTagTokenizer()), gen, max_frame_window=window,
+                       num_inference_steps=steps, img_guidance_scale=1.5, prediction_type=pt).start(history)
+    ws_of_frame, plans, freed = {}, [], False
+    for r in range(rounds):
+        n_hist = len(history)
+        ws = window_start(n_hist, gen, window)
+        for f in range(n_hist):
+            ws_of_frame.setdefault(f, ws)
+        got = ro.next_clip(initial_noise=noises[r])
+        plans.append(ro.engine.plan)
+        freed = freed or min(ro._phys) > 0
+        d = po.frame_block_inputs(n_hist, gen, H, W, True, 1)
+        mk = dict(input_ids=d["input_ids"], input_img_latents=history, input_image_sizes=d["input_image_sizes"],
+                  attention_mask=_history_mask(d, n_hist, gen, bl, ws_of_frame, ws), position_ids=d["position_ids"],
+                  denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
+                  use_img_cfg=True)
+        with torch.no_grad():
+            want = so.euler_sample([x.clone() for x in noises[r]] * 2,
+                                   lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                                   mk, num_steps=steps, prediction_type=pt)[:gen]
+        assert _maxerr(got, want) < TOL, f"round {r}"
+        history += [x.clone() for x in got]
+    assert ro.prefilled_frames == n0 + gen * (rounds - 1)          # every context frame exactly once
+    assert plans[1] is plans[2] is plans[3]                          # refreshed in place (graph stays valid)
+    assert freed                                                     # pages behind the window were released
+
+
+def test_rollout_equals_the_reference_round_while_the_window_holds_the_history(emu):
+    """No eviction: a rollout round IS the reference's round (pipeline.next_clip_latents on all
+    frames so far) -- same mask, same positions -- although only the new frames are prefilled."""
+    from videogpt_b200 import LVMProcessor
+    from videogpt_b200.rollout import LatentRollout
+    n0, gen, H, W, steps = 1, 2, 64, 64, 2
+    m, sd = _model()
+    pipe = _pipe(m)
+    lat = synth.synthetic_latents(n0 + 3 * gen, H, W, seed=9)
+    history = [x.clone() for x in lat[:n0]]
+    ro = LatentRollout(m, pipe.processor, gen, max_frame_window=16, num_inference_steps=steps,
+                       img_guidance_scale=1.5, prediction_type="x1").start(history)
+    outs = []
+    for r in range(3):
+        outs.append(ro.next_clip(initial_noise=lat[n0 + gen * r:n0 + gen * (r + 1)]))
+    for r in range(3):        # afterwards, so that the rollout's cache is not disturbed by these calls
+        want = pipe.next_clip_latents(history, gen, num_inference_steps=steps, img_guidance_scale=1.5,
+                                      prediction_type="x1", dtype=torch.float32,
+                                      initial_noise=lat[n0 + gen * r:n0 + gen * (r + 1)])
+        assert _maxerr(outs[r], want) < TOL
+        history += [x.clone() for x in outs[r]]
+
+
+def test_pipeline_rollout_latents_persistent_and_recomputed_agree_without_eviction(emu):
+    m, _ = _model()
+    pipe = _pipe(m)
+    ctx = synth.synthetic_latents(2, 64, 64, seed=4)
+    kw = dict(num_inference_steps=2, img_guidance_scale=1.5, seed=11, prediction_type="v", dtype=torch.float32)
+    a = pipe.rollout_latents(ctx, [2, 2, 2], persistent_cache=True, **kw)
+    b = pipe.rollout_latents(ctx, [2, 2, 2], persistent_cache=False, **kw)
+    assert len(a) == len(b) == 6 and _maxerr(a, b) < TOL
+    # with eviction the two differ by design (windowed attention over cached K/V vs recompute)
+    c = pipe.rollout_latents(ctx, [2, 2, 2], persistent_cache=True, max_frame_window=4, **kw)
+    assert _maxerr(c[:2], a[:2]) < TOL and all(torch.isfinite(x).all() for x in c)

@@ -10,6 +10,7 @@ from .scheduler import LVMScheduler  # noqa: F401
 from .model import LVM  # noqa: F401
 from .pipeline import LVMPipeline  # noqa: F401
 from .transform import replace_attention  # noqa: F401
+from .rollout import LatentRollout  # noqa: F401
 
 __all__ = ["LVMProcessor", "LVMCollator", "FrameGeometry", "LVMScheduler", "LVM", "LVMPipeline",
-           "replace_attention"]
+           "replace_attention", "LatentRollout"]

@@ -83,6 +83,11 @@ class SequenceSpec:
     arg_a: np.ndarray
     arg_b: np.ndarray
     latent_rows: List[tuple] = field(default_factory=list)   # (latent index, seq-relative first image row)
+    # streaming rollout (rollout.py): the first n_cached prefix rows already have their K/V in the
+    # pool (computed in an earlier round) and are not recomputed; `pages` names the physical pool
+    # page of every logical page of this sequence (None: pages are dealt out by build_plan)
+    n_cached: int = 0
+    pages: Optional[np.ndarray] = None
 
 
 @dataclass
@@ -242,10 +247,16 @@ def shard_rows(lo: int, hi: int, rank: int, world: int):
 
 
 def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int, lat_h: int,
-               lat_w: int, device, shard: Optional[tuple] = None) -> ClipPlan:
+               lat_w: int, device, shard: Optional[tuple] = None, max_pages: Optional[int] = None,
+               pool_pages: Optional[int] = None) -> ClipPlan:
     """``shard=(rank, world)``: row-sharded plan of one rank of a sequence-parallel group -- the
     page table, key codes and tile classification describe the WHOLE sequences (every rank holds
-    all K/V), the per-phase row arrays only this rank's chunk of every sequence."""
+    all K/V), the per-phase row arrays only this rank's chunk of every sequence.
+
+    ``max_pages`` / ``pool_pages``: fixed capacities of the page table (logical pages per
+    sequence) and of the pool, for plans that are refreshed in place round after round
+    (``NextClipEngine.set_plan(keep_kv=True)``); specs may then carry their own physical pages and
+    a cached prefix."""
     S = len(specs)
     if shard is not None:
         s_rank, s_world = shard
@@ -255,16 +266,43 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
         T = sp.n_prefix + sp.n_active
         assert all(len(a) == T for a in (sp.positions, sp.codes, sp.kinds, sp.arg_a, sp.arg_b))
         if sp.n_prefix and sp.n_active:
-            # caching the prefix is exact only if no prefix query can see an active key
-            if int(sp.codes[:sp.n_prefix].max()) >= int(sp.codes[sp.n_prefix:].min()):
+            # caching the prefix is exact only if no prefix query can see an active key (rows whose
+            # K/V are already cached are no queries here; their codes only describe them as keys)
+            if sp.n_cached < sp.n_prefix and \
+                    int(sp.codes[sp.n_cached:sp.n_prefix].max()) >= int(sp.codes[sp.n_prefix:].min()):
                 raise ValueError("prefix rows can see active rows: this mask cannot be prefix-cached")
     pages = [(sp.n_prefix + sp.n_active + PAGE_TOKENS - 1) // PAGE_TOKENS for sp in specs]
-    max_pages = max(pages)
+    if max_pages is None:
+        max_pages = max(pages)
+    elif max(pages) > max_pages:
+        raise ValueError(f"a sequence needs {max(pages)} pages, the page table holds {max_pages}")
     page_table = np.zeros((S, max_pages), np.int32)
+    explicit = [sp.pages is not None for sp in specs]
+    if any(explicit) != all(explicit):
+        raise ValueError("either every sequence names its physical pages or none does")
     base = 0
     for s, n in enumerate(pages):
-        page_table[s, :n] = np.arange(base, base + n)
-        base += n
+        if explicit[s]:
+            if len(specs[s].pages) < n:
+                raise ValueError(f"sequence {s}: {n} logical pages, {len(specs[s].pages)} physical pages given")
+            page_table[s, :n] = specs[s].pages[:n]
+            base = max(base, int(np.max(specs[s].pages[:n])) + 1)
+        else:
+            page_table[s, :n] = np.arange(base, base + n)
+            base += n
+    if all(explicit):
+        used = np.concatenate([page_table[s, :n] for s, n in enumerate(pages)])
+        if len(np.unique(used)) != len(used):
+            raise ValueError("two logical pages share a physical page")
+    if pool_pages is not None:
+        if base > pool_pages:
+            raise ValueError(f"plan needs physical page {base - 1}, the pool holds {pool_pages}")
+        base = pool_pages
+    for sp in specs:
+        if not (0 <= sp.n_cached <= sp.n_prefix):
+            raise ValueError("n_cached must lie inside the prefix")
+        if sp.n_cached and shard is not None:
+            raise ValueError("a cached prefix is not supported on row-sharded plans")
     tiles_per_page = PAGE_TOKENS // ATTN_KV_TILE
     max_k_tiles = max_pages * tiles_per_page
     k_code = np.full((S, max_pages * PAGE_TOKENS), INT_MAX, np.int32)
@@ -282,7 +320,7 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
         pos, slot, qc, kd, aa, ab, seqs = [], [], [], [], [], [], []
         row0, max_q = 0, 0
         for s, sp in enumerate(specs):
-            lo, hi = (0, sp.n_prefix) if which == "prefix" else (sp.n_prefix, sp.n_prefix + sp.n_active)
+            lo, hi = (sp.n_cached, sp.n_prefix) if which == "prefix" else (sp.n_prefix, sp.n_prefix + sp.n_active)
             kv_len = hi                        # every key up to the end of this phase's rows
             if shard is not None:
                 lo, hi = shard_rows(lo, hi, s_rank, s_world)
@@ -344,12 +382,42 @@ class NextClipEngine:
         self.plan: Optional[ClipPlan] = None
         self._graph = None
         self._rope_tab = None
+        self.rope_reserve = 0            # positions to provision the RoPE table for (rollouts grow)
         half = 128
         self._t_freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half).to(self.device)
         self._inv_freq = (1.0 / (rope_theta ** (torch.arange(0, self.D, 2, dtype=torch.int64).float() / self.D))).to(self.device)
 
     # ---- setup ---------------------------------------------------------------------------------
-    def set_plan(self, plan: ClipPlan):
+    def _refresh_in_place(self, new: ClipPlan) -> bool:
+        """Same shapes as the current plan (a later round of a rollout, the next clip of a stream):
+        overwrite the plan's device arrays instead of replacing them, so workspaces, K/V pool and the
+        captured CUDA graph -- which holds these arrays' addresses -- all stay valid."""
+        old = self.plan
+        if old is None or self.peers is not None or old.shard is not None or new.shard is not None:
+            return False
+        scal = lambda p: (p.n_latents, p.n_ctx_latents, p.lat_h, p.lat_w, p.total_pages, p.prefix.rows, p.step.rows,
+                          p.prefix.max_q_rows, p.step.max_q_rows)
+        if scal(old) != scal(new) or self._rope_tab is None or new.max_pos > self._rope_tab.shape[0]:
+            return False
+        pairs = [(getattr(old, k), getattr(new, k)) for k in ("page_table", "k_code", "k_tile_minmax", "lat_row0")]
+        for ph in ("prefix", "step"):
+            o, n = getattr(old, ph), getattr(new, ph)
+            pairs += [(getattr(o, k), getattr(n, k)) for k in ("row_pos", "row_slot", "q_code", "kind", "arg_a", "arg_b", "seqs")]
+        if any(a.shape != b.shape for a, b in pairs):
+            return False
+        for a, b in pairs:
+            a.copy_(b)
+        old.specs, old.max_pos = new.specs, new.max_pos
+        self.prefilled = False
+        return True
+
+    def set_plan(self, plan: ClipPlan, keep_kv: bool = False):
+        """``keep_kv``: the K/V pool carries rows cached by an earlier plan (``SequenceSpec.n_cached``):
+        keep its contents -- and, when nothing but the contents of the plan's arrays changed, keep
+        everything (``_refresh_in_place``)."""
+        if keep_kv and self._refresh_in_place(plan):
+            return
+        old_kv = getattr(self, "kv", None) if keep_kv and self.peers is None else None
         self.plan = plan
         self._graph = None
         dev, bf = self.device, ACT_DTYPE
@@ -366,7 +434,12 @@ class NextClipEngine:
         if self.peers is None:
             if plan.shard is not None:
                 raise ValueError("a row-sharded plan needs an engine with a peer group")
-            self.kv = torch.zeros(kv_shape, device=dev, dtype=bf)
+            if old_kv is not None and tuple(old_kv.shape) == kv_shape:
+                self.kv = old_kv              # physical pages keep their contents
+            else:
+                if any(sp.n_cached for sp in plan.specs):
+                    raise ValueError("the plan counts on cached K/V rows but the pool is being (re)allocated")
+                self.kv = torch.zeros(kv_shape, device=dev, dtype=bf)
             self.pred = torch.zeros_like(self.z)
             self._kv_ptrs = None
         else:
@@ -396,7 +469,7 @@ class NextClipEngine:
         self.scalars = torch.zeros(3, device=dev, dtype=torch.float32)
         self.pos_rows = self._pos_rows(plan.lat_h, plan.lat_w)
         if self._rope_tab is None or self._rope_tab.shape[0] < plan.max_pos:
-            self._rope_tab = ops.rope_table(self._inv_freq, max(plan.max_pos, 1), self.D)
+            self._rope_tab = ops.rope_table(self._inv_freq, max(plan.max_pos, self.rope_reserve, 1), self.D)
         self.prefilled = False
         if self.peers is not None:
             self.peers.host_barrier()         # every rank has finished allocating

@@ -273,6 +273,45 @@ class LVMPipeline:
                             offload_kv_cache=False, prediction_type=prediction_type, vae=self.vae)
         return samples.chunk(1 + num_cfg, dim=0)[0]                                               # 297
 
+    @torch.no_grad()
+    def rollout_latents(self, context_latents: List[torch.Tensor], gen_nums: List[int],
+                        num_inference_steps: int = 50, img_guidance_scale: float = 1.6,
+                        use_img_guidance: bool = True, seed: Optional[int] = None,
+                        time_shifting_factor: float = 1.0, prediction_type: str = "v",
+                        dtype: torch.dtype = torch.bfloat16, clean_image_noise_level: float = 0.0,
+                        max_frame_window: int = 16, persistent_cache: bool = True) -> List[torch.Tensor]:
+        """The autoregressive loop of ``prompt_condition_frame_block_autoregressive_inference``
+        (pipeline.py:418-424, 485-500) in LATENT space: no VAE decode / uint8 / re-encode between
+        rounds.  Returns the latents of all generated frames.
+
+        ``persistent_cache`` (needs equal ``gen_nums``): every context frame is prefilled once and
+        its K/V stay in the paged pool across rounds (``rollout.LatentRollout`` -- identical to the
+        reference's round while the window holds the whole history, windowed attention over the
+        cached K/V afterwards).  Otherwise every round recomputes its window from scratch exactly
+        like the reference (positions restart at the window start)."""
+        self.model.to(dtype)
+        generated: List[torch.Tensor] = []
+        if persistent_cache and len(set(gen_nums)) == 1:
+            from .rollout import LatentRollout
+            ro = LatentRollout(self.model, self.processor, gen_nums[0], max_frame_window, num_inference_steps,
+                               img_guidance_scale, use_img_guidance, time_shifting_factor, prediction_type,
+                               clean_image_noise_level, rounds_hint=len(gen_nums)).start(context_latents)
+            for _ in gen_nums:
+                generated += ro.next_clip(seed=seed)
+            return generated
+        frames = [x.to(self.device, dtype) for x in context_latents]
+        for k, gen_num in enumerate(gen_nums):
+            if len(frames) + gen_num > max_frame_window:                                  # 421-422
+                frames = frames[gen_num + len(frames) - max_frame_window:]
+            out = self.next_clip_latents(frames, gen_num, num_inference_steps=num_inference_steps,
+                                         img_guidance_scale=img_guidance_scale, use_img_guidance=use_img_guidance,
+                                         seed=seed, time_shifting_factor=time_shifting_factor,
+                                         prediction_type=prediction_type, dtype=dtype)
+            generated += out
+            a = clean_image_noise_level or 0.0
+            frames = frames + [((1 - a) * x + a * torch.randn_like(x)) if a else x for x in out]
+        return generated
+
     # ---- reference user API --------------------------------------------------------------------
     @torch.no_grad()
     def __call__(self, input_images=None, height: int = 1024, width: int = 1024, gen_num: int = 1,

@@ -57,9 +57,15 @@ class LVMScheduler:
         else:
             e = model.prepare_single_frame(mk["input_ids"], mk["input_img_latents"], mk["input_image_sizes"],
                                            mk["attention_mask"], mk["position_ids"], lat_h, lat_w)
+        return self.run_prepared(e, z, bool(mk["use_img_cfg"]), float(mk["img_cfg_scale"]), prediction_type)
+
+    def run_prepared(self, e, z, use_cfg: bool, guidance: float, prediction_type: str):
+        """The sampling loop on an engine whose plan is set and whose prefix is prefilled
+        (``_run_engine`` after ``LVM.prepare_*``; ``rollout.LatentRollout`` after its own plan)."""
+        is_list = isinstance(z, list)
+        lat_h, lat_w = z[0].shape[-2:]
         n = e.plan.n_latents
         assert len(z) == n
-        use_cfg = bool(mk["use_img_cfg"])
         e.z.copy_(torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0) if is_list else z)
         vel = torch.empty_like(e.z[: n // 2 if use_cfg else n]) if self.record_velocity is not None else None
         e.uniform_t = True              # one sigma for every latent (scheduler.py:171)
@@ -68,8 +74,7 @@ class LVMScheduler:
                 e.t.fill_(float(self.sigma[i]))
                 e.predict()
                 oms, ds = self._scalars(i)
-                ops.cfg_euler(e.z, e.pred, use_cfg, prediction_type == "x1", oms, ds,
-                              float(mk["img_cfg_scale"]), vel_out=vel)
+                ops.cfg_euler(e.z, e.pred, use_cfg, prediction_type == "x1", oms, ds, guidance, vel_out=vel)
                 if vel is not None:
                     self.record_velocity.append(vel.clone())
         finally:
