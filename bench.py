@@ -458,6 +458,10 @@ def main():
     if os.environ.get("VGPT_FAULT_DUMP"):      # debugging aid: dump every thread's stack after N seconds and exit
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["VGPT_FAULT_DUMP"]), exit=True)
+    if args.parallelism == "sp":
+        # sequence-parallel ranks spin on each other inside kernels: load every kernel image up front
+        # so that no rank stops in the driver (lazy module load) in the middle of a clip
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
