@@ -339,3 +339,15 @@ def test_pipeline_rollout_latents_persistent_and_recomputed_agree_without_evicti
     # with eviction the two differ by design (windowed attention over cached K/V vs recompute)
     c = pipe.rollout_latents(ctx, [2, 2, 2], persistent_cache=True, max_frame_window=4, **kw)
     assert _maxerr(c[:2], a[:2]) < TOL and all(torch.isfinite(x).all() for x in c)
+
+
+def test_rollout_refuses_to_continue_after_the_engine_was_used_for_another_clip(emu):
+    from videogpt_b200.rollout import LatentRollout
+    m, _ = _model()
+    pipe = _pipe(m)
+    ctx = synth.synthetic_latents(2, 64, 64, seed=4)
+    ro = LatentRollout(m, pipe.processor, 2, num_inference_steps=1, prediction_type="x1").start(ctx)
+    ro.next_clip(seed=1)
+    pipe.next_clip_latents(ctx, 2, num_inference_steps=1, dtype=torch.float32, seed=1)     # replaces the engine's plan
+    with pytest.raises(RuntimeError, match="start\\(\\) again"):
+        ro.next_clip(seed=1)

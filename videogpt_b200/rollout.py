@@ -72,6 +72,7 @@ class LatentRollout:
         self._phys = {}            # absolute page -> physical page (conditional sequence)
         self._free: List[int] = []
         self.prefilled_frames = 0  # statistics: context frames pushed through the transformer so far
+        self._plan = self._kv = None
 
     # ---- set-up ----------------------------------------------------------------------------------
     def start(self, context_latents: List[torch.Tensor]):
@@ -167,6 +168,9 @@ class LatentRollout:
             raise RuntimeError("call start(context_latents) first")
         if self.model._engine is not e:
             raise RuntimeError("the model rebuilt its engine (weights moved or changed): start() the rollout again")
+        if self.round > 0 and (e.plan is not self._plan or e.kv is not self._kv):
+            raise RuntimeError("the engine was used for something else since the last round: its K/V pool no longer "
+                               "holds this rollout's context; start() again")
         specs, c = self._specs()
         new_ctx = self.pending[c - self.n_done:]
         plan = eng.build_plan(specs, gen * (2 if self.use_cfg else 1), len(new_ctx), self.lat_h, self.lat_w, self.dev,
@@ -191,5 +195,6 @@ class LatentRollout:
         a = self.noise_level
         self.pending = [((1 - a) * x + a * torch.randn_like(x)) if a else x for x in out]
         self.n_done, self.n_hist = self.n_hist, self.n_hist + gen
+        self._plan, self._kv = e.plan, e.kv
         self.round += 1
         return out
