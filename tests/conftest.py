@@ -50,4 +50,5 @@ def emu(monkeypatch):
         return self._engine
     monkeypatch.setattr(model.LVM, "engine", engine_cpu)
     emu_ops.calls.clear()
+    emu_ops._peer_bufs.clear()
     return emu_ops

@@ -104,6 +104,58 @@ def rope_kv_append(qkv, row_pos, row_slot, table, k_pool, v_pool, heads: int, he
     v_pool[page, :, off, :] = v[keep]
 
 
+# ---- sequence parallel: the producing kernels store into every rank's buffers (peer.LocalPeerGroup) ----
+_peer_bufs = []     # uint8 tensors of the virtual ranks' shared buffers (tests register them)
+
+
+def register_peer_buffers(shared):
+    """``shared``: a ``peer.SharedBuffer`` of a ``LocalPeerGroup`` on CPU -- remember every rank's bytes so
+    that the raw pointers the engine hands to the ``*_peers`` wrappers can be turned back into tensors."""
+    import ctypes
+    n = shared.local.numel()
+    for ptr in shared.ptrs:
+        _peer_bufs[:] = [(b, t) for b, t in _peer_bufs if b != ptr]       # an address can be reused by a later test
+        _peer_bufs.append((ptr, torch.frombuffer((ctypes.c_char * n).from_address(ptr), dtype=torch.uint8)))
+
+
+def _from_ptr(ptr: int, dtype):
+    for base, t in _peer_bufs:
+        if base <= ptr < base + t.numel():
+            return t[ptr - base:].view(dtype)
+    raise AssertionError("pointer does not belong to a registered peer buffer")
+
+
+def rope_kv_append_peers(qkv, row_pos, row_slot, table, k_pool_ptrs, v_pool_ptrs, n_pools: int, heads: int,
+                         head_dim: int):
+    per_page = heads * PAGE_TOKENS * head_dim
+    q0 = qkv.clone()
+    for g in range(n_pools):
+        k = _from_ptr(int(k_pool_ptrs[g]), qkv.dtype)
+        v = _from_ptr(int(v_pool_ptrs[g]), qkv.dtype)
+        k = k[:k.numel() // per_page * per_page].view(-1, heads, PAGE_TOKENS, head_dim)
+        v = v[:v.numel() // per_page * per_page].view(-1, heads, PAGE_TOKENS, head_dim)
+        n = min(k.shape[0], v.shape[0])          # views run to the end of the buffer: trim to a common length
+        k, v = k[:n], v[:n]
+        qkv.copy_(q0)                            # q is rotated in place: once per call, not once per pool
+        rope_kv_append(qkv, row_pos, row_slot, table, k, v, heads, head_dim)
+
+
+def final_layer_rows(hidden, row_kind, row_a, row_b, mod, w, bias, pred_ptrs, n_preds: int, lat_h: int, lat_w: int):
+    _log("final_layer_rows")
+    rows, hs = hidden.shape
+    C, pw = 4, lat_w // 2
+    preds = [_from_ptr(int(pred_ptrs[g]), hidden.dtype) for g in range(n_preds)]
+    for r in range(rows):
+        if int(row_kind[r]) != ROW_NOISY_PATCH:
+            continue
+        j, tkn = int(row_a[r]), int(row_b[r])
+        y = _final_rows(hidden[r:r + 1], mod[j, :hs], mod[j, hs:], w, bias)[0].reshape(2, 2, C)     # (p, q, c)
+        py, px = tkn // pw, tkn % pw
+        for p_ in preds:
+            view = p_[:(j + 1) * C * lat_h * lat_w].view(j + 1, C, lat_h, lat_w)
+            view[j, :, 2 * py:2 * py + 2, 2 * px:2 * px + 2] = y.permute(2, 0, 1).to(view.dtype)
+
+
 def attention(q, out, k_pool, v_pool, page_table, seqs, max_q_rows: int, q_code, k_code, k_tile_minmax,
               heads: int, head_dim: int, scale: float, impl: str = None):
     _log("attention")

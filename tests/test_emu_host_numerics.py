@@ -351,3 +351,60 @@ def test_rollout_refuses_to_continue_after_the_engine_was_used_for_another_clip(
     pipe.next_clip_latents(ctx, 2, num_inference_steps=1, dtype=torch.float32, seed=1)     # replaces the engine's plan
     with pytest.raises(RuntimeError, match="start\\(\\) again"):
         ro.next_clip(seed=1)
+
+
+# ---- sequence parallelism: row-sharded plans on virtual ranks --------------------------------------
+@pytest.mark.parametrize("world,geom", [(2, (3, 2, 64, 96)), (3, (2, 2, 64, 64)), (4, (8, 2, 64, 64)), (8, (4, 4, 128, 128)), (8, (1, 1, 32, 32))])
+def test_row_sharded_virtual_ranks_reproduce_the_unsharded_engine_and_the_oracle(emu, world, geom):
+    """CPU twin of tests/test_sequence_parallel.py::test_virtual_ranks_match_unsharded_engine_bit_exact:
+    every virtual rank runs its chunk of the rows of every sequence, the K/V-append and final-layer
+    emulations store into every rank's buffers through the raw pointers the engine hands out, and
+    all ranks end up with the complete K/V pool and the complete prediction -- equal to the
+    unsharded engine's (fp32 rounding) and, over 3 Euler steps, to the oracle's sampler."""
+    from videogpt_b200 import engine as eng, peer
+    n_ctx, n_gen, H, W = geom
+    dims = synth.REDUCED
+    sd = synth.init_state_dict(dims, seed=0, dtype=torch.float32)
+    dev = torch.device("cpu")
+    w = eng.EngineWeights(sd, dims.num_hidden_layers, dev)
+    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+    specs, n_lat, n_ctx_lat = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
+                                                    d["denoise_image_sizes"], d["time_emb_inx"])
+    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)
+    ctx, z0 = torch.cat(lat[:n_ctx], 0), torch.cat(lat[n_ctx:] * 2, 0)
+
+    def engine(peers=None):
+        return eng.NextClipEngine(w, dims.hidden_size, dims.intermediate_size, dims.num_hidden_layers,
+                                  dims.num_attention_heads, dims.rms_norm_eps, dims.rope_theta, dev,
+                                  use_cuda_graph=False, peers=peers)
+
+    ref = engine()
+    ref.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev))
+    ref.prefill(ctx)
+    ranks = [engine(m) for m in peer.LocalPeerGroup.create(world, dev)]
+    for r, e in enumerate(ranks):
+        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev, shard=(r, world)))
+        emu.register_peer_buffers(e._kv_shared)
+        emu.register_peer_buffers(e._pred_shared)
+    eng.run_lockstep([e.prefill_steps(ctx) for e in ranks])
+    for e in ranks:
+        assert (e.kv - ref.kv).abs().max() < 1e-4
+    sigma = torch.linspace(0, 1, 4)
+    for e in [ref] + ranks:
+        e.z.copy_(z0)
+    for i in range(3):
+        for e in [ref] + ranks:
+            e.t.fill_(float(sigma[i]))
+        ref.predict()
+        eng.run_lockstep([e.predict_steps() for e in ranks])
+        for e in ranks:
+            assert (e.pred - ref.pred).abs().max() < 1e-4 * float(ref.pred.abs().max()), f"step {i}"
+        for e in [ref] + ranks:
+            emu.cfg_euler(e.z, e.pred, True, True, float(1 - sigma[i]), float(sigma[i + 1] - sigma[i]), 1.5)
+    mk, z_list = _mk(n_ctx, n_gen, H, W)
+    with torch.no_grad():
+        want = so.euler_sample([x.clone() for x in z_list] * 2,
+                               lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(dims), z, t, **kw),
+                               mk, num_steps=3, prediction_type="x1")
+    for e in ranks:
+        assert _maxerr([e.z], [torch.cat(want, 0)]) < 5 * TOL

@@ -448,14 +448,15 @@ class NextClipEngine:
             if plan.shard != (self.peers.rank, self.peers.world):
                 raise ValueError(f"plan shard {plan.shard} does not match the peer group "
                                  f"({self.peers.rank}, {self.peers.world})")
-            kv_bytes, pred_bytes = 2 * math.prod(kv_shape), 2 * self.z.numel()
+            esize = self.z.element_size()
+            kv_bytes, pred_bytes = esize * math.prod(kv_shape), esize * self.z.numel()
             if self._kv_shared is None or self._kv_shared.local.numel() < kv_bytes:
                 self._kv_shared = self.peers.alloc(kv_bytes)
             if self._pred_shared is None or self._pred_shared.local.numel() < pred_bytes:
                 self._pred_shared = self.peers.alloc(pred_bytes)
             self.kv = self._kv_shared.local[:kv_bytes].view(bf).view(kv_shape)
             self.pred = self._pred_shared.local[:pred_bytes].view(bf).view(self.z.shape)
-            pool_bytes = 2 * math.prod(kv_shape[2:])
+            pool_bytes = esize * math.prod(kv_shape[2:])
             self._kv_ptrs = [(self._kv_shared.ptr_array((2 * li) * pool_bytes),
                               self._kv_shared.ptr_array((2 * li + 1) * pool_bytes)) for li in range(self.L)]
             self._pred_ptrs = self._pred_shared.ptr_array()
