@@ -14,7 +14,6 @@ refuses CPU tensors.  The kernels themselves are checked against the oracle by t
 """
 from __future__ import annotations
 
-import math
 
 import torch
 import torch.nn.functional as F

@@ -15,7 +15,7 @@ Differences from the reference that a caller can observe:
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import numpy as np
 import torch

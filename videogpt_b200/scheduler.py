@@ -10,7 +10,7 @@ applies the update with the CUDA kernel.  CPU tensors are rejected: there is no 
 from __future__ import annotations
 
 import gc
-from typing import Callable, List, Optional
+from typing import Callable, Optional
 
 import torch
 

@@ -9,7 +9,7 @@ embedders, N(0, 0.02) timestep MLPs) and the HF Phi-3 init (N(0, 0.02)), EXCEPT 
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, asdict
+from dataclasses import dataclass
 from typing import Dict
 
 import numpy as np

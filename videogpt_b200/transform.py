@@ -18,7 +18,6 @@ import math
 from types import MethodType
 from typing import Optional
 
-import numpy as np
 import torch
 
 from . import ops
