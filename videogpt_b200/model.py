@@ -251,6 +251,12 @@ class LVM(nn.Module):
             self._peers = peer.PeerGroup(ranks, group=hccl_info.group)
         return self._peers
 
+    def invalidate_plan_cache(self):
+        """Forget which conditioning inputs the engine's current plan belongs to (callers that set
+        engine plans themselves -- ``rollout.LatentRollout`` -- call this so that the next
+        ``prepare_*`` rebuilds instead of trusting a plan it did not make)."""
+        self._plan_key = self._layout_key = self._plan_refs = None
+
     def _shard(self):
         e = self._engine
         return None if e is None or e.peers is None else (e.peers.rank, e.peers.world)

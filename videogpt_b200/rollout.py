@@ -81,7 +81,7 @@ class LatentRollout:
         self.lat_h, self.lat_w = (int(x) for x in context_latents[0].shape[-2:])
         self.bl = (self.lat_h // 2) * (self.lat_w // 2) + 2          # tokens per frame block
         e = self.engine = self.model.engine()
-        self.model._plan_key = self.model._layout_key = None          # the engine's plan is ours now
+        self.model.invalidate_plan_cache()                            # the engine's plan is ours now
         self.dev = e.device
         self.pending = [x.to(self.dev, eng.ACT_DTYPE).reshape(1, 4, self.lat_h, self.lat_w) for x in context_latents]
         self.n_hist, self.n_done = len(self.pending), 0
@@ -166,7 +166,7 @@ class LatentRollout:
         e, gen = self.engine, self.gen
         if e is None:
             raise RuntimeError("call start(context_latents) first")
-        if self.model._engine is not e:
+        if self.model.engine() is not e:
             raise RuntimeError("the model rebuilt its engine (weights moved or changed): start() the rollout again")
         if self.round > 0 and (e.plan is not self._plan or e.kv is not self._kv):
             raise RuntimeError("the engine was used for something else since the last round: its K/V pool no longer "
@@ -178,7 +178,7 @@ class LatentRollout:
         if plan.max_pos > e.rope_reserve:
             e.rope_reserve = 2 * plan.max_pos
         e.set_plan(plan, keep_kv=self.round > 0)
-        self.model._plan_key = self.model._layout_key = None
+        self.model.invalidate_plan_cache()
         e.prefill(torch.cat(new_ctx, 0) if new_ctx else None)
         self.prefilled_frames += len(new_ctx)
         if initial_noise is not None:
