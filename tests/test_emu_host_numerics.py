@@ -408,3 +408,70 @@ def test_row_sharded_virtual_ranks_reproduce_the_unsharded_engine_and_the_oracle
                                mk, num_steps=3, prediction_type="x1")
     for e in ranks:
         assert _maxerr([e.z], [torch.cat(want, 0)]) < 5 * TOL
+
+
+def test_rollout_under_sequence_parallelism_matches_the_single_rank_rollout(emu):
+    """BASELINE configs[2] in full: long-context rollout with the persistent K/V cache AND the rows
+    of every round dealt to the ranks of a sequence-parallel group.  Three virtual ranks run as
+    threads (barrier = threading.Barrier; K/V and predictions stored into every rank's buffers by
+    the emulated peer kernels); with eviction, 4 rounds; every rank must reproduce the single-rank
+    rollout, which the oracle test above pins."""
+    import threading
+    from videogpt_b200 import LVMProcessor, peer
+    from videogpt_b200.rollout import LatentRollout
+    world, n0, gen, window, H, W, steps, rounds = 3, 2, 2, 6, 128, 128, 2, 4
+    lat = synth.synthetic_latents(n0 + gen * rounds, H, W, seed=3)
+    noises = [lat[n0 + gen * r:n0 + gen * (r + 1)] for r in range(rounds)]
+    proc = LVMProcessor(synth.SingleIdTagTokenizer())
+    kw = dict(max_frame_window=window, num_inference_steps=steps, img_guidance_scale=1.5, prediction_type="x1")
+
+    m0, _ = _model()
+    single = LatentRollout(m0, proc, gen, **kw).start(lat[:n0])
+    want = [single.next_clip(initial_noise=noises[r]) for r in range(rounds)]
+
+    bar, lock = threading.Barrier(world), threading.Lock()
+
+    class ThreadPeers(peer.LocalPeerGroup):
+        lockstep = False
+
+        def alloc(self, nbytes):
+            with lock:
+                buf = super().alloc(nbytes)
+                emu.register_peer_buffers(buf)
+            bar.wait()
+            return buf
+
+        def barrier(self):
+            bar.wait()
+
+        host_barrier = barrier
+
+    registry = []
+    members = [ThreadPeers(r, world, torch.device("cpu"), registry) for r in range(world)]
+    models = [_model()[0] for _ in range(world)]
+    got, errors = [None] * world, []
+
+    def rank_main(r):
+        try:
+            from videogpt_b200 import engine as eng
+            m, d = models[r], models[r].dims()
+            m._engine = eng.NextClipEngine(eng.EngineWeights(m.state_dict(), d.num_hidden_layers, "cpu"), d.hidden_size,
+                                           d.intermediate_size, d.num_hidden_layers, d.num_attention_heads,
+                                           d.rms_norm_eps, d.rope_theta, "cpu", use_cuda_graph=False, peers=members[r])
+            m._engine_key = tuple(p._version for p in m.parameters())
+            ro = LatentRollout(m, proc, gen, **kw).start(lat[:n0])
+            got[r] = [ro.next_clip(initial_noise=noises[k]) for k in range(rounds)]
+            assert ro.engine.plan.shard == (r, world)
+        except BaseException as exc:          # a dead rank must not leave the others waiting forever
+            errors.append(exc)
+            bar.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    for r in range(world):
+        for k in range(rounds):
+            assert _maxerr(got[r][k], want[k]) < 5 * TOL, f"rank {r} round {k}"

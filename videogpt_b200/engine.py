@@ -301,8 +301,6 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
     for sp in specs:
         if not (0 <= sp.n_cached <= sp.n_prefix):
             raise ValueError("n_cached must lie inside the prefix")
-        if sp.n_cached and shard is not None:
-            raise ValueError("a cached prefix is not supported on row-sharded plans")
     tiles_per_page = PAGE_TOKENS // ATTN_KV_TILE
     max_k_tiles = max_pages * tiles_per_page
     k_code = np.full((S, max_pages * PAGE_TOKENS), INT_MAX, np.int32)
@@ -451,6 +449,8 @@ class NextClipEngine:
             esize = self.z.element_size()
             kv_bytes, pred_bytes = esize * math.prod(kv_shape), esize * self.z.numel()
             if self._kv_shared is None or self._kv_shared.local.numel() < kv_bytes:
+                if any(sp.n_cached for sp in plan.specs):
+                    raise ValueError("the plan counts on cached K/V rows but the pool is being (re)allocated")
                 self._kv_shared = self.peers.alloc(kv_bytes)
             if self._pred_shared is None or self._pred_shared.local.numel() < pred_bytes:
                 self._pred_shared = self.peers.alloc(pred_bytes)

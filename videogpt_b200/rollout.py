@@ -23,6 +23,12 @@ What it computes (its parity definition, pinned against the oracle by
   depend on position differences, so nothing inside the window moves relative to anything else.
 * ``clean_image_noise_level`` is applied once, when a generated clip becomes context (the
   reference re-noises every re-encoded frame every round).
+
+Under sequence parallelism (``initialize_sequence_parallel_state(P)``, BASELINE configs[2]) the
+rounds run on row-sharded plans: each rank prefills its chunk of the NEW context rows and stores
+their K/V into every peer's pool, which persists across rounds like the single-GPU one; latents
+are replicated, so every rank carries the same history (``clean_image_noise_level > 0`` would
+need a shared generator and is refused).
 """
 from __future__ import annotations
 
@@ -168,13 +174,16 @@ class LatentRollout:
             raise RuntimeError("call start(context_latents) first")
         if self.model.engine() is not e:
             raise RuntimeError("the model rebuilt its engine (weights moved or changed): start() the rollout again")
-        if self.round > 0 and (e.plan is not self._plan or e.kv is not self._kv):
+        if self.round > 0 and (e.plan is not self._plan or e.kv.data_ptr() != self._kv):
             raise RuntimeError("the engine was used for something else since the last round: its K/V pool no longer "
                                "holds this rollout's context; start() again")
         specs, c = self._specs()
         new_ctx = self.pending[c - self.n_done:]
+        shard = None if e.peers is None else (e.peers.rank, e.peers.world)     # sequence parallel: rows dealt to the ranks
+        if shard is not None and seed is None and initial_noise is None:
+            raise ValueError("under sequence parallelism every rank must draw the same noise: pass seed or initial_noise")
         plan = eng.build_plan(specs, gen * (2 if self.use_cfg else 1), len(new_ctx), self.lat_h, self.lat_w, self.dev,
-                              max_pages=self.max_pages, pool_pages=self.pool_pages)
+                              shard=shard, max_pages=self.max_pages, pool_pages=self.pool_pages)
         if plan.max_pos > e.rope_reserve:
             e.rope_reserve = 2 * plan.max_pos
         e.set_plan(plan, keep_kv=self.round > 0)
@@ -193,8 +202,10 @@ class LatentRollout:
         out = sch.run_prepared(e, z, self.use_cfg, self.guidance, self.pt)[:gen]
         # the clip becomes context of the next round
         a = self.noise_level
+        if a and e.peers is not None:
+            raise NotImplementedError("clean_image_noise_level > 0 under sequence parallelism (ranks would draw different noise)")
         self.pending = [((1 - a) * x + a * torch.randn_like(x)) if a else x for x in out]
         self.n_done, self.n_hist = self.n_hist, self.n_hist + gen
-        self._plan, self._kv = e.plan, e.kv
+        self._plan, self._kv = e.plan, e.kv.data_ptr()
         self.round += 1
         return out
