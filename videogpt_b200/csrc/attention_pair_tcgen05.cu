@@ -119,9 +119,15 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   int32_t* t_tmax = t_page + kPairMaxTiles;                                         // max key code of tile i
   int32_t* t_kt = t_tmax + kPairMaxTiles;                                           // logical tile index
 
-  const int seq_id = blockIdx.z, head = blockIdx.y;
+  // Grid (head, query pair, sequence), head fastest.  CTAs are dispatched in linear block order to
+  // whichever SM frees up first, and a CTA's work is (query tiles) x (KV tiles it can see): with the
+  // heads innermost all full pairs of the longest (first: conditional) sequence start before its
+  // half-empty last pair and before the short unconditional sequence -- longest first.  With the
+  // pair index innermost the first wave mixed 4 full pairs : 1 tail per head and left 12 full-size
+  // CTAs for a second round (cost model: makespan 42 -> 36 us at cfg2, 151 -> 113 us at cfg3).
+  const int seq_id = blockIdx.z, head = blockIdx.x;
   const AttnSeqP sq = seqs[seq_id];
-  const int q0 = blockIdx.x * 2 * kPairBM;
+  const int q0 = blockIdx.y * 2 * kPairBM;
   if (q0 >= sq.n_q) return;
   const int rows_cta = min(2 * kPairBM, sq.n_q - q0);          // valid rows of A and B together
   const bool has_b = rows_cta > kPairBM;
@@ -494,7 +500,7 @@ static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int 
     VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     attr_set = true;
   }
-  dim3 grid(q_pairs, H, num_seqs);
+  dim3 grid(H, q_pairs, num_seqs);
   kern<<<grid, kPairThreads, C::kSmem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
                                             (const AttnSeqP*)seqs, q_code, k_code, k_tile_minmax,
                                             max_k_tiles64, H, scale * 1.4426950408889634f, debug_attn_flags());
