@@ -52,19 +52,18 @@ def gemm_cycles(rows, n, k, skinny=False):
     return waves(rows, n, bn) * (k // 16) * (bn / 2 + SS_OVERHEAD) + extra, bn
 
 
-def attention_cycles(seqs):
+def attention_cycles(seqs, head_fastest=True):
     """seqs: [(q_rows, kv_len)] per sequence.  Unit = 128 x 128 tile: 6 S MMAs (SS) + 8 P V MMAs (TS)
-    at head_dim 96.  CTAs = pairs of query tiles, one per SM at a time, list-scheduled in grid order
-    (query pair fastest, then head, then sequence)."""
+    at head_dim 96.  CTAs = pairs of query tiles, one per SM at a time, list-scheduled in grid order:
+    (head, query pair, sequence) with the head innermost (current), or the query pair innermost (the
+    grid of the r01h measurements)."""
     unit = (D // 16) * (128 / 2 + SS_OVERHEAD) + (128 // 16) * (D / 2 + TS_OVERHEAD)
     q_pairs = max(math.ceil(q / 256) for q, _ in seqs)
     ctas = []
     for q, kv in seqs:
-        for _ in range(HEADS):
-            for p in range(q_pairs):
-                tiles = min(2, max(0, math.ceil((q - p * 256) / 128)))
-                if tiles:
-                    ctas.append(tiles * math.ceil(kv / 128))
+        work = [min(2, max(0, math.ceil((q - p * 256) / 128))) * math.ceil(kv / 128) for p in range(q_pairs)]
+        order = [w for w in work for _ in range(HEADS)] if head_fastest else [w for _ in range(HEADS) for w in work]
+        ctas += [w for w in order if w]
     sms = [0.0] * 148
     for c in ctas:                                   # hardware dispatch: next CTA to the first free SM
         i = min(range(148), key=sms.__getitem__)
@@ -98,9 +97,11 @@ def main():
                           + (f", measured {meas} us at burst clocks)" if meas else ")"))
         seqs = [(t_gen, t_ctx + t_gen)] * vids + [(t_gen, t_gen)] * vids
         mk, even, useful = attention_cycles(seqs)
+        mk_old = attention_cycles(seqs, head_fastest=False)[0]
         meas = MEASURED_US.get((name, "attention"))
-        print(f"   attention : makespan {us(mk):6.1f} us, evenly spread {us(even):6.1f}, without padding {us(useful):6.1f}"
-              f" (tensor-pipe chain only" + (f"; measured {meas} us with softmax, 53 us chain alone)" if meas else ")"))
+        print(f"   attention : makespan {us(mk):6.1f} us (query pair innermost, the r01h grid: {us(mk_old):6.1f}), evenly spread "
+              f"{us(even):6.1f}, without padding {us(useful):6.1f} (tensor-pipe chain only"
+              + (f"; measured {meas} us with softmax, 53 us chain alone, both on the r01h grid)" if meas else ")"))
         step = LAYERS * (tot[False] + mk)
         print(f"   GEMMs per layer {us(tot[False]):6.1f} us -> with the skinny tail kernel {us(tot[True]):6.1f} us "
               f"({100 * (tot[True] / tot[False] - 1):+.1f} %)")
