@@ -240,3 +240,74 @@ def test_sequence_parallel_host_flow_world2():
     assert out[0][0] == out[1][0] == [L + 2 * (L + 1)] * 3
     assert out[0][1] == (0, 2) and out[1][1] == (1, 2)
     assert out[0][2][0] + out[1][2][0] == 3 * 26 and out[0][2][1] + out[1][2][1] == 2 * 2 * 26
+
+
+# ---- CFG-branch pairs, numerically: two gloo ranks, kernel wrappers emulated on CPU (fp32) --------
+def _cfg_split_numeric(rank, world):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emu_ops
+    from transformers import Phi3Config
+    from oracle import model_oracle as mo, processor_oracle as po, scheduler_oracle as so
+    from videogpt_b200 import LVM, LVMScheduler, engine, model as model_mod, scheduler as sched_mod, synth
+    torch.set_num_threads(2)
+    for mod in (engine, model_mod, sched_mod):
+        mod.ops = emu_ops
+    engine.ACT_DTYPE = torch.float32
+    torch.cuda.is_available = lambda: True
+    dims = synth.REDUCED
+    sd = synth.init_state_dict(dims, seed=0)
+    m = LVM(Phi3Config(**dims.phi3_kwargs()), device="cpu")
+    m.load_state_dict(sd)
+    m.float().eval()
+
+    def engine_cpu(self):
+        if self._engine is None:
+            d = self.dims()
+            w = engine.EngineWeights(self.state_dict(), d.num_hidden_layers, "cpu")
+            self._engine = engine.NextClipEngine(w, d.hidden_size, d.intermediate_size, d.num_hidden_layers,
+                                                 d.num_attention_heads, d.rms_norm_eps, d.rope_theta, "cpu",
+                                                 use_cuda_graph=False)
+        return self._engine
+    LVM.engine = engine_cpu
+    # the split path calls ops through `from . import ops` inside the function: patch the package attribute too
+    import videogpt_b200
+    videogpt_b200.ops = emu_ops
+    sys.modules["videogpt_b200.ops"] = emu_ops
+
+    n_ctx, n_gen, H, W, steps = 3, 2, 64, 96, 3
+    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)
+    mk = dict(input_ids=d["input_ids"], input_img_latents=lat[:n_ctx], input_image_sizes=d["input_image_sizes"],
+              attention_mask=d["attention_mask"], position_ids=d["position_ids"],
+              denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
+              use_img_cfg=True)
+    grp = parallel.CfgBranchGroup()
+    errs = {}
+    for pt in ("x1", "v"):
+        got = parallel.sample_cfg_split(m, LVMScheduler(steps), [x.clone() for x in lat[n_ctx:]] * 2, mk, grp, pt)
+        cfg = mo.OracleConfig(hidden_size=dims.hidden_size, intermediate_size=dims.intermediate_size,
+                              num_hidden_layers=dims.num_hidden_layers, num_attention_heads=dims.num_attention_heads)
+        w = {k: v.float() for k, v in sd.items()}
+        with torch.no_grad():
+            want = so.euler_sample([x.clone() for x in lat[n_ctx:]] * 2,
+                                   lambda z, t, **kw: mo.frame_block_forward_with_cfg(w, cfg, z, t, **kw),
+                                   mk, num_steps=steps, prediction_type=pt)[:n_gen]
+        a, b = torch.cat(got), torch.cat(want)
+        errs[pt] = float((a - b).abs().max() / b.abs().max())
+    return grp.branch, e_rows(m), errs
+
+
+def e_rows(m):
+    return int(m._engine.plan.step.rows)
+
+
+def test_cfg_branch_split_reproduces_the_oracle_numerically_world2():
+    """Rank 0 runs the conditional sequence (context + clip), rank 1 the unconditional one (clip only,
+    latents renumbered by ``branch_spec``); one all-gather of the raw prediction per Euler step; both
+    ranks must end on the oracle's latents (fp32, kernel wrappers emulated: tests/emu_ops.py)."""
+    out = _spawn(2, _cfg_split_numeric)
+    assert out[0][0] == 0 and out[1][0] == 1
+    assert out[0][1] == out[1][1] == 2 * (64 * 96 // 256 + 2)         # each rank: only its own branch's rows
+    for r in (0, 1):
+        assert all(v < 5e-5 for v in out[r][2].values()), out[r][2]

@@ -126,7 +126,7 @@ def sample_cfg_split(model, scheduler, z: List[torch.Tensor], model_kwargs: dict
     model._plan_key = None                               # the engine does not hold a 2-row plan
     ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in mk["input_img_latents"]], 0) if n_ctx else None
     e.prefill(ctx)
-    z_all = torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0).to(e.device, torch.bfloat16).contiguous()
+    z_all = torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0).to(e.device, eng.ACT_DTYPE).contiguous()
     pred_all = torch.empty_like(z_all)
     for i in range(scheduler.num_steps):
         e.z.copy_(z_all[:n_gen])                         # both halves of z_all are identical (quirk q7)
