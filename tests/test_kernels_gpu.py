@@ -399,3 +399,47 @@ def test_attention_long_context_tile_skipping(ops):
     """8 context clips (32 frames): most KV tiles of a context query tile are fully masked."""
     _attention_case(ops, 32, 4, 64, 64, 2, 96, "prefix", 400)
     _attention_case(ops, 32, 4, 64, 64, 2, 96, "step", 401)
+
+
+# ---------------------------------------------------------------------------------------------
+# experimental attention variants (VGPT_ATTN_VARIANT; csrc/attention_pair_tcgen05.cu kVar*)
+# ---------------------------------------------------------------------------------------------
+def _attention_out(ops, n_ctx, n_gen, H_px, W_px, heads, D, phase, seed):
+    from videogpt_b200 import engine as eng
+    d = po.frame_block_inputs(n_ctx, n_gen, H_px, W_px, True, 1)
+    specs, n_lat, n_c = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
+                                              d["denoise_image_sizes"], d["time_emb_inx"])
+    plan = eng.build_plan(specs, n_lat, n_c, H_px // 8, W_px // 8, DEV)
+    k_pool = _rand((plan.total_pages, heads, 128, D), seed + 1)
+    v_pool = _rand((plan.total_pages, heads, 128, D), seed + 2)
+    ph = plan.prefix if phase == "prefix" else plan.step
+    q = _rand((ph.rows, 3 * heads * D), seed + 3)
+    out = torch.zeros(ph.rows, heads * D, device=DEV, dtype=BF)
+    ops.attention(q[:, :heads * D], out, k_pool, v_pool, plan.page_table, ph.seqs, ph.max_q_rows, ph.q_code,
+                  plan.k_code, plan.k_tile_minmax, heads, D, 1.0 / math.sqrt(D))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.skipif(os.environ.get("VGPT_TEST_EXPERIMENTAL") != "1",
+                    reason="attention variants: written after the round's GPU budget was spent, never run on "
+                           "hardware; set VGPT_TEST_EXPERIMENTAL=1 to validate them")
+@pytest.mark.parametrize("geom", [(4, 4, 256, 256, 4), (3, 5, 176, 320, 2), (2, 2, 64, 96, 2), (32, 4, 64, 64, 2)])
+@pytest.mark.parametrize("phase", ["step", "prefix"])
+def test_attention_variants_against_the_validated_kernel(ops, geom, phase, monkeypatch):
+    """Variant 1 (ragged last KV tile issued with N = ceil16(tail) and tail/16 k-steps) only skips
+    products with zeros: BIT-identical to variant 0.  Variant 2 (every fourth exponential by a
+    degree-3 polynomial on the FMA pipe, relative error 1e-4 before the bf16 rounding of P): within
+    one bf16 ulp of the output scale of variant 0, and still inside the SDPA tolerance."""
+    n_ctx, n_gen, H_px, W_px, heads = geom
+    outs = {}
+    for var in (0, 1, 2, 3):
+        monkeypatch.setenv("VGPT_ATTN_VARIANT", str(var))
+        outs[var] = _attention_out(ops, n_ctx, n_gen, H_px, W_px, heads, 96, phase, 500)
+    monkeypatch.setenv("VGPT_ATTN_VARIANT", "0")
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[1], outs[0]), "trimmed ragged tile changed bits"
+    assert torch.equal(outs[3], outs[2]), "trimmed ragged tile changed bits (with the polynomial)"
+    scale = outs[0].float().abs().max().item()
+    assert (outs[2].float() - outs[0].float()).abs().max().item() <= 2.0 ** -7 * scale
+    assert _rel(outs[2].float(), outs[0].float()) < 2e-3

@@ -11,8 +11,8 @@ WANT = [  # (object, substring of the demangled name, short file name)
     ("gemm2_tcgen05.o", "gemm_bf16_tcgen05_pair_kernel<256, 0>", "gemm_pair_bn256_store"),
     ("gemm2_tcgen05.o", "gemm_bf16_tcgen05_pair_kernel<256, 2>", "gemm_pair_bn256_swiglu"),
     ("gemm2_tcgen05.o", "gemm_bf16_tcgen05_pair_kernel<192, 1>", "gemm_pair_bn192_residual"),
-    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<96>", "attn_pair_d96"),
-    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<128>", "attn_pair_d128"),
+    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<96, 0>", "attn_pair_d96"),
+    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<128, 0>", "attn_pair_d128"),
     ("elementwise.o", "rmsnorm_kernel", "rmsnorm"),
     ("elementwise.o", "rope_kv_append_kernel", "rope_kv_append"),
     ("elementwise.o", "embed_assemble_kernel", "embed_assemble"),

@@ -9,9 +9,13 @@ PT="python -m pytest -q -m gpu --no-header -p no:cacheprovider --tb=short"
 run tests        1500 $PT tests
 # 2. experimental kernels, opt-in: skinny-tail GEMM bit-exactness, then its effect on the bench line
 VGPT_TEST_EXPERIMENTAL=1 run skinny_test 300 $PT tests/test_kernels_gpu.py -k skinny
+VGPT_TEST_EXPERIMENTAL=1 run attn_variants 300 $PT tests/test_kernels_gpu.py -k variants
+for v in 0 1 2 3; do VGPT_ATTN_VARIANT=$v run attnbench_var$v 200 python tools/attn_bench.py; done
+VGPT_ATTN_VARIANT=3 run tests_var3 900 $PT tests/test_kernels_gpu.py tests/test_model_gpu.py -k "attention or next_clip"
 run smoke        200 python __graft_entry__.py --smoke
 run bench_cfg2   600 python bench.py --steps 3 --warmup 3
 VGPT_GEMM_SKINNY_TAIL=1 run bench_cfg2_skinny 600 python bench.py --steps 3 --warmup 3
+VGPT_ATTN_VARIANT=3 run bench_cfg2_var3 600 python bench.py --steps 3 --warmup 3
 run gemmsweep    300 python tools/gemm_bench.py
 VGPT_GEMM_SKINNY_TAIL=1 run gemmsweep_skinny 300 python tools/gemm_bench.py
 # 3. workloads that have never been measured: batch of videos (4 per pass), rollout with / without the cache
@@ -31,6 +35,6 @@ echo "ncu_gemm exit $?" >> gpurun_out/summary.txt
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:attn_pair -s 1 -c 1 \
     -o gpurun_out/prof_attn -f python tools/profile_step.py --no-prefill > gpurun_out/ncu_attn.log 2>&1
 echo "ncu_attn exit $?" >> gpurun_out/summary.txt
-for f in tests skinny_test smoke bench_cfg2 bench_cfg2_skinny bench_cfg4 bench_cfg4_b8 bench_roll bench_roll_re; do
+for f in tests skinny_test attn_variants attnbench_var0 attnbench_var1 attnbench_var2 attnbench_var3 tests_var3 bench_cfg2_var3 smoke bench_cfg2 bench_cfg2_skinny bench_cfg4 bench_cfg4_b8 bench_roll bench_roll_re; do
   echo "=== $f"; tail -n ${TAILN:-6} gpurun_out/$f.log | cut -c1-600; done
 cat gpurun_out/summary.txt

@@ -85,9 +85,32 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
       : "f"(a0), "f"(a1));
 }
 
+// 2^x on the FMA pipe (variant 2): x = n + f with n = rint(x), f in [-0.5, 0.5]; 2^f by a degree-3
+// minimax polynomial (max relative error 1.0e-4, far below the bf16 rounding of P), scaled by 2^n
+// through the exponent field.  The magic-number add leaves n in the low mantissa bits of t.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.055008664727211f, f, 0.24221056699752808f);
+  p = fmaf(p, f, 0.6932829022407532f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// Experimental variants of the kernel (bit mask in VGPT_ATTN_VARIANT, head_dim 96 only; 0 = the
+// kernel that was validated and measured on hardware, and its SASS is unchanged by their presence):
+//   1  ragged last KV tile: keys beyond kv_len are masked for every query, so S is issued with
+//      N = ceil16(tail) columns and P V with tail / 16 k-steps instead of 128 / 8 (exact: the
+//      skipped products are zeros);
+//   2  every fourth exponential (key column % 4 == 3, a function of the column only, so row results
+//      stay independent of the row partition) is computed on the FMA pipe by ex2_poly instead of
+//      the MUFU unit, which is as loaded as the tensor pipe in this kernel.
+constexpr int kVarTrimRagged = 1, kVarPolyExp = 2;
+
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
-template <int D>
+template <int D, int VAR>
 __global__ void __launch_bounds__(kPairThreads, 1)
 attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int out_ld,
@@ -190,7 +213,11 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int n_vis = s_nvis;
 
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if constexpr (VAR & kVarTrimRagged) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // the trimmed-tile state does not fit in 56 (256 x 224 + 128 x 64 = 64 K)
+    } else {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    }
   if (warp == 8) {
     // =================================== TMA producer ===================================
     // (whole warp runs the loop; one elected lane issues)
@@ -216,16 +243,24 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
     constexpr uint32_t idesc_s = make_idesc_bf16(128, kPairBN);        // S = Q K^T (both K-major)
     constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O = P V   (V MN-major)
-    auto issue_s = [&](int x, int stage) {
+    // variant 1: width of S / depth of P V for the LAST visible tile when it is the ragged one
+    int n_last = kPairBN;
+    if constexpr (VAR & kVarTrimRagged) {
+      const int tail = sq.kv_len & (kPairBN - 1);
+      if (tail != 0 && n_vis > 0 && t_kt[n_vis - 1] == n_kt - 1) n_last = (tail + 15) & ~15;
+    }
+    auto issue_s = [&](int x, int stage, bool last = false) {
       if (elect_one_sync()) {
         const uint32_t sk = s_kv + 2 * stage * C::kTileBytes, sqx = s_q + x * C::kTileBytes;
+        uint32_t idesc = idesc_s;
+        if constexpr (VAR & kVarTrimRagged) idesc = last ? make_idesc_bf16(128, n_last) : idesc_s;
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
 #pragma unroll
           for (int ks = 0; ks < C::kCW / 16; ++ks) {
             const uint64_t da = make_smem_desc(sqx + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
             const uint64_t db = make_smem_desc(sk + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
-            umma_f16_ss(tmem + x * 128, da, db, idesc_s, (c | ks) ? 1u : 0u);
+            umma_f16_ss(tmem + x * 128, da, db, idesc, (c | ks) ? 1u : 0u);
           }
         }
         if (!(dbg & 32)) umma_commit(bar_s_full(x));          // (dbg & 32: timing probe, fewer commits)
@@ -237,6 +272,9 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const uint32_t sv = s_kv + 2 * stage * C::kTileBytes + C::kTileBytes;
 #pragma unroll
         for (int ks = 0; ks < kPairBN / 16; ++ks) {
+          if constexpr (VAR & kVarTrimRagged) {
+            if (j == n_vis - 1 && ks >= (n_last >> 4)) continue;   // P is zero in these columns
+          }
           const uint64_t db = make_smem_desc(sv + ks * 16 * C::kRowBytes, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);
           umma_f16_ts(tmem + C::kTmemO + x * D, tmem + (C::kEarlyS ? C::kTmemP : x * 128) + ks * 8, db, idesc_o,
                       (j > 0 || ks > 0) ? 1u : 0u);
@@ -252,8 +290,8 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (n_vis > 0) {                            // prologue: S_A(0), S_B(0)
       mbar_wait(bar_kv_full(stage_s), phase_s);
       tc_fence_after();
-      issue_s(0, stage_s);
-      if (has_b) issue_s(1, stage_s);
+      issue_s(0, stage_s, n_vis == 1);
+      if (has_b) issue_s(1, stage_s, n_vis == 1);
       if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
     }
     if constexpr (C::kEarlyS) {
@@ -268,7 +306,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
             if (x == 0) mbar_wait(bar_kv_full(stage_s), phase_s);
             tc_fence_after();
-            issue_s(x, stage_s);
+            issue_s(x, stage_s, j + 2 == n_vis);
           }
           if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
           tc_fence_after();
@@ -286,13 +324,13 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (has_next) {
           mbar_wait(bar_kv_full(stage_s), phase_s);
           tc_fence_after();
-          issue_s(0, stage_s);                    // S_A(j+1) overwrites P_A(j): behind P V_A(j) in pipe order
+          issue_s(0, stage_s, j + 2 == n_vis);    // S_A(j+1) overwrites P_A(j): behind P V_A(j) in pipe order
         }
         if (has_b) {
           mbar_wait(bar_p_full(1), j & 1);
           tc_fence_after();
           issue_pv(1, stage_o, j, true);
-          if (has_next) issue_s(1, stage_s);
+          if (has_next) issue_s(1, stage_s, j + 2 == n_vis);
         }
         if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
         if (++stage_o == kStages) stage_o = 0;
@@ -382,7 +420,12 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int i = 0; i < 64; ++i) {
           float p0, p1;
           ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), scale_log2, nsub);
-          if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
+          if constexpr (VAR & kVarPolyExp) {
+            p0 = ex2_ftz(p0);
+            p1 = (i & 1) ? ex2_poly(p1) : ex2_ftz(p1);            // key column 2i + 1 = 3 (mod 4): FMA pipe
+          } else {
+            if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
+          }
           fadd2(sum0, sum1, p0, p1);
           s[i] = pack_bf16x2(p0, p1);                             // P overwrites the dead half of s[]
         }
@@ -469,7 +512,12 @@ static int debug_attn_flags() {     // VGPT_DEBUG_ATTN_FLAGS: timing probes only
   return f;
 }
 
-template <int D>
+static int attn_variant() {         // VGPT_ATTN_VARIANT: experimental kernel variants (see kVar* above), default 0.
+  const char* e = getenv("VGPT_ATTN_VARIANT");   // read at every launch so that one process can compare variants
+  return e ? (atoi(e) & 3) : 0;
+}
+
+template <int D, int VAR>
 static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                             const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                             const void* seqs, int num_seqs, int q_pairs, const int32_t* q_code,
@@ -494,7 +542,7 @@ static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int 
     rc = encode_tensor_map(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(v_pool), dims, strides, box, estr, swz);
     if (rc) return rc;
   }
-  auto kern = attn_pair_tcgen05_kernel<D>;
+  auto kern = attn_pair_tcgen05_kernel<D, VAR>;
   static bool attr_set = false;
   if (!attr_set) {
     VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
@@ -527,14 +575,18 @@ int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int ou
   VGPT_CHECK_ARG(max_pages <= kPairMaxTiles, "vgpt_attn_clip_causal: %d pages per sequence (at most %d)", max_pages, kPairMaxTiles);
   if (num_seqs <= 0 || max_q_rows <= 0) return 0;
   const int q_pairs = (max_q_rows + 2 * kPairBM - 1) / (2 * kPairBM);
-#define VGPT_ATTN_CASE(D_)                                                                               \
-  if (D == D_)                                                                                            \
-    return launch_attn_pair<D_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,   \
-                                max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,       \
-                                max_k_tiles, H, scale, s);
-  VGPT_ATTN_CASE(64)
-  VGPT_ATTN_CASE(96)
-  VGPT_ATTN_CASE(128)
+  const int var = (D == 96) ? attn_variant() : 0;
+#define VGPT_ATTN_CASE(D_, V_)                                                                              \
+  if (D == D_ && var == V_)                                                                                  \
+    return launch_attn_pair<D_, V_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,  \
+                                    max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,      \
+                                    max_k_tiles, H, scale, s);
+  VGPT_ATTN_CASE(64, 0)
+  VGPT_ATTN_CASE(96, 0)
+  VGPT_ATTN_CASE(96, 1)
+  VGPT_ATTN_CASE(96, 2)
+  VGPT_ATTN_CASE(96, 3)
+  VGPT_ATTN_CASE(128, 0)
 #undef VGPT_ATTN_CASE
   return -1;
 }
