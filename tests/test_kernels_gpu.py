@@ -433,13 +433,14 @@ def test_attention_variants_against_the_validated_kernel(ops, geom, phase, monke
     one bf16 ulp of the output scale of variant 0, and still inside the SDPA tolerance."""
     n_ctx, n_gen, H_px, W_px, heads = geom
     outs = {}
-    for var in (0, 1, 2, 3):
+    for var in (0, 1, 2, 3, 4, 5):
         monkeypatch.setenv("VGPT_ATTN_VARIANT", str(var))
         outs[var] = _attention_out(ops, n_ctx, n_gen, H_px, W_px, heads, 96, phase, 500)
     monkeypatch.setenv("VGPT_ATTN_VARIANT", "0")
     assert torch.isfinite(outs[0].float()).all()
     assert torch.equal(outs[1], outs[0]), "trimmed ragged tile changed bits"
-    assert torch.equal(outs[3], outs[2]), "trimmed ragged tile changed bits (with the polynomial)"
+    assert torch.equal(outs[3], outs[2]) and torch.equal(outs[5], outs[4]), "trimmed ragged tile changed bits (with the polynomial)"
     scale = outs[0].float().abs().max().item()
-    assert (outs[2].float() - outs[0].float()).abs().max().item() <= 2.0 ** -7 * scale
-    assert _rel(outs[2].float(), outs[0].float()) < 2e-3
+    for var in (2, 4):
+        assert (outs[var].float() - outs[0].float()).abs().max().item() <= 2.0 ** -7 * scale
+        assert _rel(outs[var].float(), outs[0].float()) < 2e-3

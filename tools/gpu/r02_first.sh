@@ -10,7 +10,7 @@ run tests        1500 $PT tests
 # 2. experimental kernels, opt-in: skinny-tail GEMM bit-exactness, then its effect on the bench line
 VGPT_TEST_EXPERIMENTAL=1 run skinny_test 300 $PT tests/test_kernels_gpu.py -k skinny
 VGPT_TEST_EXPERIMENTAL=1 run attn_variants 300 $PT tests/test_kernels_gpu.py -k variants
-for v in 0 1 2 3; do VGPT_ATTN_VARIANT=$v run attnbench_var$v 200 python tools/attn_bench.py; done
+for v in 0 1 2 3 4 5; do VGPT_ATTN_VARIANT=$v run attnbench_var$v 200 python tools/attn_bench.py; done
 VGPT_ATTN_VARIANT=3 run tests_var3 900 $PT tests/test_kernels_gpu.py tests/test_model_gpu.py -k "attention or next_clip"
 run smoke        200 python __graft_entry__.py --smoke
 run bench_cfg2   600 python bench.py --steps 3 --warmup 3
@@ -35,6 +35,6 @@ echo "ncu_gemm exit $?" >> gpurun_out/summary.txt
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:attn_pair -s 1 -c 1 \
     -o gpurun_out/prof_attn -f python tools/profile_step.py --no-prefill > gpurun_out/ncu_attn.log 2>&1
 echo "ncu_attn exit $?" >> gpurun_out/summary.txt
-for f in tests skinny_test attn_variants attnbench_var0 attnbench_var1 attnbench_var2 attnbench_var3 tests_var3 bench_cfg2_var3 smoke bench_cfg2 bench_cfg2_skinny bench_cfg4 bench_cfg4_b8 bench_roll bench_roll_re; do
+for f in tests skinny_test attn_variants attnbench_var0 attnbench_var1 attnbench_var2 attnbench_var3 attnbench_var4 attnbench_var5 tests_var3 bench_cfg2_var3 smoke bench_cfg2 bench_cfg2_skinny bench_cfg4 bench_cfg4_b8 bench_roll bench_roll_re; do
   echo "=== $f"; tail -n ${TAILN:-6} gpurun_out/$f.log | cut -c1-600; done
 cat gpurun_out/summary.txt

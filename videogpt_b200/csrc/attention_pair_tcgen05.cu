@@ -105,8 +105,10 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //      skipped products are zeros);
 //   2  every fourth exponential (key column % 4 == 3, a function of the column only, so row results
 //      stay independent of the row partition) is computed on the FMA pipe by ex2_poly instead of
-//      the MUFU unit, which is as loaded as the tensor pipe in this kernel.
-constexpr int kVarTrimRagged = 1, kVarPolyExp = 2;
+//      the MUFU unit, which is as loaded as the tensor pipe in this kernel;
+//   4  every second exponential (odd key columns) by ex2_poly (MUFU 1024 cycles per pair of tiles
+//      and KV tile instead of 2048, FMA pipe ~1660 instead of ~640).
+constexpr int kVarTrimRagged = 1, kVarPolyExp = 2, kVarPolyExpHalf = 4;
 
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
@@ -420,7 +422,10 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int i = 0; i < 64; ++i) {
           float p0, p1;
           ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), scale_log2, nsub);
-          if constexpr (VAR & kVarPolyExp) {
+          if constexpr (VAR & kVarPolyExpHalf) {
+            p0 = ex2_ftz(p0);
+            p1 = ex2_poly(p1);                                    // odd key columns: FMA pipe
+          } else if constexpr (VAR & kVarPolyExp) {
             p0 = ex2_ftz(p0);
             p1 = (i & 1) ? ex2_poly(p1) : ex2_ftz(p1);            // key column 2i + 1 = 3 (mod 4): FMA pipe
           } else {
@@ -514,7 +519,8 @@ static int debug_attn_flags() {     // VGPT_DEBUG_ATTN_FLAGS: timing probes only
 
 static int attn_variant() {         // VGPT_ATTN_VARIANT: experimental kernel variants (see kVar* above), default 0.
   const char* e = getenv("VGPT_ATTN_VARIANT");   // read at every launch so that one process can compare variants
-  return e ? (atoi(e) & 3) : 0;
+  const int v = e ? atoi(e) : 0;
+  return (v >= 0 && v <= 5) ? v : 0;
 }
 
 template <int D, int VAR>
@@ -586,6 +592,8 @@ int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int ou
   VGPT_ATTN_CASE(96, 1)
   VGPT_ATTN_CASE(96, 2)
   VGPT_ATTN_CASE(96, 3)
+  VGPT_ATTN_CASE(96, 4)
+  VGPT_ATTN_CASE(96, 5)
   VGPT_ATTN_CASE(128, 0)
 #undef VGPT_ATTN_CASE
   return -1;
