@@ -184,6 +184,13 @@ int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img,
 int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out,
                          void* stream);
 
+/* Diagnostic: with VGPT_ATTN_VARIANT=8 the attention kernel's CTA (0, 0, 0) records a clock64 time stamp
+ * at every hand-over between its roles (TMA producer, MMA issuer, softmax warps).  Copies the events
+ * recorded so far into out[2 * max_events] uint64 (host memory; pairs of clock and
+ * warp << 40 | tile << 32 | kv_tile << 8 | event), resets the recorder, synchronises the stream.
+ * Not on any product path (tools/attn_trace.py). */
+int vgpt_debug_attn_trace(void* out, int max_events, int* n_events, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

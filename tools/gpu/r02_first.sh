@@ -11,6 +11,7 @@ run tests        1500 $PT tests
 VGPT_TEST_EXPERIMENTAL=1 run skinny_test 300 $PT tests/test_kernels_gpu.py -k skinny
 VGPT_TEST_EXPERIMENTAL=1 run attn_variants 300 $PT tests/test_kernels_gpu.py -k variants
 for v in 0 1 2 3 4 5; do VGPT_ATTN_VARIANT=$v run attnbench_var$v 200 python tools/attn_bench.py; done
+VGPT_ATTN_VARIANT=8 run attn_trace 200 python tools/attn_trace.py
 VGPT_ATTN_VARIANT=3 run tests_var3 900 $PT tests/test_kernels_gpu.py tests/test_model_gpu.py -k "attention or next_clip"
 run smoke        200 python __graft_entry__.py --smoke
 run bench_cfg2   600 python bench.py --steps 3 --warmup 3

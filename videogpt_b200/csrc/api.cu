@@ -134,4 +134,8 @@ int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every
   return vgpt::umma_rate(mode, N, iters, n_acc, commit_every, ctas, out, S(stream));
 }
 
+int vgpt_debug_attn_trace(void* out, int max_events, int* n_events, void* stream) {
+  return vgpt::attn_trace_read(out, max_events, n_events, S(stream));
+}
+
 }  // extern "C"

@@ -108,7 +108,35 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //      the MUFU unit, which is as loaded as the tensor pipe in this kernel;
 //   4  every second exponential (odd key columns) by ex2_poly (MUFU 1024 cycles per pair of tiles
 //      and KV tile instead of 2048, FMA pipe ~1660 instead of ~640).
-constexpr int kVarTrimRagged = 1, kVarPolyExp = 2, kVarPolyExpHalf = 4;
+//   8  (diagnostic) CTA (0, 0, 0) records a clock64 time stamp at every hand-over between its roles
+//      into a device buffer (vgpt_debug_attn_trace, tools/attn_trace.py): which of the tensor pipe,
+//      the softmax warps and the loads actually waits for which.
+constexpr int kVarTrimRagged = 1, kVarPolyExp = 2, kVarPolyExpHalf = 4, kVarTrace = 8;
+
+constexpr int kTraceMax = 8192;
+__device__ unsigned long long g_attn_trace[2 * kTraceMax];     // (clock, warp << 40 | tile << 32 | j << 8 | event)
+__device__ unsigned int g_attn_trace_n;
+
+enum : int {   // trace events
+  kEvSFree = 1, kEvSIssued = 2, kEvPFull = 3, kEvPVIssued = 4,                    // MMA warp
+  kEvSFull = 10, kEvSRead = 11, kEvExpDone = 12, kEvPBufFree = 13, kEvPWritten = 14, kEvEpilogue = 15,   // softmax warps
+  kEvKvEmpty = 20, kEvKvIssued = 21,                                                // TMA warp
+  kEvStart = 30, kEvTableDone = 31, kEvEnd = 32
+};
+
+template <int VAR>
+__device__ __forceinline__ void attn_trace(int tile, int j, int ev) {
+  if constexpr ((VAR & kVarTrace) != 0) {
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0) {
+      const unsigned i = atomicAdd(&g_attn_trace_n, 1u);
+      if (i < (unsigned)kTraceMax) {
+        g_attn_trace[2 * i] = (unsigned long long)clock64();
+        g_attn_trace[2 * i + 1] = ((unsigned long long)(threadIdx.x >> 5) << 40) | ((unsigned long long)(tile & 0xff) << 32) |
+                                  ((unsigned long long)(j & 0xffffff) << 8) | (unsigned long long)ev;
+      }
+    }
+  }
+}
 
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
@@ -177,6 +205,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const int n_kt = (sq.kv_len + kPairBN - 1) / kPairBN;
+  attn_trace<VAR>(0, 0, kEvStart);
   if (warp == 8) {                        // Q does not need the table: start its load now
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_q, (has_b ? 2 : 1) * C::kTileBytes);
@@ -213,9 +242,10 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   }
   __syncthreads();
   const int n_vis = s_nvis;
+  attn_trace<VAR>(0, n_vis, kEvTableDone);
 
   if (warp >= 8) {
-    if constexpr (VAR & kVarTrimRagged) {
+    if constexpr ((VAR & (kVarTrimRagged | kVarTrace)) != 0) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // the trimmed-tile state does not fit in 56 (256 x 224 + 128 x 64 = 64 K)
     } else {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -227,6 +257,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     for (int i = 0; i < n_vis; ++i) {
       const int row = (t_page[i] * H + head) * kPairBN;         // pool viewed as [(page*H + head)*128 + tok][D]
       mbar_wait(bar_kv_empty(stage), phase ^ 1);
+      attn_trace<VAR>(0, i, kEvKvEmpty);
       if ((dbg & 8) && i >= kStages) {                          // timing probe: operands not refreshed
         if (elect_one_sync()) mbar_arrive(bar_kv_full(stage));
       } else if (elect_one_sync()) {
@@ -238,6 +269,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int c = 0; c < C::kChunks; ++c) tma_load_2d(sv + c * C::kChunkBytes, &tmap_v, bar_kv_full(stage), c * C::kCW, row);
       }
       __syncwarp();
+      attn_trace<VAR>(0, i, kEvKvIssued);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 9) {
@@ -307,12 +339,16 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           if (has_next) {
             if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
             if (x == 0) mbar_wait(bar_kv_full(stage_s), phase_s);
+            attn_trace<VAR>(x, j + 1, kEvSFree);
             tc_fence_after();
             issue_s(x, stage_s, j + 2 == n_vis);
+            attn_trace<VAR>(x, j + 1, kEvSIssued);
           }
           if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
+          attn_trace<VAR>(x, j, kEvPFull);
           tc_fence_after();
           issue_pv(x, stage_o, j, x == (has_b ? 1 : 0));
+          attn_trace<VAR>(x, j, kEvPVIssued);
         }
         if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
         if (++stage_o == kStages) stage_o = 0;
@@ -361,6 +397,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
         const int tmax = t_tmax[j], kt = t_kt[j];                 // (shared memory, before the wait)
         mbar_wait(bar_s_full(x), j & 1);
+        if (quad == 0) attn_trace<VAR>(x, j, kEvSFull);
         tc_fence_after();
         if (dbg & 1) {                                            // timing probe: tensor-pipe chain only
           tc_fence_before();
@@ -400,6 +437,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_s_free(x));
         }
+        if (quad == 0) attn_trace<VAR>(x, j, kEvSRead);
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -434,6 +472,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           fadd2(sum0, sum1, p0, p1);
           s[i] = pack_bf16x2(p0, p1);                             // P overwrites the dead half of s[]
         }
+        if (quad == 0) attn_trace<VAR>(x, j, kEvExpDone);
         if constexpr (C::kEarlyS) {
           // the P buffer is shared: its previous reader is P V of the other tile (B: tile j of A;
           // A: tile j-1 of B), or of this tile when it is alone
@@ -443,6 +482,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             mbar_wait(bar_o_full(y), need & 1);
             tc_fence_after();
           }
+          if (quad == 0) attn_trace<VAR>(x, j, kEvPBufFree);
           tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
           tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
         } else {
@@ -469,12 +509,14 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 per tile)
+        if (quad == 0) attn_trace<VAR>(x, j, kEvPWritten);
       }
       // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------
       if (n_vis > 0) {
         mbar_wait(bar_o_full(x), (n_vis - 1) & 1);
         tc_fence_after();
       }
+      if (quad == 0) attn_trace<VAR>(x, n_vis, kEvEpilogue);
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __nv_bfloat16* orow = out + (size_t)grow * out_ld + head * D;
 #pragma unroll
@@ -503,6 +545,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 
   tc_fence_before();
   __syncthreads();
+  attn_trace<VAR>(0, 0, kEvEnd);
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
@@ -520,7 +563,7 @@ static int debug_attn_flags() {     // VGPT_DEBUG_ATTN_FLAGS: timing probes only
 static int attn_variant() {         // VGPT_ATTN_VARIANT: experimental kernel variants (see kVar* above), default 0.
   const char* e = getenv("VGPT_ATTN_VARIANT");   // read at every launch so that one process can compare variants
   const int v = e ? atoi(e) : 0;
-  return (v >= 0 && v <= 5) ? v : 0;
+  return ((v >= 0 && v <= 5) || v == kVarTrace) ? v : 0;
 }
 
 template <int D, int VAR>
@@ -562,6 +605,23 @@ static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int 
   return 0;
 }
 
+// Diagnostic: copy the events recorded by the last launches of the kVarTrace variant (and reset the
+// counter).  out: 2 * max_events uint64 (clock, tag) in host or device memory; returns the number of
+// events through *n_events.
+int attn_trace_read(void* out, int max_events, int* n_events, cudaStream_t s) {
+  VGPT_CHECK_ARG(out && n_events && max_events > 0, "vgpt_debug_attn_trace: bad arguments");
+  VGPT_CHECK_CUDA(cudaStreamSynchronize(s));
+  unsigned int n = 0;
+  VGPT_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_attn_trace_n, sizeof(n)));
+  if (n > (unsigned)kTraceMax) n = kTraceMax;
+  if (n > (unsigned)max_events) n = max_events;
+  if (n) VGPT_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_attn_trace, (size_t)n * 2 * sizeof(unsigned long long)));
+  const unsigned int zero = 0;
+  VGPT_CHECK_CUDA(cudaMemcpyToSymbol(g_attn_trace_n, &zero, sizeof(zero)));
+  *n_events = (int)n;
+  return 0;
+}
+
 int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                           const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                           const void* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
@@ -594,6 +654,7 @@ int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int ou
   VGPT_ATTN_CASE(96, 3)
   VGPT_ATTN_CASE(96, 4)
   VGPT_ATTN_CASE(96, 5)
+  VGPT_ATTN_CASE(96, 8)
   VGPT_ATTN_CASE(128, 0)
 #undef VGPT_ATTN_CASE
   return -1;

@@ -76,6 +76,7 @@ int cfg_combine(void* pred, int half_numel, float guidance, cudaStream_t s);
 int mask_from_codes(const int32_t* qc, const int32_t* kc, void* out, int Lq, int Lk, cudaStream_t s);
 int umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes, uint64_t b_desc_base,
                   uint32_t idesc, int k_steps, uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s);
+int attn_trace_read(void* out, int max_events, int* n_events, cudaStream_t s);
 int umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out, cudaStream_t s);
 int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t a_desc_base,
                uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t a_step_bytes,
