@@ -186,3 +186,16 @@ def test_codes_from_mask_recovers_block_causal_masks(case):
             assert torch.equal(qc[:, None] >= kc[None, :], m)
     with pytest.raises(ValueError):
         codes_from_mask(torch.eye(5, dtype=torch.bool).flip(0))
+
+
+def test_planning_tools_run_without_a_gpu():
+    """tools/cost_model.py and tools/attn_schedule_sim.py are pure arithmetic over measured constants:
+    they must keep running on a GPU-less machine (DESIGN.md cites their output under profiles/)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tool, needle in (("cost_model.py", "with the skinny tail kernel"), ("attn_schedule_sim.py", "period per pair of tiles")):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", tool)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        assert needle in r.stdout
