@@ -475,3 +475,37 @@ def test_rollout_under_sequence_parallelism_matches_the_single_rank_rollout(emu)
     for r in range(world):
         for k in range(rounds):
             assert _maxerr(got[r][k], want[k]) < 5 * TOL, f"rank {r} round {k}"
+
+
+def test_rollout_window_smaller_than_two_clips_skips_frames_that_are_never_visible(emu):
+    """max_frame_window - gen_num < gen_num: part of a generated clip is already outside the window
+    when it becomes context -- those frames are never prefilled (and never visible), the rest is."""
+    from videogpt_b200 import LVMProcessor
+    from videogpt_b200.rollout import LatentRollout, window_start
+    n0, gen, window, H, W, steps, rounds = 1, 3, 4, 64, 64, 2, 3
+    bl = (H // 16) * (W // 16) + 2
+    m, sd = _model()
+    lat = synth.synthetic_latents(n0 + gen * rounds, H, W, seed=8)
+    history = [x.clone() for x in lat[:n0]]
+    ro = LatentRollout(m, LVMProcessor(synth.SingleIdTagTokenizer()), gen, max_frame_window=window,
+                       num_inference_steps=steps, img_guidance_scale=1.5, prediction_type="x1").start(history)
+    ws_of_frame = {}
+    for r in range(rounds):
+        n_hist = len(history)
+        ws = window_start(n_hist, gen, window)
+        for f in range(n_hist):
+            ws_of_frame.setdefault(f, min(ws, f))        # a frame outside the window keeps (only) itself in the oracle
+        noise = lat[n0 + gen * r:n0 + gen * (r + 1)]
+        got = ro.next_clip(initial_noise=noise)
+        d = po.frame_block_inputs(n_hist, gen, H, W, True, 1)
+        mk = dict(input_ids=d["input_ids"], input_img_latents=history, input_image_sizes=d["input_image_sizes"],
+                  attention_mask=_history_mask(d, n_hist, gen, bl, ws_of_frame, ws), position_ids=d["position_ids"],
+                  denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
+                  use_img_cfg=True)
+        with torch.no_grad():
+            want = so.euler_sample([x.clone() for x in noise] * 2,
+                                   lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                                   mk, num_steps=steps, prediction_type="x1")[:gen]
+        assert _maxerr(got, want) < TOL, f"round {r}"
+        history += [x.clone() for x in got]
+    assert ro.prefilled_frames == n0 + 1 + 1            # per later round only the one frame inside the window
