@@ -199,3 +199,20 @@ def test_planning_tools_run_without_a_gpu():
                            text=True, timeout=120)
         assert r.returncode == 0, r.stderr
         assert needle in r.stdout
+
+
+def test_bench_reference_arm_prints_the_contract_line_on_cpu():
+    """`bench.py --impl reference` (the reference's path on the host cores: oracle port) needs no GPU;
+    its one JSON line must carry the keys the driver's ratio is computed from."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "cfg1",
+                        "--steps", "1", "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "next_clip_tokens_per_s" and line["unit"] == "tokens/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["config"]["workload"] == "cfg1"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
