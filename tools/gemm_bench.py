@@ -20,7 +20,10 @@ for name, (N, K, epi) in shapes.items():
     a = torch.randn(M, K, device=dev).to(torch.bfloat16)
     n_out = N // 2 if epi == ops.EPI_SWIGLU else N
     out = torch.zeros(M, n_out, device=dev, dtype=torch.bfloat16)
-    for bn, pair in ((256, 0), (192, 0), (256, 1), (192, 1)):
+    # (0, -1) = the library's own choice (with VGPT_GEMM_SKINNY_TAIL=1: main tiles + skinny tail kernel);
+    # (0, 2) = skinny tail forced (experimental)
+    variants = ((256, 0), (192, 0), (256, 1), (192, 1), (0, -1)) + (((0, 2),) if os.environ.get("VGPT_GEMM_SKINNY_TAIL") == "1" else ())
+    for bn, pair in variants:
         def run():
             for w in ws:
                 ops.gemm(a, w, out=out, residual=out if epi == ops.EPI_RESIDUAL else None, epilogue=epi, block_n=bn, cta_pair=pair)
