@@ -51,6 +51,22 @@ const char* vgpt_last_error(void);
 int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
                    int ldc, int epilogue, int block_n, int cta_pair, void* stream);
 
+/* EXPERIMENTAL (never run on hardware; opt-in through VGPT_FOLD_RMSNORM=1 in the engine): Phi3RMSNorm
+ * folded into the projections around it -- (x * rstd * w) W^T == rstd * (x (W diag(w))^T), so the
+ * rmsnorm kernel and its [M, hidden] round trip disappear from Phi3DecoderLayer.  epilogue
+ * VGPT_EPI_RESIDUAL_SS (3): the residual epilogue of o_proj / down_proj also writes, per row and per N tile,
+ * the sum of squares of the bf16 values it stores into row_ss[M][VGPT_NORM_PARTS] (fixed slots, no atomics);
+ * VGPT_EPI_STORE_SCALED (4) / VGPT_EPI_SWIGLU_SCALED (5): qkv_proj / gate_up_proj on the RAW hidden rows with
+ * weights from vgpt_fold_norm_weight, every accumulator row scaled by rsqrt(sum(row_ss[row]) / K + eps)
+ * before the bf16 rounding.  Rounding points differ from the reference's (no bf16 rounding of the
+ * normalised activations).  CTA pairs only. */
+#define VGPT_NORM_PARTS 32
+int vgpt_gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
+                        int ldc, int epilogue, float* row_ss, float eps, void* stream);
+
+/* out[n][k] = bf16(w[n][k] * ln[k]): projection weight [N,K] with the preceding RMSNorm weight [K] folded in. */
+int vgpt_fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, void* stream);
+
 /* gate_up_proj.weight [2I,K] ([gate | up] rows, Phi3MLP chunk(2)) -> block-interleaved rows. */
 int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream);
 

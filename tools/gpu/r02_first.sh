@@ -11,6 +11,7 @@ run smoke        200 python __graft_entry__.py --smoke
 # 2. opt-in kernels: bit-exactness / tolerance tests, then timings
 VGPT_TEST_EXPERIMENTAL=1 run skinny_test 300 $PT tests/test_kernels_gpu.py -k skinny
 VGPT_TEST_EXPERIMENTAL=1 run attn_variants 300 $PT tests/test_kernels_gpu.py -k variants
+VGPT_TEST_EXPERIMENTAL=1 run fold_test 300 $PT tests/test_model_gpu.py -k folding
 for v in 0 1 2 3 4 5; do VGPT_ATTN_VARIANT=$v run attnbench_var$v 200 python tools/attn_bench.py; done
 VGPT_ATTN_VARIANT=8 run attn_trace 200 python tools/attn_trace.py
 run gemmsweep    300 python tools/gemm_bench.py
@@ -19,9 +20,10 @@ run umma_rate    200 python tools/umma_rate.py
 # 3. the headline line with the default kernels, with the skinny tail, with the attention variants
 run bench_cfg2   600 python bench.py --steps 3 --warmup 3
 VGPT_GEMM_SKINNY_TAIL=1 run bench_cfg2_skinny 600 python bench.py --steps 3 --warmup 3
+VGPT_FOLD_RMSNORM=1 run bench_cfg2_fold 600 python bench.py --steps 3 --warmup 3
 VGPT_ATTN_VARIANT=3 run tests_var3 900 $PT tests/test_kernels_gpu.py tests/test_model_gpu.py -k "attention or next_clip"
 VGPT_ATTN_VARIANT=3 VGPT_GEMM_SKINNY_TAIL=1 run bench_cfg2_var3_skinny 600 python bench.py --steps 3 --warmup 3
-for f in tests smoke skinny_test attn_variants attnbench_var0 attnbench_var1 attnbench_var2 attnbench_var3 attnbench_var4 \
+for f in tests smoke skinny_test attn_variants fold_test bench_cfg2_fold attnbench_var0 attnbench_var1 attnbench_var2 attnbench_var3 attnbench_var4 \
          attnbench_var5 tests_var3 bench_cfg2 bench_cfg2_skinny bench_cfg2_var3_skinny; do
   echo "=== $f"; tail -n ${TAILN:-5} gpurun_out/$f.log | cut -c1-500; done
 cat gpurun_out/summary.txt

@@ -41,6 +41,8 @@ SIGNATURES = {
     "vgpt_mask_from_codes": [P, P, P, I, I, P],
     "vgpt_debug_umma_rate": [I, I, I, I, I, I, P, P],
     "vgpt_debug_attn_trace": [P, I, P, P],
+    "vgpt_gemm_bf16_norm": [P, P, P, P, I, I, I, I, I, I, P, F, P],
+    "vgpt_fold_norm_weight": [P, P, P, I, I, P],
     "vgpt_debug_umma_probe_ts": [P, I, P, I, c_uint64, c_uint32, I, c_uint32, P, I, P],
     "vgpt_debug_umma_probe": [P, I, P, I, c_uint64, c_uint64, c_uint32, I, c_uint32, c_uint32, P, I, P],
 }

@@ -134,6 +134,13 @@ int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every
   return vgpt::umma_rate(mode, N, iters, n_acc, commit_every, ctas, out, S(stream));
 }
 
+int vgpt_gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
+                        int ldc, int epilogue, float* row_ss, float eps, void* stream) {
+  return vgpt::gemm_bf16_norm(A, W, C, R, M, N, K, lda, ldc, epilogue, row_ss, eps, S(stream));
+}
+int vgpt_fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, void* stream) {
+  return vgpt::fold_norm_weight(w, ln, out, N, K, S(stream));
+}
 int vgpt_debug_attn_trace(void* out, int max_events, int* n_events, void* stream) {
   return vgpt::attn_trace_read(out, max_events, n_events, S(stream));
 }

@@ -608,6 +608,30 @@ int pack_gate_up(const void* w, void* packed, int I, int K, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// RMSNorm weight folded into the following projection (vgpt_gemm_bf16_norm): out[n][k] = w[n][k] * ln[k],
+// product in fp32, rounded to bf16 once.  One-time weight preparation, like pack_gate_up.
+// ---------------------------------------------------------------------------------------------
+__global__ void fold_norm_weight_kernel(const uint4* __restrict__ w, const uint4* __restrict__ ln,
+                                        uint4* __restrict__ out, int kchunks) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < kchunks; c += blockDim.x) {
+    float a[8], b[8];
+    unpack8(w[(size_t)n * kchunks + c], a);
+    unpack8(ln[c], b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] *= b[i];
+    out[(size_t)n * kchunks + c] = pack8(a);
+  }
+}
+
+int fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, cudaStream_t s) {
+  VGPT_CHECK_ARG(w && ln && out && N > 0 && K > 0 && K % 8 == 0, "vgpt_fold_norm_weight: bad arguments (N=%d K=%d)", N, K);
+  fold_norm_weight_kernel<<<N, 128, 0, s>>>((const uint4*)w, (const uint4*)ln, (uint4*)out, K / 8);
+  VGPT_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Dense mask from token codes: out[q][k] = (q_code[q] >= k_code[k]).  The attention kernel
 // evaluates exactly this predicate in registers; materialising it is only for parity tests and
 // for callers that want the reference's [L,L] tensor (LVM/processor.py:682-731).

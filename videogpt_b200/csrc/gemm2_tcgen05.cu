@@ -39,7 +39,21 @@ struct Gemm2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
 };
 
-enum : int { kG2Store = 0, kG2Residual = 1, kG2SwiGLU = 2 };
+enum : int { kG2Store = 0, kG2Residual = 1, kG2SwiGLU = 2,
+             // RMSNorm folded into the GEMMs around it (EXPERIMENTAL, vgpt_gemm_bf16_norm):
+             //   (x * rstd * w) W^T == rstd * (x (W diag(w))^T)
+             // 3: residual epilogue that also writes, per row and per N tile, the sum of squares of the
+             //    bf16 values it stores (fixed slots, no atomics: the consumer's sum is deterministic);
+             // 4 / 5: store / SwiGLU epilogues that scale every accumulator row by
+             //    rstd = rsqrt(sum of that row's parts / K + eps) before the bf16 rounding.
+             kG2ResidualSS = 3, kG2StoreScaled = 4, kG2SwiGLUScaled = 5 };
+
+constexpr int kNormParts = 32;     // slots per row of the sum-of-squares buffer [M][kNormParts]
+struct NormArgs { float* ss; float inv_k; float eps; };
+template <int EPI> struct EpiExtra { };                                  // nothing for the plain epilogues
+template <> struct EpiExtra<kG2ResidualSS> { NormArgs na; };
+template <> struct EpiExtra<kG2StoreScaled> { NormArgs na; };
+template <> struct EpiExtra<kG2SwiGLUScaled> { NormArgs na; };
 
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -79,11 +93,37 @@ __device__ __forceinline__ void store_chunk2(const uint32_t (&acc)[32], __nv_bfl
   }
 }
 
+// Residual chunk that also returns the sum of squares of the 32 bf16 values it stores.
+__device__ __forceinline__ float store_chunk2_ss(const uint32_t (&acc)[32], __nv_bfloat16* __restrict__ out,
+                                                 const __nv_bfloat16* __restrict__ res) {
+  uint4 r[4];
+  const uint4* rp = reinterpret_cast<const uint4*>(res);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[i] = rp[i];
+  uint4* op = reinterpret_cast<uint4*>(out);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t rv = (&r[i].x)[j];
+      const float a = rbf(rbf(__uint_as_float(acc[i * 8 + j * 2])) + bf16lo(rv));
+      const float b = rbf(rbf(__uint_as_float(acc[i * 8 + j * 2 + 1])) + bf16hi(rv));
+      ss = fmaf(a, a, ss);
+      ss = fmaf(b, b, ss);
+      w[j] = pack_bf16x2(a, b);
+    }
+    op[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return ss;
+}
+
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                               __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ R, int M, int N,
-                              int K, int ldc, int flags) {
+                              int K, int ldc, int flags, EpiExtra<EPI> ex) {
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -191,7 +231,17 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       mbar_wait(tmem_full_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
-      if constexpr (EPI == kG2SwiGLU) {
+      [[maybe_unused]] float rstd = 1.f;
+      if constexpr (EPI == kG2StoreScaled || EPI == kG2SwiGLUScaled) {
+        if (row < M) {                       // fixed-order sum of the producer's per-tile parts
+          const float4* p = reinterpret_cast<const float4*>(ex.na.ss + (size_t)row * kNormParts);
+          float ssum = 0.f;
+#pragma unroll
+          for (int i = 0; i < kNormParts / 4; ++i) { const float4 v = p[i]; ssum += v.x; ssum += v.y; ssum += v.z; ssum += v.w; }
+          rstd = rsqrtf(ssum * ex.na.inv_k + ex.na.eps);
+        }
+      }
+      if constexpr (EPI == kG2SwiGLU || EPI == kG2SwiGLUScaled) {
         __nv_bfloat16* crow = C + (size_t)row * ldc + n0 / 2;
 #pragma unroll 1
         for (int c = 0; c < BN / 64; ++c) {
@@ -202,12 +252,36 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
           if (row < M && n0 + c * 64 < N) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float gv = rbf(__uint_as_float(g[i]));
-              float uv = rbf(__uint_as_float(u[i]));
+              float gv, uv;
+              if constexpr (EPI == kG2SwiGLUScaled) {
+                gv = rbf(__uint_as_float(g[i]) * rstd);
+                uv = rbf(__uint_as_float(u[i]) * rstd);
+              } else {
+                gv = rbf(__uint_as_float(g[i]));
+                uv = rbf(__uint_as_float(u[i]));
+              }
               g[i] = __float_as_uint(uv * rbf(silu_f(gv)));
             }
             store_chunk2<kG2Store>(g, crow + c * 32, nullptr);
           }
+        }
+      } else if constexpr (EPI == kG2ResidualSS) {
+        __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+        const __nv_bfloat16* rrow = R + (size_t)row * ldc + n0;
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          if (row < M && n0 + c * 32 < N) ss += store_chunk2_ss(acc, crow + c * 32, rrow + c * 32);
+        }
+        if (row < M) {
+          const int part = tile / m_tiles;           // this tile's slot; slot 0's owner clears the unused ones
+          float* p = ex.na.ss + (size_t)row * kNormParts;
+          p[part] = ss;
+          if (part == 0)
+            for (int i = n_tiles; i < kNormParts; ++i) p[i] = 0.f;
         }
       } else {
         __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
@@ -217,7 +291,13 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
           uint32_t acc[32];
           tmem_ld_32x32b_x32(taddr + c * 32, acc);
           tmem_ld_wait();
-          if (row < M && n0 + c * 32 < N) store_chunk2<EPI>(acc, crow + c * 32, rrow + c * 32);
+          if constexpr (EPI == kG2StoreScaled) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) * rstd);
+            if (row < M && n0 + c * 32 < N) store_chunk2<kG2Store>(acc, crow + c * 32, nullptr);
+          } else {
+            if (row < M && n0 + c * 32 < N) store_chunk2<EPI>(acc, crow + c * 32, rrow + c * 32);
+          }
         }
       }
       tc_fence_before();
@@ -408,7 +488,7 @@ gemm_bf16_skinny_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const _
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI>
 static int launch_gemm2(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                        int ldc, int num_sms, cudaStream_t stream) {
+                        int ldc, int num_sms, cudaStream_t stream, EpiExtra<EPI> ex = EpiExtra<EPI>()) {
   using Cfg = Gemm2Cfg<BN>;
   CUtensorMap ta, tb;
   {
@@ -437,7 +517,7 @@ static int launch_gemm2(const void* A, const void* W, void* C, const void* R, in
   const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
   kern<<<2 * clusters, kG2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C),
                                                              static_cast<const __nv_bfloat16*>(R), M, N, K, ldc,
-                                                             debug_gemm_flags());
+                                                             debug_gemm_flags(), ex);
   VGPT_CHECK_LAUNCH();
   return 0;
 }
@@ -495,6 +575,37 @@ int gemm_bf16_skinny(const void* A_tail, const void* W, void* C_tail, const void
   VGPT_SKINNY_CASE(32, kG2SwiGLU)
 #undef VGPT_SKINNY_CASE
   set_last_error("vgpt_gemm_bf16: no skinny kernel for epilogue=%d", epilogue);
+  return -1;
+}
+
+// RMSNorm folded into the neighbouring GEMMs (EXPERIMENTAL: never run on hardware).  epilogue 3 writes the
+// per-row, per-N-tile sums of squares into row_ss[M][kNormParts]; 4 / 5 read them.  CTA pairs only.
+int gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
+                   int epilogue, float* row_ss, float eps, cudaStream_t stream) {
+  VGPT_CHECK_ARG(A && W && C && row_ss && M > 0 && N > 0 && K > 0 && K % kG2BlockK == 0 && N % 64 == 0,
+                 "vgpt_gemm_bf16_norm: bad arguments (M=%d N=%d K=%d)", M, N, K);
+  VGPT_CHECK_ARG(epilogue >= kG2ResidualSS && epilogue <= kG2SwiGLUScaled, "vgpt_gemm_bf16_norm: epilogue %d", epilogue);
+  VGPT_CHECK_ARG(epilogue != kG2ResidualSS || R, "vgpt_gemm_bf16_norm: the residual epilogue needs R");
+  VGPT_CHECK_ARG(((uintptr_t)row_ss & 15) == 0, "vgpt_gemm_bf16_norm: row_ss must be 16-byte aligned");
+  const int sms = device_sm_count();
+  const int bn = pick_pair_block_n(M, N, sms);
+  VGPT_CHECK_ARG(epilogue != kG2ResidualSS || (N + bn - 1) / bn <= kNormParts,
+                 "vgpt_gemm_bf16_norm: N=%d needs more than %d sum-of-squares slots", N, kNormParts);
+  NormArgs na{row_ss, 1.0f / (float)K, eps};
+#define VGPT_GEMM2N_CASE(BN_, EPI_)                                                                   \
+  if (bn == BN_ && epilogue == EPI_) {                                                                \
+    EpiExtra<EPI_> ex;                                                                                \
+    ex.na = na;                                                                                       \
+    return launch_gemm2<BN_, EPI_>(A, W, C, R, M, N, K, lda, ldc, sms, stream, ex);                  \
+  }
+  VGPT_GEMM2N_CASE(256, kG2ResidualSS)
+  VGPT_GEMM2N_CASE(192, kG2ResidualSS)
+  VGPT_GEMM2N_CASE(256, kG2StoreScaled)
+  VGPT_GEMM2N_CASE(192, kG2StoreScaled)
+  VGPT_GEMM2N_CASE(256, kG2SwiGLUScaled)
+  VGPT_GEMM2N_CASE(192, kG2SwiGLUScaled)
+#undef VGPT_GEMM2N_CASE
+  set_last_error("vgpt_gemm_bf16_norm: no kernel for block_n=%d epilogue=%d", bn, epilogue);
   return -1;
 }
 

@@ -44,7 +44,7 @@ constexpr int kDefaultCtaPair = 1;
 // Tile width for the CTA-pair kernel: fewest (waves x tile width), with the narrower tile charged
 // for its higher L2 -> SMEM fill rate per MMA cycle (profiles/r01c_gemm_sweep_pair.txt: qkv and
 // gate_up prefer 256, the N = 3072 projections prefer 192 at M = 2064).
-static int pick_pair_block_n(int M, int N, int num_sms) {
+int pick_pair_block_n(int M, int N, int num_sms) {
   const int clusters = num_sms / 2;
   const int m_tiles = (M + 255) / 256;
   double best = 0;

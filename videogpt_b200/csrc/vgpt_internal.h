@@ -28,6 +28,10 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
 int debug_gemm_flags();
 int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
                    int epilogue, int block_n, cudaStream_t stream);
+int pick_pair_block_n(int M, int N, int num_sms);
+int gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
+                   int epilogue, float* row_ss, float eps, cudaStream_t stream);
+int fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, cudaStream_t s);
 int gemm_bf16_skinny(const void* A_tail, const void* W, void* C_tail, const void* R_tail, int rows, int N, int K,
                      int lda, int ldc, int epilogue, cudaStream_t stream);
 int pack_gate_up(const void* w, void* packed, int I, int K, cudaStream_t s);

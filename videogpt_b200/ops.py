@@ -14,6 +14,8 @@ import torch
 from . import _lib
 
 EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2
+EPI_RESIDUAL_SS, EPI_STORE_SCALED, EPI_SWIGLU_SCALED = 3, 4, 5      # RMSNorm folded into the GEMMs (experimental)
+NORM_PARTS = 32
 ROW_TOKEN, ROW_TIME, ROW_NOISY_PATCH, ROW_CONTEXT_PATCH = 0, 1, 2, 3
 PAGE_TOKENS = 128
 ATTN_KV_TILE = 64
@@ -58,6 +60,37 @@ def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int 
         assert residual.shape == out.shape and residual.stride(0) == out.stride(0)
     _lib.call("vgpt_gemm_bf16", _p(a), _p(w), _p(out), _p(residual), M, N, K, a.stride(0),
               out.stride(0), epilogue, block_n, cta_pair, _stream())
+    return out
+
+
+def gemm_norm(a, w, out, row_ss, eps: float, epilogue: int, residual=None):
+    """EXPERIMENTAL (``vgpt_gemm_bf16_norm``): GEMM with the neighbouring RMSNorm folded in.
+    ``EPI_RESIDUAL_SS``: ``out = bf16(a w^T) + residual`` and ``row_ss[M, NORM_PARTS]`` receives the
+    per-tile sums of squares of the stored rows; ``EPI_STORE_SCALED`` / ``EPI_SWIGLU_SCALED``: ``a`` is
+    the RAW hidden matrix, ``w`` carries the norm weight (``fold_norm_weight``), rows are scaled by
+    ``rsqrt(sum(row_ss[row]) / K + eps)``."""
+    _req(a, BF16, "a", contiguous=False); _req(w, BF16, "w"); _req(out, BF16, "out", contiguous=False)
+    _req(row_ss, F32, "row_ss")
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if epilogue == EPI_SWIGLU_SCALED else N
+    assert a.stride(1) == 1 and w.shape[1] == K and out.shape == (M, n_out) and out.stride(1) == 1
+    assert row_ss.shape[0] >= M and row_ss.shape[1] == NORM_PARTS
+    assert epilogue in (EPI_RESIDUAL_SS, EPI_STORE_SCALED, EPI_SWIGLU_SCALED)
+    if epilogue == EPI_RESIDUAL_SS:
+        _req(residual, BF16, "residual", contiguous=False)
+        assert residual.shape == out.shape and residual.stride(0) == out.stride(0)
+    _lib.call("vgpt_gemm_bf16_norm", _p(a), _p(w), _p(out), _p(residual), M, N, K, a.stride(0), out.stride(0),
+              epilogue, _p(row_ss), float(eps), _stream())
+    return out
+
+
+def fold_norm_weight(w, ln):
+    """``w[N, K] * ln[K]`` rounded to bf16 once (projection weight with the preceding RMSNorm weight)."""
+    _req(w, BF16, "w"); _req(ln, BF16, "ln")
+    assert w.dim() == 2 and ln.numel() == w.shape[1]
+    out = torch.empty_like(w)
+    _lib.call("vgpt_fold_norm_weight", _p(w), _p(ln), _p(out), w.shape[0], w.shape[1], _stream())
     return out
 
 
