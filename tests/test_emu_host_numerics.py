@@ -540,3 +540,25 @@ def test_rmsnorm_folded_into_the_gemms_is_the_same_function(emu, pt, monkeypatch
     # per predict: layer 0's input norm + the final norm; per prefill: layer 0's input norm (+ ln2 never: folded)
     assert emu.calls.count("rmsnorm") == 3 * 2 + 1
     assert emu.calls.count("gemm_norm") == 3 * (4 * L - 1) + (4 * (L - 1))
+
+
+def test_model_helper_methods_match_the_oracle(emu):
+    """The reference model's public helpers (LVM/model.py:255-327) on the drop-in: ``cropped_pos_embed``
+    and ``unpatchify`` are index arithmetic; ``patch_multiple_resolutions`` goes through the assembly
+    kernel (emulated here) for both embedders, tensors and lists."""
+    m, sd = _model()
+    cfg = _ocfg(synth.REDUCED)
+    lat = torch.cat(synth.synthetic_latents(3, 64, 96, seed=2), 0)                        # [3,4,8,12]
+    pe = m.cropped_pos_embed(8, 12)
+    assert torch.equal(pe, mo.cropped_pos_embed(sd["pos_embed"], cfg.pos_embed_max_size, 8, 12, 2))
+    for is_ctx, name in ((False, "x_embedder"), (True, "input_x_embedder")):
+        got, n_tok, shapes = m.patch_multiple_resolutions(lat, is_input_images=is_ctx)
+        want = torch.cat([mo.patch_embed(lat[i:i + 1], sd[f"{name}.proj.weight"], sd[f"{name}.proj.bias"],
+                                         sd["pos_embed"], cfg) for i in range(3)], 0)
+        assert n_tok == 24 and shapes == [8, 12] and float((got - want).abs().max()) < 1e-5
+        got_l, n_l, shapes_l = m.patch_multiple_resolutions([lat[:1], lat[1:3]], is_input_images=is_ctx)
+        assert n_l == [24, 24] and shapes_l == [[8, 12], [8, 12]] and float((torch.cat(got_l, 0) - want).abs().max()) < 1e-5
+    y = torch.randn(2, 24, 16)
+    assert torch.equal(m.unpatchify(y, 8, 12), mo.unpatchify(y, 8, 12, cfg))
+    with pytest.raises(ValueError, match="pos_embed_max_size"):
+        m.cropped_pos_embed(2 * 193, 8)

@@ -39,3 +39,24 @@ def test_batch_of_videos_equals_the_videos_run_alone(pt):
         for a, b in zip(got[v], alone):
             assert torch.isfinite(a.float()).all()
             assert torch.equal(a, b), f"video {v}: batched and single runs differ"
+
+
+def test_patch_multiple_resolutions_matches_the_reference_embedders():
+    """LVM.patch_multiple_resolutions (reference model.py:292-327) through vgpt_embed_assemble: conv output
+    rounded to bf16, then + position embedding rounded to bf16 -- the reference's rounding points, so the
+    comparison with the oracle's bf16 PatchEmbedMR is bit-level up to the conv's fp32 summation order."""
+    from oracle import model_oracle as mo
+    pipe = _pipe(synth.REDUCED)
+    m = pipe.model
+    sd = {k: v.to(DEV, BF) for k, v in synth.init_state_dict(synth.REDUCED, seed=0).items()}
+    cfg = mo.OracleConfig(hidden_size=synth.REDUCED.hidden_size, intermediate_size=synth.REDUCED.intermediate_size,
+                          num_hidden_layers=synth.REDUCED.num_hidden_layers,
+                          num_attention_heads=synth.REDUCED.num_attention_heads)
+    lat = torch.cat(synth.synthetic_latents(3, 64, 96, seed=2), 0).to(DEV, BF)
+    for is_ctx, name in ((False, "x_embedder"), (True, "input_x_embedder")):
+        got, n_tok, shapes = m.patch_multiple_resolutions(lat, is_input_images=is_ctx)
+        want = torch.cat([mo.patch_embed(lat[i:i + 1], sd[f"{name}.proj.weight"], sd[f"{name}.proj.bias"],
+                                         sd["pos_embed"], cfg) for i in range(3)], 0)
+        assert n_tok == 24 and shapes == [8, 12]
+        err = (got.float() - want.float()).abs().max().item()
+        assert err <= 2.0 ** -7 * want.float().abs().max().item(), err

@@ -217,6 +217,70 @@ class LVM(nn.Module):
                             rope_theta=float(_cfg_get(c, "rope_theta", 10000.0)),
                             vocab_size=c.vocab_size, pos_embed_max_size=self.pos_embed_max_size)
 
+    # ---- the reference model's helper methods (LVM/model.py:255-327) -----------------------------------
+    def unpatchify(self, x, h, w):
+        """``LVM.unpatchify`` (model.py:255-265): ``[N, T, p*p*C]`` -> ``[N, C, h, w]`` (pure data movement;
+        on the hot path the final-layer kernel scatters straight into this layout)."""
+        c, p = self.out_channels, self.patch_size
+        x = x.reshape(x.shape[0], h // p, w // p, p, p, c)
+        return torch.einsum("nhwpqc->nchpwq", x).reshape(x.shape[0], c, h, w)
+
+    def cropped_pos_embed(self, height, width):
+        """``LVM.cropped_pos_embed`` (model.py:268-289): centre crop of the position table for a latent of
+        ``height x width``, ``[1, tokens, hidden]`` in the model's dtype (a gather: exact)."""
+        if self.pos_embed_max_size is None:
+            raise ValueError("`pos_embed_max_size` must be set for cropping.")
+        hh, ww = height // self.patch_size, width // self.patch_size
+        if hh > self.pos_embed_max_size:
+            raise ValueError(f"Height ({hh}) cannot be greater than `pos_embed_max_size`: {self.pos_embed_max_size}.")
+        if ww > self.pos_embed_max_size:
+            raise ValueError(f"Width ({ww}) cannot be greater than `pos_embed_max_size`: {self.pos_embed_max_size}.")
+        ref = self.x_embedder.proj.weight
+        if self.pos_embed is not None:
+            top, left = (self.pos_embed_max_size - hh) // 2, (self.pos_embed_max_size - ww) // 2
+            pe = self.pos_embed.reshape(1, self.pos_embed_max_size, self.pos_embed_max_size, -1)
+            return pe[:, top:top + hh, left:left + ww, :].reshape(1, hh * ww, -1)
+        from .synth import cropped_pos_embed_rows
+        return cropped_pos_embed_rows(self.hidden_size, height, width, self.patch_size,
+                                      self.pos_embed_max_size).to(ref.device, ref.dtype)[None]
+
+    @torch.no_grad()
+    def patch_multiple_resolutions(self, latents, padding_latent=None, is_input_images: bool = False):
+        """``LVM.patch_multiple_resolutions`` (model.py:292-327): patch embedding (``x_embedder`` /
+        ``input_x_embedder``) + cropped position embedding of a latent ``[B,4,h,w]`` or of a list of them,
+        through the assembly kernel (``vgpt_embed_assemble``).  Returns ``(latents, num_tokens, shapes)``
+        like the reference."""
+        def embed(lat):
+            b, _, h, w = lat.shape
+            n_tok = (h // self.patch_size) * (w // self.patch_size)
+            dev = lat.device
+            pos = self.cropped_pos_embed(h, w)[0].to(dev, eng.ACT_DTYPE).contiguous()
+            kind = torch.full((b * n_tok,), ops.ROW_CONTEXT_PATCH if is_input_images else ops.ROW_NOISY_PATCH,
+                              dtype=torch.int32, device=dev)
+            a = torch.arange(b, dtype=torch.int32, device=dev).repeat_interleave(n_tok)
+            t = torch.arange(n_tok, dtype=torch.int32, device=dev).repeat(b)
+            out = torch.empty(b * n_tok, self.hidden_size, device=dev, dtype=eng.ACT_DTYPE)
+            cast = lambda p_: p_.detach().to(dev, eng.ACT_DTYPE).contiguous()
+            z = lat.to(eng.ACT_DTYPE).contiguous()
+            ops.embed_assemble(out, kind, a, t, cast(self.llm.embed_tokens.weight), None, z, z, h, w,
+                               cast(self.x_embedder.proj.weight), cast(self.x_embedder.proj.bias),
+                               cast(self.input_x_embedder.proj.weight), cast(self.input_x_embedder.proj.bias), pos)
+            return out.reshape(b, n_tok, self.hidden_size), n_tok, [h, w]
+
+        if not isinstance(latents, list):
+            return embed(latents)
+        return_list = padding_latent is None
+        pads = [None] * len(latents) if return_list else padding_latent
+        patched, num_tokens, shapes = [], [], []
+        for lat, pad in zip(latents, pads):
+            e, n_tok, shape = embed(lat)
+            if pad is not None:
+                e = torch.cat([e, pad], dim=-2)
+            patched.append(e)
+            num_tokens.append(n_tok)
+            shapes.append(shape)
+        return (patched if return_list else torch.cat(patched, dim=0)), num_tokens, shapes
+
     # ---- engine ---------------------------------------------------------------------------------
     def engine(self) -> eng.NextClipEngine:
         dev = self.x_embedder.proj.weight.device
