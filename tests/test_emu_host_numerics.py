@@ -562,3 +562,18 @@ def test_model_helper_methods_match_the_oracle(emu):
     assert torch.equal(m.unpatchify(y, 8, 12), mo.unpatchify(y, 8, 12, cfg))
     with pytest.raises(ValueError, match="pos_embed_max_size"):
         m.cropped_pos_embed(2 * 193, 8)
+
+
+def test_submodule_forwards_match_the_oracle(emu):
+    """TimestepEmbedder / PatchEmbedMR / FinalLayer of the drop-in are callable like the reference's
+    modules (LVM/model.py:26-83, 138-154) and run on the hot path's kernels (emulated here)."""
+    m, sd = _model()
+    cfg = _ocfg(synth.REDUCED)
+    t = torch.tensor([0.0, 0.25, 0.9])
+    for name, mod in (("time_token", m.time_token), ("t_embedder", m.t_embedder)):
+        assert float((mod(t) - mo.timestep_embedder(sd, name, t, torch.float32)).abs().max()) < 1e-5
+    lat = torch.cat(synth.synthetic_latents(2, 64, 96, seed=5), 0)
+    want = torch.nn.functional.conv2d(lat, sd["x_embedder.proj.weight"], sd["x_embedder.proj.bias"], stride=2)
+    assert float((m.x_embedder(lat) - want.flatten(2).transpose(1, 2)).abs().max()) < 1e-5
+    x, c = torch.randn(2, 24, synth.REDUCED.hidden_size), torch.randn(2, synth.REDUCED.hidden_size)
+    assert float((m.final_layer(x, c) - mo.final_layer(sd, x, c)).abs().max()) < 1e-4

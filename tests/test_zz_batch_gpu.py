@@ -60,3 +60,28 @@ def test_patch_multiple_resolutions_matches_the_reference_embedders():
         assert n_tok == 24 and shapes == [8, 12]
         err = (got.float() - want.float()).abs().max().item()
         assert err <= 2.0 ** -7 * want.float().abs().max().item(), err
+
+
+def test_submodule_forwards_on_the_gpu():
+    """TimestepEmbedder / PatchEmbedMR / FinalLayer forwards of the drop-in (kernel-backed) vs the oracle's
+    bf16 modules: within bf16 rounding of the output scale."""
+    from oracle import model_oracle as mo
+    pipe = _pipe(synth.REDUCED)
+    m = pipe.model
+    sd = {k: v.to(DEV, BF) for k, v in synth.init_state_dict(synth.REDUCED, seed=0).items()}
+    hs = synth.REDUCED.hidden_size
+
+    def close(got, want, tol=2.0 ** -6):
+        assert torch.isfinite(got.float()).all()
+        assert (got.float() - want.float()).abs().max().item() <= tol * want.float().abs().max().item()
+
+    t = torch.tensor([0.0, 0.25, 0.9], device=DEV)
+    close(m.time_token(t), mo.timestep_embedder(sd, "time_token", t, BF))
+    close(m.t_embedder(t), mo.timestep_embedder(sd, "t_embedder", t, BF))
+    lat = torch.cat(synth.synthetic_latents(2, 64, 96, seed=5), 0).to(DEV, BF)
+    want = torch.nn.functional.conv2d(lat, sd["x_embedder.proj.weight"], sd["x_embedder.proj.bias"], stride=2)
+    close(m.x_embedder(lat), want.flatten(2).transpose(1, 2))
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(2, 24, hs, device=DEV, generator=g).to(BF)
+    c = torch.randn(2, hs, device=DEV, generator=g).to(BF)
+    close(m.final_layer(x, c), mo.final_layer(sd, x, c), tol=2.0 ** -5)

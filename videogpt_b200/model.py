@@ -53,11 +53,30 @@ class _Seq(nn.Module):
             self.add_module(k, m)
 
 
+def _k(t):
+    """Parameter / input as the kernels take it: detached, contiguous, activation dtype."""
+    return t.detach().to(eng.ACT_DTYPE).contiguous()
+
+
 class TimestepEmbedder(nn.Module):          # LVM/model.py:26-63
     def __init__(self, hidden_size, frequency_embedding_size=256):
         super().__init__()
         self.mlp = _Seq({"0": _Linear(frequency_embedding_size, hidden_size), "2": _Linear(hidden_size, hidden_size)})
         self.frequency_embedding_size = frequency_embedding_size
+
+    @torch.no_grad()
+    def forward(self, t, dtype=None):
+        """``TimestepEmbedder.forward`` (model.py:60-63): sinusoid ([cos | sin], fp32 -> model dtype) ->
+        Linear -> SiLU -> Linear, on the kernels of the hot path.  ``t``: ``[n]`` on the model's device."""
+        import math
+        half = self.frequency_embedding_size // 2
+        l0, l2 = getattr(self.mlp, "0"), getattr(self.mlp, "2")
+        dev = l0.weight.device
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half).to(dev)
+        x = torch.empty(t.numel(), 2 * half, device=dev, dtype=eng.ACT_DTYPE)
+        ops.timestep_sinusoid(t.to(dev, torch.float32).contiguous(), freqs, x)
+        hdn = ops.linear_small(x, _k(l0.weight), _k(l0.bias), post_silu=True)
+        return ops.linear_small(hdn, _k(l2.weight), _k(l2.bias))
 
 
 class FinalLayer(nn.Module):                # LVM/model.py:66-83
@@ -65,6 +84,22 @@ class FinalLayer(nn.Module):                # LVM/model.py:66-83
         super().__init__()
         self.linear = _Linear(hidden_size, patch_size * patch_size * out_channels)
         self.adaLN_modulation = _Seq({"1": _Linear(hidden_size, 2 * hidden_size)})
+        self.patch_size, self.out_channels = patch_size, out_channels
+
+    @torch.no_grad()
+    def forward(self, x, c):
+        """``FinalLayer.forward`` (model.py:79-83): ``x [B, T, hidden]``, ``c [B, hidden]`` ->
+        ``[B, T, p*p*C]`` (feature order (p, q, c)).  Runs the fused final-layer kernel -- which
+        scatters into latent layout -- on a one-patch-row latent of 2 x 2T pixels and reads it back
+        in token order (indexing only)."""
+        b, t, hs = x.shape
+        p, ch = self.patch_size, self.out_channels
+        ada = getattr(self.adaLN_modulation, "1")
+        mod = ops.linear_small(_k(c), _k(ada.weight), _k(ada.bias), pre_silu=True)
+        pred = torch.empty(b, ch, p, p * t, device=x.device, dtype=eng.ACT_DTYPE)
+        row0 = (torch.arange(b, dtype=torch.int32, device=x.device) * t).contiguous()
+        ops.final_layer(_k(x).reshape(b * t, hs), row0, mod, _k(self.linear.weight), _k(self.linear.bias), pred)
+        return pred.reshape(b, ch, p, t, p).permute(0, 3, 2, 4, 1).reshape(b, t, p * p * ch)
 
 
 class PatchEmbedMR(nn.Module):              # LVM/model.py:138-154
@@ -73,6 +108,25 @@ class PatchEmbedMR(nn.Module):              # LVM/model.py:138-154
         self.proj = nn.Module()
         self.proj.weight = nn.Parameter(torch.empty(embed_dim, in_chans, patch_size, patch_size))
         self.proj.bias = nn.Parameter(torch.zeros(embed_dim))
+        self.patch_size = patch_size
+
+    @torch.no_grad()
+    def forward(self, latent, pos_rows=None):
+        """``PatchEmbedMR.forward`` (model.py:149-153): ``[B, 4, h, w]`` -> ``[B, tokens, hidden]`` (conv with
+        kernel = stride = patch, flattened row-major), through the assembly kernel; ``pos_rows``
+        ``[tokens, hidden]`` is added in the same pass when given (the model always adds one)."""
+        b, _, h, w = latent.shape
+        n_tok = (h // self.patch_size) * (w // self.patch_size)
+        dev, hs = latent.device, self.proj.weight.shape[0]
+        pos = torch.zeros(n_tok, hs, device=dev, dtype=eng.ACT_DTYPE) if pos_rows is None else _k(pos_rows)
+        kind = torch.full((b * n_tok,), ops.ROW_NOISY_PATCH, dtype=torch.int32, device=dev)
+        a = torch.arange(b, dtype=torch.int32, device=dev).repeat_interleave(n_tok)
+        t = torch.arange(n_tok, dtype=torch.int32, device=dev).repeat(b)
+        out = torch.empty(b * n_tok, hs, device=dev, dtype=eng.ACT_DTYPE)
+        z = _k(latent)
+        wt, bs = _k(self.proj.weight), _k(self.proj.bias)
+        ops.embed_assemble(out, kind, a, t, wt.reshape(hs, -1), None, z, z, h, w, wt, bs, wt, bs, pos)
+        return out.reshape(b, n_tok, hs)
 
 
 class _Norm(nn.Module):
@@ -251,21 +305,9 @@ class LVM(nn.Module):
         through the assembly kernel (``vgpt_embed_assemble``).  Returns ``(latents, num_tokens, shapes)``
         like the reference."""
         def embed(lat):
-            b, _, h, w = lat.shape
-            n_tok = (h // self.patch_size) * (w // self.patch_size)
-            dev = lat.device
-            pos = self.cropped_pos_embed(h, w)[0].to(dev, eng.ACT_DTYPE).contiguous()
-            kind = torch.full((b * n_tok,), ops.ROW_CONTEXT_PATCH if is_input_images else ops.ROW_NOISY_PATCH,
-                              dtype=torch.int32, device=dev)
-            a = torch.arange(b, dtype=torch.int32, device=dev).repeat_interleave(n_tok)
-            t = torch.arange(n_tok, dtype=torch.int32, device=dev).repeat(b)
-            out = torch.empty(b * n_tok, self.hidden_size, device=dev, dtype=eng.ACT_DTYPE)
-            cast = lambda p_: p_.detach().to(dev, eng.ACT_DTYPE).contiguous()
-            z = lat.to(eng.ACT_DTYPE).contiguous()
-            ops.embed_assemble(out, kind, a, t, cast(self.llm.embed_tokens.weight), None, z, z, h, w,
-                               cast(self.x_embedder.proj.weight), cast(self.x_embedder.proj.bias),
-                               cast(self.input_x_embedder.proj.weight), cast(self.input_x_embedder.proj.bias), pos)
-            return out.reshape(b, n_tok, self.hidden_size), n_tok, [h, w]
+            h, w = lat.shape[-2:]
+            emb = (self.input_x_embedder if is_input_images else self.x_embedder)(lat, self.cropped_pos_embed(h, w)[0])
+            return emb, emb.shape[1], [h, w]
 
         if not isinstance(latents, list):
             return embed(latents)
