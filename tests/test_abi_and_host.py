@@ -216,3 +216,16 @@ def test_bench_reference_arm_prints_the_contract_line_on_cpu():
     assert line["value"] > 0 and line["higher_is_better"] is True and line["config"]["workload"] == "cfg1"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_scheduler_cache_cropping_helpers_slice_like_the_reference():
+    import torch
+    from videogpt_b200 import LVMScheduler
+    s = LVMScheduler(num_steps=2)
+    pos = torch.arange(20).reshape(2, 10)
+    assert torch.equal(s.crop_position_ids_for_cache(pos, 3), pos[:, -4:])
+    assert [x.shape for x in s.crop_position_ids_for_cache([pos.clone(), pos.clone()], 3)] == [(2, 4), (2, 4)]
+    mask = torch.ones(2, 10, 10)
+    assert s.crop_attention_mask_for_cache(mask, 3).shape == (2, 4, 10)
+    assert s.crop_attention_mask_for_cache([mask], 3)[0].shape == (2, 4, 10)
+    assert torch.allclose(s.sigma, torch.tensor([0.0, 0.5, 1.0]))
