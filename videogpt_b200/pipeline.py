@@ -78,6 +78,11 @@ class LVMPipeline:
             vae = AutoencoderKL.from_pretrained(vae_path if vae_path is not None else "stabilityai/sdxl-vae")
         return cls(vae, model, processor)
 
+    def merge_lora(self, lora_path: str):
+        """pipeline.py:97-101 (peft).  Out of scope here: merge the adapter into the checkpoint with the
+        reference tooling and load the merged weights (same state-dict names)."""
+        raise NotImplementedError("merge_lora is out of scope (DESIGN.md section 8): load an already merged checkpoint")
+
     def to(self, device: Union[str, torch.device]):
         if isinstance(device, str):
             device = torch.device(device)
