@@ -187,7 +187,7 @@ def _sp_host_flow(rank, world):
     barriers = []
     bf = torch.bfloat16
 
-    def make_group(ranks, group=None, device=None):
+    def make_group(ranks, group=None, device=None, host_group=None):
         g = _fake_peer_group(ranks, group=group)
         g.barrier = lambda: barriers.append(1)          # the flag-barrier kernel launch
         return g

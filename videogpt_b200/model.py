@@ -354,7 +354,7 @@ class LVM(nn.Module):
             from . import peer
             ranks = dist.get_process_group_ranks(hccl_info.group) if hccl_info.group is not None else \
                 list(range(dist.get_world_size()))
-            self._peers = peer.PeerGroup(ranks, group=hccl_info.group)
+            self._peers = peer.PeerGroup(ranks, group=hccl_info.group, host_group=getattr(hccl_info, "host_group", None))
         return self._peers
 
     def invalidate_plan_cache(self):

@@ -18,6 +18,10 @@ class COMM_INFO:
         self.group = None
         self.world_size = 0
         self.rank = -1
+        # host-side rendezvous group of the same ranks (gloo) when VGPT_SP_HOST_BACKEND=gloo: the peer
+        # group's handle exchange and host barriers then launch no GPU kernels at all (an NCCL barrier
+        # is an all-reduce kernel that has to share the GPUs with spinning vgpt_peer_barrier kernels)
+        self.host_group = None
 
 
 hccl_info = COMM_INFO()
@@ -31,7 +35,7 @@ def initialize_sequence_parallel_state(sequence_parallel_size: int):
         _SEQUENCE_PARALLEL_STATE = True
         initialize_sequence_parallel_group(sequence_parallel_size)
     else:
-        hccl_info.group, hccl_info.world_size, hccl_info.rank = None, 1, 0
+        hccl_info.group, hccl_info.world_size, hccl_info.rank, hccl_info.host_group = None, 1, 0, None
 
 
 def get_sequence_parallel_state() -> bool:
@@ -49,13 +53,14 @@ def initialize_sequence_parallel_group(sequence_parallel_size: int):
     for i in range(world_size // sequence_parallel_size):
         ranks = list(range(i * sequence_parallel_size, (i + 1) * sequence_parallel_size))
         group = dist.new_group(ranks)
+        host_group = dist.new_group(ranks, backend="gloo") if os.getenv("VGPT_SP_HOST_BACKEND") == "gloo" else None
         if rank in ranks:
-            hccl_info.group = group
+            hccl_info.group, hccl_info.host_group = group, host_group
 
 
 def destroy_sequence_parallel_group():
     global _SEQUENCE_PARALLEL_STATE
-    hccl_info.group, hccl_info.world_size, hccl_info.rank = None, 0, -1
+    hccl_info.group, hccl_info.world_size, hccl_info.rank, hccl_info.host_group = None, 0, -1, None
     _SEQUENCE_PARALLEL_STATE = False
 
 

@@ -56,14 +56,16 @@ class PeerGroup:
     cooperate on one video.  Every method marked *collective* must be called by all of them in the
     same order."""
 
-    def __init__(self, ranks: Sequence[int], group=None, device=None):
+    def __init__(self, ranks: Sequence[int], group=None, device=None, host_group=None):
+        """``host_group``: process group for the HOST-side collectives of this class (handle exchange,
+        ``host_barrier``); defaults to ``group``.  A gloo group keeps them off the GPUs entirely."""
         import torch.distributed as dist
         self.ranks = list(ranks)
         self.world = len(self.ranks)
         if self.world > 8:
             raise ValueError("at most 8 ranks per sequence-parallel group (one NVSwitch domain)")
         self.rank = self.ranks.index(dist.get_rank())
-        self.group = group
+        self.group = group if host_group is None else host_group
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._owned: List[int] = []
         self._imported: List[int] = []
