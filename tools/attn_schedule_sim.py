@@ -40,6 +40,32 @@ def period(t_softmax, handover, s=642, pv=464, n=80, t_pwrite=100):
     return (pv_done[(1, n - 1)] - pv_done[(1, n // 2)]) / (n - 1 - n // 2)
 
 
+def period_single_tile(t_softmax, handover, s=444, pv=464, n=80, t_pwrite=100, p_bufs=1):
+    """Candidate design: ONE query tile per CTA, S double-buffered (S(j+2) issued into the buffer softmax(j)
+    has just read), S in TS form with Q in tensor memory (6 x 74 cycles; TMEM: 2 x 128 S + 96 O + 64 P +
+    48 Q = 464 columns), one P buffer.  Same hand-over model as above; period per KV tile."""
+    pipe_free, t = 0.0, 0.0
+    s_done, pv_done, sm_done = {}, {}, {-1: 0.0}
+
+    def issue(dur):
+        nonlocal pipe_free, t
+        pipe_free = max(pipe_free, t) + dur
+        return pipe_free
+
+    s_done[0] = issue(s)
+    s_done[1] = issue(s)
+    for j in range(n):
+        done = max(s_done[j] + handover, sm_done[j - 1]) + t_softmax
+        if j - p_bufs >= 0:
+            done = max(done, pv_done[j - p_bufs] + handover)
+        sm_done[j] = done + t_pwrite
+        t = max(t, sm_done[j] + handover)
+        pv_done[j] = issue(pv)
+        if j + 2 < n:
+            s_done[j + 2] = issue(s)
+    return (pv_done[n - 1] - pv_done[n // 2]) / (n - 1 - n // 2)
+
+
 if __name__ == "__main__":
     lat = (0, 1100, 1600, 2300, 3000, 4000)
     print("period per pair of tiles and KV tile (tensor-pipe work: 2212 cycles)")
@@ -47,3 +73,9 @@ if __name__ == "__main__":
     for h in (100, 200, 300, 400, 600, 800):
         print(f"{h:>26d} " + "".join(f"{period(x, h):7.0f}" for x in lat))
     print("measured (r01h, old grid): 83 us per launch = 4400-5200 cycles per period; tensor-pipe chain alone 53 us = 2800-3300")
+    print("\ncandidate: one query tile per CTA, S double-buffered, S in TS form -- period per KV tile for ONE tile")
+    print("(compare with HALF the numbers above; tensor-pipe work 908, MUFU 1024 per tile)")
+    lat1 = (700, 1100, 1300, 1600)
+    print("hand-over \\ softmax latency " + "".join(f"{x:>7d}" for x in lat1))
+    for h in (100, 300, 500, 700):
+        print(f"{h:>26d} " + "".join(f"{period_single_tile(x, h):7.0f}" for x in lat1))
