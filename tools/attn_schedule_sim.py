@@ -74,7 +74,9 @@ if __name__ == "__main__":
         print(f"{h:>26d} " + "".join(f"{period(x, h):7.0f}" for x in lat))
     print("measured (r01h, old grid): 83 us per launch = 4400-5200 cycles per period; tensor-pipe chain alone 53 us = 2800-3300")
     print("\ncandidate: one query tile per CTA, S double-buffered, S in TS form -- period per KV tile for ONE tile")
-    print("(compare with HALF the numbers above; tensor-pipe work 908, MUFU 1024 per tile)")
+    print("(compare with HALF the numbers above; tensor-pipe work 908, MUFU 1024 per tile.  Reality check: the first")
+    print(" tcgen05 kernel, attention_tcgen05.cu, IS one tile with double-buffered S and P (SS form) and measured")
+    print(" 101 us = 3000-3800 cycles per tile -- a real softmax pass is much longer than the latencies assumed here)")
     lat1 = (700, 1100, 1300, 1600)
     print("hand-over \\ softmax latency " + "".join(f"{x:>7d}" for x in lat1))
     for h in (100, 300, 500, 700):
