@@ -98,6 +98,36 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Two exponentials at once with the packed fp32x2 instructions (variant 4): 2 FMNMX + 6 packed + 4 integer
+// instructions per pair instead of 2 x 9.
+__device__ __forceinline__ void ex2_poly2(float& x0, float& x1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float t0, t1, p0, p1;
+  asm("{\n\t.reg .b64 rx, rt, rn, rf, rp, rk;\n\t"
+      "mov.b64 rx, {%4, %5};\n\t"
+      "mov.b64 rk, {%6, %6};\n\t"                    // +magic
+      "add.rn.f32x2 rt, rx, rk;\n\t"                 // t = x + 1.5 * 2^23
+      "mov.b64 rk, {%7, %7};\n\t"                    // -magic
+      "add.rn.f32x2 rn, rt, rk;\n\t"                 // n = rint(x)
+      "mov.b64 rk, {%8, %8};\n\t"                    // -1
+      "fma.rn.f32x2 rf, rn, rk, rx;\n\t"             // f = x - n
+      "mov.b64 rp, {%9, %9};\n\t"
+      "mov.b64 rk, {%10, %10};\n\t"
+      "fma.rn.f32x2 rp, rp, rf, rk;\n\t"             // c3 f + c2
+      "mov.b64 rk, {%11, %11};\n\t"
+      "fma.rn.f32x2 rp, rp, rf, rk;\n\t"             // (..) f + c1
+      "mov.b64 rk, {%12, %12};\n\t"
+      "fma.rn.f32x2 rp, rp, rf, rk;\n\t"             // (..) f + 1
+      "mov.b64 {%0, %1}, rt;\n\t"
+      "mov.b64 {%2, %3}, rp;\n\t}"
+      : "=f"(t0), "=f"(t1), "=f"(p0), "=f"(p1)
+      : "f"(x0), "f"(x1), "f"(12582912.0f), "f"(-12582912.0f), "f"(-1.0f), "f"(0.055008664727211f),
+        "f"(0.24221056699752808f), "f"(0.6932829022407532f), "f"(1.0f));
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 // Experimental variants of the kernel (bit mask in VGPT_ATTN_VARIANT, head_dim 96 only; 0 = the
 // kernel that was validated and measured on hardware, and its SASS is unchanged by their presence):
 //   1  ragged last KV tile: keys beyond kv_len are masked for every query, so S is issued with
@@ -106,8 +136,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //   2  every fourth exponential (key column % 4 == 3, a function of the column only, so row results
 //      stay independent of the row partition) is computed on the FMA pipe by ex2_poly instead of
 //      the MUFU unit, which is as loaded as the tensor pipe in this kernel;
-//   4  every second exponential (odd key columns) by ex2_poly (MUFU 1024 cycles per pair of tiles
-//      and KV tile instead of 2048, FMA pipe ~1660 instead of ~640).
+//   4  every second PAIR of exponentials (key columns 4k+2, 4k+3) by ex2_poly2 (packed fp32x2): MUFU
+//      1024 cycles per pair of tiles and KV tile instead of 2048, ~6 more FMA-pipe instructions per
+//      element moved.
 //   8  (diagnostic) CTA (0, 0, 0) records a clock64 time stamp at every hand-over between its roles
 //      into a device buffer (vgpt_debug_attn_trace, tools/attn_trace.py): which of the tensor pipe,
 //      the softmax warps and the loads actually waits for which.
@@ -245,8 +276,8 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   attn_trace<VAR>(0, n_vis, kEvTableDone);
 
   if (warp >= 8) {
-    if constexpr ((VAR & (kVarTrimRagged | kVarTrace)) != 0) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // the trimmed-tile state does not fit in 56 (256 x 224 + 128 x 64 = 64 K)
+    if constexpr (VAR != 0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // the variants' extra state does not fit in 56 (256 x 224 + 128 x 64 = 64 K)
     } else {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     }
@@ -461,8 +492,12 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           float p0, p1;
           ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), scale_log2, nsub);
           if constexpr (VAR & kVarPolyExpHalf) {
-            p0 = ex2_ftz(p0);
-            p1 = ex2_poly(p1);                                    // odd key columns: FMA pipe
+            if (i & 1) {                                          // key columns 4k+2, 4k+3: FMA pipe, packed
+              ex2_poly2(p0, p1);
+            } else {
+              p0 = ex2_ftz(p0);
+              p1 = ex2_ftz(p1);
+            }
           } else if constexpr (VAR & kVarPolyExp) {
             p0 = ex2_ftz(p0);
             p1 = (i & 1) ? ex2_poly(p1) : ex2_ftz(p1);            // key column 2i + 1 = 3 (mod 4): FMA pipe
