@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-2 first contact, part 1 (1 GPU, ~20 min of box time): validate what was written after the round-1
+# Round-2 first contact, part 1 (1 GPU, ~25-30 min of box time): validate what was written after the round-1
 # GPU minutes were spent.  Every stage under its own timeout; logs into gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash tools/gpu/r02_first.sh'      then tools/gpu/r02_second.sh
+#   gpurun --timeout 2400 -- 'bash tools/gpu/r02_first.sh'      then tools/gpu/r02_second.sh
 mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
 run() { name=$1; shift; timeout "$@" > gpurun_out/$name.log 2>&1; echo "$name exit $?" >> gpurun_out/summary.txt; }
 PT="python -m pytest -q -m gpu --no-header -p no:cacheprovider --tb=short"
