@@ -398,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
         roofline["whole_clip_tflops"] = roofline["whole_clip_frac_of_sustained"] = None
 
     gpu_eager = None
-    if world == 1 and kind == "full" and not args.rollout:
+    if world == 1 and kind == "full" and not args.rollout and not args.no_baselines:
         try:      # the reference path as written, eager bf16 on this GPU (reported next to ours)
             sec_step = gpu_eager_oracle(model, dims, n_ctx, n_gen, H, W, dev)
             gpu_eager = {"value": 2 * n_gen * block / sec_step, "unit": "tokens/s", "ms_per_euler_step": 1e3 * sec_step,
@@ -409,7 +409,10 @@ def run_ours(args, rank, world, local_rank):
             gpu_eager = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
         torch.cuda.empty_cache()
     threads = os.cpu_count() or 1
-    cpu_v, cpu_desc, _ = cpu_reference_sample(dims, n_ctx, n_gen, H, W, euler, 8 if kind == "full" else dims.num_hidden_layers, threads)
+    if args.no_baselines:        # exploratory runs (tools/gpu/*.sh): skip the CPU / eager legs, never the default line
+        cpu_v, cpu_desc = None, "skipped (--no-baselines)"
+    else:
+        cpu_v, cpu_desc, _ = cpu_reference_sample(dims, n_ctx, n_gen, H, W, euler, 8 if kind == "full" else dims.num_hidden_layers, threads)
     lat_bytes = 4 * (H // 8) * (W // 8) * 2
     line = {"metric": "next_clip_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
@@ -454,6 +457,8 @@ def main():
     ap.add_argument("--rollout", type=int, default=0, help="a step = this many clips generated autoregressively in "
                     "latent space (window = the workload's context + clip); 0 = one clip per step")
     ap.add_argument("--recompute", action="store_true", help="--rollout without the persistent K/V cache")
+    ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / gpu_eager_baseline legs "
+                    "(exploratory runs only; the default line always carries them)")
     args = ap.parse_args()
     if os.environ.get("VGPT_FAULT_DUMP"):      # debugging aid: dump every thread's stack after N seconds and exit
         import faulthandler

@@ -206,7 +206,8 @@ def backbone(w, inputs_embeds, attention_mask, position_ids, cfg: OracleConfig,
 
 def frame_block_forward(w, cfg: OracleConfig, x: List[torch.Tensor], timestep, input_ids,
                         input_img_latents, input_image_sizes, attention_mask, position_ids,
-                        denoise_image_sizes, time_emb_inx, return_hidden: bool = False):
+                        denoise_image_sizes, time_emb_inx, return_hidden: bool = False,
+                        layer_outputs: Optional[list] = None):
     dtype = x[0].dtype
     shapes = [list(l.shape[-2:]) for l in x]
     xs = [patch_embed(l, w["x_embedder.proj.weight"], w["x_embedder.proj.bias"], w["pos_embed"], cfg)
@@ -230,7 +231,11 @@ def frame_block_forward(w, cfg: OracleConfig, x: List[torch.Tensor], timestep, i
         for s, e in denoise_image_sizes[b]:
             emb[b, s:e] = xs[n]; n += 1
     assert n == len(xs)
-    hidden = backbone(w, emb, attention_mask, position_ids, cfg)           # 465
+    if layer_outputs is not None:          # diagnostic: hidden state after every decoder layer
+        hidden, per_layer = backbone(w, emb, attention_mask, position_ids, cfg, return_layer_outputs=True)
+        layer_outputs.extend(per_layer)
+    else:
+        hidden = backbone(w, emb, attention_mask, position_ids, cfg)       # 465
     t_emb = timestep_embedder(w, "t_embedder", timestep, dtype)            # 480
     out, n = [], 0
     for b in denoise_image_sizes.keys():                                   # 481-486

@@ -401,6 +401,14 @@ def test_attention_long_context_tile_skipping(ops):
     _attention_case(ops, 32, 4, 64, 64, 2, 96, "step", 401)
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("phase", ["step", "prefix"])
+def test_attention_cfg3_geometry(ops, phase):
+    """BASELINE configs[2] at full frame size: 32 context frames of 258 tokens + 4 generated, 73 pages per
+    sequence (the conditional CTA of a generated query pair walks 73 KV tiles, a context CTA up to 65)."""
+    _attention_case(ops, 32, 4, 256, 256, 1, 96, phase, 450)
+
+
 # ---------------------------------------------------------------------------------------------
 # experimental attention variants (VGPT_ATTN_VARIANT; csrc/attention_pair_tcgen05.cu kVar*)
 # ---------------------------------------------------------------------------------------------

@@ -396,6 +396,9 @@ class NextClipEngine:
         import os
         self.fold_norm = os.environ.get("VGPT_FOLD_RMSNORM") == "1" and peers is None
         self.plan: Optional[ClipPlan] = None
+        # diagnostic tap (tools/parity_floor.py): a list that receives a copy of the hidden rows after every
+        # decoder layer of eager (non-graph) passes; None in production
+        self.layer_tap: Optional[list] = None
         self._graph = None
         self._rope_tab = None
         self.rope_reserve = 0            # positions to provision the RoPE table for (rollouts grow)
@@ -573,6 +576,8 @@ class NextClipEngine:
                 ops.rmsnorm(hidden, lw["ln2"], self.eps, out=xn)
                 ops.gemm(xn, lw["gate_up"], out=mlp_h, epilogue=ops.EPI_SWIGLU)
                 ops.gemm(mlp_h, lw["down"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
+            if self.layer_tap is not None:
+                self.layer_tap.append(hidden.clone())
 
     def _drive(self, gen):
         """Run a kernel-sequence generator; at its sync points enqueue the cross-GPU barrier."""

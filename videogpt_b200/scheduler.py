@@ -105,6 +105,10 @@ class LVMScheduler:
                     self.record_velocity.append(vel.clone())
         finally:
             e.uniform_t = False
+        if e.peers is not None:
+            # sequence parallel: a barrier that timed out (a peer died or fell behind by ~10 s) lets this rank run
+            # on K/V and prediction rows its peers never delivered -- never return such latents as a result
+            e.peers.check()
         if not is_list:
             return e.z.clone()
         out = [e.z[i:i + 1].clone() for i in range(n)]
