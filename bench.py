@@ -334,6 +334,8 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         clip_device()
     barrier()
+    peers = model.sequence_parallel_peers() if sp_size > 1 else None
+    barrier_s0 = peers.barrier_seconds() if peers is not None else 0.0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -346,6 +348,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     dt = s.elapsed_time(t) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
+    barrier_s = (peers.barrier_seconds() - barrier_s0) if peers is not None else 0.0
 
     clip_host()
     barrier()
@@ -356,11 +359,11 @@ def run_ours(args, rank, world, local_rank):
     dt_e2e = time.perf_counter() - t0
 
     if world > 1:
-        tt = torch.tensor([dt, dt_e2e], device=dev, dtype=torch.float64)
+        tt = torch.tensor([dt, dt_e2e, barrier_s, -barrier_s], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = float(tt[0]), float(tt[1])
+        dt, dt_e2e, barrier_max, barrier_min = float(tt[0]), float(tt[1]), float(tt[2]), -float(tt[3])
     if rank != 0:
-        return
+        return None
     tokens_per_clip = 2 * n_gen * block * euler * rounds
     videos = world // 2 if cfg_split else world // sp_size
     if vids_rank:
@@ -439,7 +442,108 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": {"value": cpu_v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": cpu_desc}}
     if gpu_eager is not None:
         line["gpu_eager_baseline"] = gpu_eager
-    print(json.dumps(line), flush=True)
+    if sp_size > 1:
+        # one video on sp_size GPUs: where the time goes besides the kernels.  Every rank pushes the post-RoPE K / V
+        # rows it computes to the other sp_size - 1 ranks (NVLink peer stores fused into rope_kv_append), plus the
+        # prediction rows; the flag barriers (one per layer + one per step) are timed on the device (globaltimer).
+        rows_step, rows_prefill = 2 * n_gen * block, n_ctx * block
+        kv_row = 2 * dims.hidden_size * 2 * dims.num_hidden_layers
+        n_steps_timed = args.steps * rounds * euler
+        line["sequence_parallel"] = {
+            "sp": sp_size, "per_gpu_tflops": clip_fl * args.steps / dt / 1e12 / sp_size,
+            "barrier_ms_per_euler_step": {"slowest_rank": 1e3 * barrier_max / n_steps_timed,
+                                          "fastest_rank": 1e3 * barrier_min / n_steps_timed,
+                                          "note": "device time inside vgpt_peer_barrier kernels (%d per step): waiting for the "
+                                                  "slowest peer + NVLink flag round trip; prefill barriers included" % (dims.num_hidden_layers + 1)},
+            "nvlink_bytes_per_euler_step": (sp_size - 1) * (rows_step * kv_row + 2 * n_gen * lat_bytes),
+            "nvlink_bytes_prefill": (sp_size - 1) * rows_prefill * kv_row}
+        roofline["whole_clip_frac_of_sustained"] = roofline["whole_clip_tflops"] / sp_size / peaks.get("bf16_tflops_sustained", 1400.0)
+        roofline["whole_clip_frac_note"] = "per GPU: whole-clip TFLOP/s / sp / sustained peak"
+    return line
+
+
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _run_child(cmd, env, timeout_s):
+    """Run `cmd` in its own session; on time-out kill the whole process group.  Returns (last JSON line of its stdout,
+    None) or (None, reason)."""
+    import signal
+    p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        p.wait()
+        return None, f"timed out after {timeout_s} s (child process group killed)"
+    line = None
+    for ln in out.splitlines():
+        if ln.startswith("{"):
+            try:
+                line = json.loads(ln)
+            except ValueError:
+                pass
+    if p.returncode != 0 or line is None:
+        return None, f"exit {p.returncode}: {(err or out)[-300:]}"
+    return line, None
+
+
+def strong_scaling_child(world, config, timeout_s):
+    """One video of `config` sharded over all `world` GPUs (sequence parallel: rows split, K/V pushed to the peers over
+    NVLink) in a CHILD torchrun with a hard time-out, so that a stall there can never cost the parent's bench line."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.abspath(__file__), "--gpus", str(world), "--parallelism", "sp",
+           "--config", config, "--steps", "2", "--warmup", "3", "--no-baselines", "--strong", "none"]
+    drop = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_NAME",
+            "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS")
+    env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC")}
+    t0 = time.perf_counter()
+    line, err = _run_child(cmd, env, timeout_s)
+    if line is None:
+        return {"error": err}
+    keep = {k: line.get(k) for k in ("s_per_clip", "value", "unit", "n_gpus", "scaling", "gpu_launches", "sequence_parallel")}
+    keep["e2e_s_per_clip"] = line["e2e"]["s_per_clip"]
+    keep["parallelism"] = line["config"]["parallelism"]
+    keep["child_wall_s"] = time.perf_counter() - t0
+    return keep
+
+
+def strong_scaling_single(configs):
+    """The one-GPU denominators of the strong-scaling lines: the same videos on ONE GPU, in-process (fresh model)."""
+    from videogpt_b200 import LVMPipeline, LVMProcessor, synth
+    from videogpt_b200.synth import SingleIdTagTokenizer as FakeTokenizer
+    dev = torch.device("cuda", 0)
+    out = {}
+    model = build_model(_dims("full"), dev)
+    pipe = LVMPipeline(None, model, LVMProcessor(FakeTokenizer()), device=dev)
+    for cfg in configs:
+        kind, n_ctx, n_gen, H, W, euler = WORKLOADS[cfg]
+        lat = [x.to(dev, torch.bfloat16) for x in synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)]
+        kw = dict(num_inference_steps=euler, img_guidance_scale=GUIDANCE, prediction_type="x1")
+        try:
+            for _ in range(2):
+                pipe.next_clip_latents([x.clone() for x in lat[:n_ctx]], n_gen, initial_noise=lat[n_ctx:], **kw)
+            torch.cuda.synchronize()
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(2):
+                pipe.next_clip_latents([x.clone() for x in lat[:n_ctx]], n_gen, initial_noise=lat[n_ctx:], **kw)
+            t.record()
+            torch.cuda.synchronize()
+            sec = s.elapsed_time(t) * 1e-3 / 2
+            block = H * W // 256 + 2
+            out[cfg] = {"s_per_clip": sec, "value": 2 * n_gen * block * euler / sec, "unit": "tokens/s", "n_gpus": 1,
+                        "per_gpu_tflops": algorithmic_flops(_dims(kind), n_ctx, n_gen, block, euler)[2] / sec / 1e12}
+        except Exception as exc:
+            out[cfg] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    return out
 
 
 def main():
@@ -457,6 +561,10 @@ def main():
     ap.add_argument("--rollout", type=int, default=0, help="a step = this many clips generated autoregressively in "
                     "latent space (window = the workload's context + clip); 0 = one clip per step")
     ap.add_argument("--recompute", action="store_true", help="--rollout without the persistent K/V cache")
+    ap.add_argument("--strong", default="auto", help="strong-scaling block: 'auto' (on for the default cfg2 / dp line: one "
+                    "cfg5 and one cfg3 video sharded over all N GPUs, sequence parallel, in a child process with a hard "
+                    "time-out; at N = 1 the one-GPU denominators), 'none', or a comma list of configs")
+    ap.add_argument("--strong-timeout", type=int, default=240)
     ap.add_argument("--no-baselines", action="store_true", help="skip the cpu_baseline / gpu_eager_baseline legs "
                     "(exploratory runs only; the default line always carries them)")
     args = ap.parse_args()
@@ -477,14 +585,36 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = None
     try:
-        run_ours(args, rank, world, local_rank)
+        line = run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             from videogpt_b200 import parallel_states
             parallel_states.destroy_sequence_parallel_group()
             import torch.distributed as dist
             dist.destroy_process_group()
+    if line is None:
+        return            # ranks > 0 are done; they exit and release their GPUs
+    strong = args.strong
+    if strong == "auto":
+        strong = "cfg5,cfg3" if (args.config == "cfg2" and args.parallelism == "dp" and not args.rollout) else "none"
+    if strong != "none":
+        # The weak-scaling `value` above is replicas (no collective on the data path).  This block is the part of the
+        # multi-GPU design that has one: ONE video sharded over all N GPUs (rows split, K/V rows pushed into the peers'
+        # pools over NVLink by the producing kernel, flag barriers), BASELINE configs[2] (cfg3) and configs[4] (cfg5).
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        cfgs = [c for c in strong.split(",") if c in WORKLOADS]
+        if world == 1:
+            line["strong_scaling"] = {"n_gpus": 1, "mode": "one GPU (denominator of the sp lines at N > 1)", **strong_scaling_single(cfgs)}
+        else:
+            time.sleep(2.0)      # the other ranks of this job are exiting and releasing their GPUs
+            line["strong_scaling"] = {"n_gpus": world, "mode": f"sp{world}: one video over all GPUs, child torchrun, "
+                                      f"hard time-out {args.strong_timeout} s",
+                                      **{c: strong_scaling_child(world, c, args.strong_timeout) for c in cfgs}}
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -158,7 +158,8 @@ int vgpt_peer_import(const void* handle64, void** out);
 int vgpt_peer_close(void* p);
 
 /* Barrier over n_ranks GPUs through peer-mapped flag words: flag_ptrs[j] -> rank j's uint32[n_ranks]
- * (flag_ptrs[rank] is local); state = local uint32[2] {epoch, timed_out}.  Enqueued like any other
+ * (flag_ptrs[rank] is local); state = local, 8-byte aligned uint32[4] {epoch, timed_out, uint64 nanoseconds
+ * spent inside barrier kernels so far}.  Enqueued like any other
  * kernel (graph capturable); every rank must enqueue the same sequence of barriers.  A peer that
  * never arrives sets state[1] after ~10 s instead of hanging the GPU; later barriers then return
  * at once (fail fast; the host checks state[1]). */

@@ -45,11 +45,13 @@ def _run(monkeypatch, capsys, argv, workload):
         fn = getattr(pipeline.LVMPipeline, name)
         monkeypatch.setattr(pipeline.LVMPipeline, name, (lambda f: lambda self, *a, **k: f(self, *a, **{**k, "dtype": torch.float32}))(fn))
     args = bench.argparse.Namespace(**argv)
-    bench.run_ours(args, 0, 1, 0)
-    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-    return line
+    line = bench.run_ours(args, 0, 1, 0)
+    if argv.get("strong_single"):
+        line["strong_scaling"] = bench.strong_scaling_single(argv["strong_single"])
+    return json.loads(json.dumps(line))        # must be JSON-serialisable
 
-BASE = dict(gpus=1, steps=1, warmup=1, impl="ours", parallelism="dp", sp=0, batch=2, rollout=0, recompute=False)
+BASE = dict(gpus=1, steps=1, warmup=1, impl="ours", parallelism="dp", sp=0, batch=2, rollout=0, recompute=False,
+            no_baselines=False, strong="none", strong_timeout=10)
 
 def test_default(emu, monkeypatch, capsys):
     line = _run(monkeypatch, capsys, dict(BASE, config="cfg2"), {"cfg2": ("reduced", 2, 2, 64, 64, 2)})
@@ -57,6 +59,14 @@ def test_default(emu, monkeypatch, capsys):
               "dtype", "data", "config", "clocks", "gpu_launches", "e2e", "roofline", "cpu_baseline"):
         assert k in line, k
     assert line["config"]["workload"] == "cfg2" and line["scaling"] == "weak" and line["e2e"]["h2d_bytes_per_step"] > 0
+
+def test_strong_scaling_single_gpu_block(emu, monkeypatch, capsys):
+    monkeypatch.setattr("bench._dims", lambda kind: __import__("videogpt_b200").synth.REDUCED)
+    line = _run(monkeypatch, capsys, dict(BASE, config="cfg2", strong_single=["cfg5", "cfg3"]),
+                {"cfg2": ("reduced", 2, 2, 64, 64, 2), "cfg5": ("reduced", 1, 1, 64, 96, 2), "cfg3": ("reduced", 3, 1, 64, 64, 2)})
+    for c in ("cfg5", "cfg3"):
+        assert "error" not in line["strong_scaling"][c], line["strong_scaling"][c]
+        assert line["strong_scaling"][c]["s_per_clip"] > 0
 
 def test_cfg4(emu, monkeypatch, capsys):
     line = _run(monkeypatch, capsys, dict(BASE, config="cfg4"), {"cfg4": ("reduced", 2, 2, 64, 64, 2)})

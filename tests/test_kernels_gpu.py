@@ -118,6 +118,48 @@ def test_gemm_skinny_tail_matches_tiled_path_bit_exact(ops, M):
     assert _rel(ops.gemm(a, w, cta_pair=2), ref) < 4e-3
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("block_n", [0, 256, 192])
+@pytest.mark.parametrize("M", [2064, 1032, 280, 8208, 258, 100, 16, 384, 2121])
+def test_gemm_fused_tail_tiles_match_tiled_path_bit_exact(ops, M, block_n):
+    """M = q*256 + tail, tail <= 128: the tail rows are computed by swapped-operand tail tiles inside the
+    persistent launch (cta_pair=3 forces it; it is the default of the auto path).  They must give the same
+    BITS as plain 256-row tiles (cta_pair=1) for all three epilogues: a row's result may not depend on which
+    kind of tile computed it (sequence-parallel shards and the unsharded run group rows differently)."""
+    K, N = 512, 1024
+    a, w, r = _rand((M, K), 21), _rand((N, K), 22, 0.05), _rand((M, N), 23)
+    kw1, kw3 = dict(block_n=block_n, cta_pair=1), dict(block_n=block_n, cta_pair=3)
+    want = ops.gemm(a, w, **kw1)
+    assert torch.equal(ops.gemm(a, w, **kw3), want)
+    assert torch.equal(ops.gemm(a, w), want)                      # the default path
+    o1, o2 = r.clone(), r.clone()
+    ops.gemm(a, w, out=o1, residual=o1, epilogue=ops.EPI_RESIDUAL, **kw1)
+    ops.gemm(a, w, out=o2, residual=o2, epilogue=ops.EPI_RESIDUAL, **kw3)
+    assert torch.equal(o1, o2)
+    packed = ops.pack_gate_up(w)
+    assert torch.equal(ops.gemm(a, packed, epilogue=ops.EPI_SWIGLU, **kw3), ops.gemm(a, packed, epilogue=ops.EPI_SWIGLU, **kw1))
+    ref = a.float() @ w.float().t()
+    assert _rel(ops.gemm(a, w, **kw3), ref) < 4e-3
+
+
+@pytest.mark.timeout(300)
+def test_gemm_fused_tail_full_size_projections(ops):
+    """The four projection shapes of the model at M = 2064 (cfg2) and at a sequence-parallel shard (M = 1040):
+    fused tail tiles vs plain tiles, bit for bit; K = 8192 exercises the long k loop of a tail tile."""
+    for M in (2064, 1040):
+        for N, K, epi in ((9216, 3072, ops.EPI_STORE), (3072, 3072, ops.EPI_RESIDUAL), (16384, 3072, ops.EPI_SWIGLU),
+                          (3072, 8192, ops.EPI_RESIDUAL)):
+            a, w = _rand((M, K), 31), _rand((N, K), 32, 0.02)
+            n_out = N // 2 if epi == ops.EPI_SWIGLU else N
+            r = _rand((M, n_out), 33)
+            o1, o2 = r.clone(), r.clone()
+            res = dict(residual=o1) if epi == ops.EPI_RESIDUAL else {}
+            ops.gemm(a, w, out=o1, epilogue=epi, cta_pair=1, **res)
+            res = dict(residual=o2) if epi == ops.EPI_RESIDUAL else {}
+            ops.gemm(a, w, out=o2, epilogue=epi, cta_pair=3, **res)
+            assert torch.equal(o1, o2), (M, N, K, epi)
+
+
 def test_gemm_rejects_bad_arguments(ops):
     from videogpt_b200._lib import VgptError
     with pytest.raises(VgptError):

@@ -53,7 +53,10 @@ def test_sharded_plans_partition_the_unsharded_plan(world, geom):
             assert torch.equal(torch.cat(pieces), getattr(f, name)), (which, name)
         for s in range(len(specs)):
             sizes = [int(x.seqs[s, 1]) for x in ph]
-            assert max(sizes) - min(sizes) <= 1                      # balanced
+            # balanced: within one row, or -- when every rank gets whole 128-row tiles -- within one tile + remainder
+            assert max(sizes) - min(sizes) <= (1 if sum(sizes) < eng.SHARD_ALIGN * world else 2 * eng.SHARD_ALIGN - 1)
+            if sum(sizes) >= eng.SHARD_ALIGN * world:
+                assert all(n % eng.SHARD_ALIGN == 0 for n in sizes[:-1])   # every shard starts on an attention tile
             assert all(int(x.seqs[s, 2]) == int(f.seqs[s, 2]) for x in ph)   # every rank sees all keys
 
 

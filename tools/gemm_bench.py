@@ -22,7 +22,9 @@ for name, (N, K, epi) in shapes.items():
     out = torch.zeros(M, n_out, device=dev, dtype=torch.bfloat16)
     # (0, -1) = the library's own choice (with VGPT_GEMM_SKINNY_TAIL=1: main tiles + skinny tail kernel);
     # (0, 2) = skinny tail forced (experimental)
-    variants = ((256, 0), (192, 0), (256, 1), (192, 1), (0, -1)) + (((0, 2),) if os.environ.get("VGPT_GEMM_SKINNY_TAIL") == "1" else ())
+    # pair: 1 = plain 256-row tiles, 3 = tail rows as swapped-operand tail tiles inside the launch, -1 = library default,
+    # 2 = tail rows in a separate skinny launch (superseded)
+    variants = ((256, 1), (192, 1), (256, 3), (192, 3), (0, -1)) + (((0, 2),) if os.environ.get("VGPT_GEMM_SKINNY_TAIL") == "1" else ())
     for bn, pair in variants:
         def run():
             for w in ws:

@@ -22,6 +22,8 @@
 
 #include <cuda.h>
 
+#include <cstring>
+
 namespace vgpt {
 
 constexpr int kG2BlockM = 128;     // rows per CTA (256 per pair)
@@ -36,7 +38,25 @@ struct Gemm2Cfg {
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;     // two accumulator stages
   static constexpr int kBarBytes = 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kXchgBytes = 2 * 16 * 32 * 4;               // tail tiles, SwiGLU: 16 up values x 32 lanes x 2 warp pairs
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kXchgBytes + 1024;
+};
+
+// Tail tiles (M % 256 rows that do not fill a 256-row tile), computed INSIDE the persistent kernel with the operands
+// swapped:   C_tail^T[N, T] = W[N, K] * A_tail[T, K]^T
+// The weight rows are the M = 256 operand of tcgen05.mma.cta_group::2 (128 per CTA, in the A slot of a stage), the T
+// tail rows the N operand (T/2 per CTA, in the B slot), the accumulator holds the tail transposed (TMEM lane = output
+// column, TMEM column = tail row).  A tail tile covers 256 output columns and costs about a third of a 256 x 256 main
+// tile (it streams W at the L2 -> SMEM fill rate and issues N = T MMAs), instead of a whole extra row of main tiles --
+// 2064 = 8 x 256 + 16 at cfg2 costs a fifth wave for qkv and an eighth for gate_up otherwise.  `owner[j]` = the cluster
+// that computes tail tile j (columns [256 j, 256 j + 256)), chosen on the host by list scheduling after the main tiles.
+constexpr int kMaxTailTiles = 64;
+struct TailArgs {
+  int rows;        // valid tail rows (0: no tail tiles)
+  int T;           // rows padded to a multiple of 16 (the MMA's N), <= 128
+  int n_tail;      // N / 256
+  int row0;        // first tail row (= rows handled by the main tiles)
+  uint8_t owner[kMaxTailTiles];
 };
 
 enum : int { kG2Store = 0, kG2Residual = 1, kG2SwiGLU = 2,
@@ -122,8 +142,9 @@ __device__ __forceinline__ float store_chunk2_ss(const uint32_t (&acc)[32], __nv
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                              const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_t,
                               __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ R, int M, int N,
-                              int K, int ldc, int flags, EpiExtra<EPI> ex) {
+                              int K, int ldc, int flags, EpiExtra<EPI> ex, const __grid_constant__ TailArgs tail) {
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -134,6 +155,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  [[maybe_unused]] float* xchg = reinterpret_cast<float*>(smem_raw + (bar_base + Cfg::kBarBytes - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -143,10 +165,12 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = K / kG2BlockK;
+  const int n_tail = tail.rows > 0 ? tail.n_tail : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (n_tail) { tma_prefetch_desc(&tmap_w); tma_prefetch_desc(&tmap_t); }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);          // leader producer's arrive.expect_tx covers both CTAs' bytes
       mbar_init(empty_bar(s), 1);         // leader's multicast commit
@@ -188,6 +212,21 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      // tail tiles: this CTA's 128 weight rows into the A slot, its half of the tail rows into the B slot
+      const uint32_t tail_tx = 2u * (uint32_t)(Cfg::kABytes + (tail.T / 2) * kG2BlockK * 2);
+      for (int j = 0; j < n_tail; ++j) {
+        if ((int)tail.owner[j] != cluster_id) continue;
+        const int n0 = j * 2 * kG2BlockM + rank * kG2BlockM;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + Cfg::kABytes;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), tail_tx);
+          tma_load_2d_pair(sa, &tmap_w, full_bar(stage), kb * kG2BlockK, n0);
+          tma_load_2d_pair(sb, &tmap_t, full_bar(stage), kb * kG2BlockK, (int)rank * (tail.T / 2));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (leader only) ================================
@@ -212,6 +251,29 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
 #pragma unroll
           for (int k = 0; k < kG2BlockK / 16; ++k)
             umma_f16_ss_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(tmem_full_bar(as));
+      }
+      const uint32_t idesc_tail = make_idesc_bf16(2 * kG2BlockM, tail.T);
+      for (int j = 0; j < n_tail; ++j) {
+        if ((int)tail.owner[j] != cluster_id) continue;
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        ++local;
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(sa + Cfg::kABytes, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kG2BlockK / 16; ++k)
+            umma_f16_ss_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_tail, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit_pair(empty_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -303,6 +365,59 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+    }
+    // ---- tail tiles: TMEM lane = output column (weight row), TMEM column = tail row --------------------
+    if constexpr (EPI == kG2Store || EPI == kG2Residual || EPI == kG2SwiGLU) {
+      for (int j = 0; j < n_tail; ++j) {
+        if ((int)tail.owner[j] != cluster_id) continue;
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        ++local;
+        mbar_wait(tmem_full_bar(as), aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
+        const int n = j * 2 * kG2BlockM + (int)rank * kG2BlockM + quad * 32 + lane;     // weight row
+        for (int c = 0; c < tail.T / 16; ++c) {
+          uint32_t acc[16];
+          tmem_ld_32x32b_x16(taddr + c * 16, acc);
+          tmem_ld_wait();
+          if constexpr (EPI == kG2SwiGLU) {
+            // packed weight rows: [gate x 32 | up x 32] per 64 -> even quads hold gate, odd quads the matching up
+            float* x = xchg + (quad >> 1) * 16 * 32;
+            if (quad & 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i * 32 + lane] = __uint_as_float(acc[i]);
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + (quad >> 1)) : "memory");
+            if (!(quad & 1)) {
+              const int oc = (j * 2 * kG2BlockM + (int)rank * kG2BlockM) / 2 + (quad >> 1) * 32 + lane;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int r = c * 16 + i;
+                if (r < tail.rows) {
+                  const float gv = rbf(__uint_as_float(acc[i]));
+                  const float uv = rbf(x[i * 32 + lane]);
+                  C[(size_t)(tail.row0 + r) * ldc + oc] = __float2bfloat16_rn(uv * rbf(silu_f(gv)));
+                }
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + (quad >> 1)) : "memory");      // x reusable
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = c * 16 + i;
+              if (r < tail.rows) {
+                float v = __uint_as_float(acc[i]);
+                if constexpr (EPI == kG2Residual) v = rbf(v) + __bfloat162float(R[(size_t)(tail.row0 + r) * ldc + n]);
+                C[(size_t)(tail.row0 + r) * ldc + n] = __float2bfloat16_rn(v);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(as), 0);
+      }
     }
   }
 
@@ -486,15 +601,18 @@ gemm_bf16_skinny_pair_kernel(const __grid_constant__ CUtensorMap tmap_w, const _
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// `tail_rows` > 0: rows [M, M + tail_rows) of A / C / R are computed by swapped-operand tail tiles inside the same
+// launch (M is then a multiple of 256, or 0); needs N % 256 == 0 and a plain epilogue (0..2).
 template <int BN, int EPI>
 static int launch_gemm2(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                        int ldc, int num_sms, cudaStream_t stream, EpiExtra<EPI> ex = EpiExtra<EPI>()) {
+                        int ldc, int num_sms, cudaStream_t stream, EpiExtra<EPI> ex = EpiExtra<EPI>(), int tail_rows = 0) {
   using Cfg = Gemm2Cfg<BN>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tw, tt;
+  cuuint32_t estr[2] = {1, 1};
   {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)(M > 0 ? M : 1)};
     cuuint64_t strides[1] = {(cuuint64_t)lda * 2};
-    cuuint32_t box[2] = {kG2BlockK, kG2BlockM}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {kG2BlockK, kG2BlockM};
     int rc = encode_tensor_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(A), dims, strides, box,
                                estr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -502,22 +620,64 @@ static int launch_gemm2(const void* A, const void* W, void* C, const void* R, in
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {kG2BlockK, BN / 2}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {kG2BlockK, BN / 2};
     int rc = encode_tensor_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box,
                                estr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = gemm_bf16_tcgen05_pair_kernel<BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  const int clusters_max = num_sms / 2;
   const int tiles = ((M + 2 * kG2BlockM - 1) / (2 * kG2BlockM)) * ((N + BN - 1) / BN);
-  const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
-  kern<<<2 * clusters, kG2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, static_cast<__nv_bfloat16*>(C),
+  TailArgs tail;
+  memset(&tail, 0, sizeof(tail));
+  tw = tb;
+  tt = ta;
+  int clusters = tiles < clusters_max ? tiles : clusters_max;
+  if (tail_rows > 0) {
+    tail.rows = tail_rows;
+    tail.T = (tail_rows + 15) & ~15;
+    tail.n_tail = N / (2 * kG2BlockM);
+    tail.row0 = M;
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+      cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+      cuuint32_t box[2] = {kG2BlockK, kG2BlockM};
+      int rc = encode_tensor_map(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)tail_rows};          // rows beyond tail_rows are zero-filled
+      cuuint64_t strides[1] = {(cuuint64_t)lda * 2};
+      cuuint32_t box[2] = {kG2BlockK, (cuuint32_t)(tail.T / 2)};
+      const __nv_bfloat16* a_tail = static_cast<const __nv_bfloat16*>(A) + (size_t)M * lda;
+      int rc = encode_tensor_map(&tt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(a_tail), dims, strides,
+                                 box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    // list scheduling: main tiles are dealt round robin (tile t -> cluster t % clusters); every tail tile goes to the
+    // cluster that is least loaded so far.  Costs in tensor-pipe cycles per k-block: a main tile issues 4 MMAs of
+    // N/2 + 43 cycles (SS form, profiles/r01h_umma_rate.txt); a tail tile 4 MMAs of T/2 + 43, but not less than the
+    // ~200 cycles its 17 KB per SM take through the L2 -> SMEM fabric.
+    clusters = (tiles + tail.n_tail) < clusters_max ? (tiles + tail.n_tail) : clusters_max;
+    const double c_main = 4.0 * (BN / 2 + 43);
+    double c_tail = 4.0 * (tail.T / 2 + 43);
+    if (c_tail < 200.0) c_tail = 200.0;
+    double load[256];
+    for (int c = 0; c < clusters; ++c) load[c] = c_main * ((tiles + clusters - 1 - c) / clusters);
+    for (int j = 0; j < tail.n_tail; ++j) {
+      int best = 0;
+      for (int c = 1; c < clusters; ++c)
+        if (load[c] < load[best] - 1e-9) best = c;
+      tail.owner[j] = (uint8_t)best;
+      load[best] += c_tail;
+    }
+  }
+  auto kern = gemm_bf16_tcgen05_pair_kernel<BN, EPI>;
+  // per launch: the attribute is per device, and a process may drive several devices (cheap, capture-safe)
+  VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  kern<<<2 * clusters, kG2Threads, Cfg::kSmemBytes, stream>>>(ta, tb, tw, tt, static_cast<__nv_bfloat16*>(C),
                                                              static_cast<const __nv_bfloat16*>(R), M, N, K, ldc,
-                                                             debug_gemm_flags(), ex);
+                                                             debug_gemm_flags(), ex, tail);
   VGPT_CHECK_LAUNCH();
   return 0;
 }
@@ -545,11 +705,7 @@ static int launch_skinny(const void* A_tail, const void* W, void* C_tail, const 
     if (rc) return rc;
   }
   auto kern = gemm_bf16_skinny_pair_kernel<T, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int tiles = N / (2 * kG2BlockM);
   const int clusters = tiles < num_sms / 2 ? tiles : num_sms / 2;
   kern<<<2 * clusters, kG2Threads, Cfg::kSmemBytes, stream>>>(tw, ta, static_cast<__nv_bfloat16*>(C_tail),
@@ -609,11 +765,15 @@ int gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, 
   return -1;
 }
 
+// `tail_rows` > 0: M main rows (a multiple of 256, or 0) + tail_rows <= 128 more rows computed by tail tiles.
 int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
-                   int epilogue, int block_n, cudaStream_t stream) {
+                   int epilogue, int block_n, cudaStream_t stream, int tail_rows) {
   const int sms = device_sm_count();
+  VGPT_CHECK_ARG(tail_rows >= 0 && tail_rows <= 128 && (tail_rows == 0 || (M % 256 == 0 && N % 256 == 0 && N / 256 <= kMaxTailTiles && sms / 2 <= 255)),
+                 "vgpt_gemm_bf16: tail tiles need M %% 256 == 0, N %% 256 == 0, N <= %d (M=%d N=%d tail=%d)", 256 * kMaxTailTiles, M, N, tail_rows);
 #define VGPT_GEMM2_CASE(BN_, EPI_) \
-  if (block_n == BN_ && epilogue == EPI_) return launch_gemm2<BN_, EPI_>(A, W, C, R, M, N, K, lda, ldc, sms, stream);
+  if (block_n == BN_ && epilogue == EPI_) \
+    return launch_gemm2<BN_, EPI_>(A, W, C, R, M, N, K, lda, ldc, sms, stream, EpiExtra<EPI_>(), tail_rows);
   VGPT_GEMM2_CASE(256, kG2Store)
   VGPT_GEMM2_CASE(256, kG2Residual)
   VGPT_GEMM2_CASE(256, kG2SwiGLU)

@@ -310,34 +310,32 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
   VGPT_CHECK_ARG(epilogue != kEpiResidual || R, "vgpt_gemm_bf16: residual epilogue needs R");
   const bool auto_pair = cta_pair < 0;
   if (cta_pair < 0) cta_pair = kDefaultCtaPair;
-  // Skinny tail, EXPERIMENTAL (written after this round's GPU budget was spent: compiled, never run
-  // on hardware).  Reached only with cta_pair == 2, or from the tuned default when the environment
-  // sets VGPT_GEMM_SKINNY_TAIL=1.  When M = q * 256 + tail with tail <= 32, the tail rows go to the
-  // swapped-operand kernel (gemm2_tcgen05.cu) and the main kernel loses its last, almost empty row
-  // of tiles -- taken when that saves at least one wave of the main kernel.
-  static const bool skinny_opt_in = [] { const char* e = getenv("VGPT_GEMM_SKINNY_TAIL"); return e && e[0] == '1'; }();
+  // Rows that do not fill a 256-row tile (M % 256 <= 128: the 16 tag / time-slot rows of M = 2064 at cfg2, the
+  // remainders of sequence-parallel shards) are computed by swapped-operand TAIL TILES inside the same persistent
+  // launch (gemm2_tcgen05.cu, TailArgs) instead of a whole extra row of mostly empty 256-row tiles.  Default for the
+  // CTA-pair path (VGPT_GEMM_FUSED_TAIL=0 switches it off for A/B timing); cta_pair == 3 forces it with any block_n.
+  static const bool fused_tail_on = [] { const char* e = getenv("VGPT_GEMM_FUSED_TAIL"); return !(e && e[0] == '0'); }();
   const int tail = M % 256;
-  if ((cta_pair == 2 || (auto_pair && skinny_opt_in)) && tail > 0 && tail <= 32 && M > 256 && N % 256 == 0 &&
-      block_n == 0) {
+  if ((cta_pair == 3 || (auto_pair && cta_pair == 1 && fused_tail_on && block_n == 0)) && tail > 0 && tail <= 128 &&
+      N % 256 == 0 && N / 256 <= 64) {
     const int sms = device_sm_count();
-    bool split = cta_pair == 2;
-    if (!split) {
-      const int clusters = sms / 2;
-      auto waves = [&](int rows, int bn) { return (((rows + 255) / 256) * ((N + bn - 1) / bn) + clusters - 1) / clusters; };
-      const int bn_full = pick_pair_block_n(M, N, sms), bn_main = pick_pair_block_n(M - tail, N, sms);
-      const double cost_full = waves(M, bn_full) * bn_full / (bn_full == 256 ? 1.0 : 0.88);
-      const double cost_main = waves(M - tail, bn_main) * bn_main / (bn_main == 256 ? 1.0 : 0.88);
-      split = cost_main + 0.5 * 256 < cost_full;       // the tail kernel costs about half a 256-wide tile
-    }
-    if (split) {
-      const int rows_main = M - tail;
-      int rc = gemm_bf16_pair(A, W, C, R, rows_main, N, K, lda, ldc, epilogue, pick_pair_block_n(rows_main, N, sms), stream);
-      if (rc) return rc;
-      const __nv_bfloat16* a_tail = static_cast<const __nv_bfloat16*>(A) + (size_t)rows_main * lda;
-      __nv_bfloat16* c_tail = static_cast<__nv_bfloat16*>(C) + (size_t)rows_main * ldc;
-      const __nv_bfloat16* r_tail = R ? static_cast<const __nv_bfloat16*>(R) + (size_t)rows_main * ldc : nullptr;
-      return gemm_bf16_skinny(a_tail, W, c_tail, r_tail, tail, N, K, lda, ldc, epilogue, stream);
-    }
+    const int rows_main = M - tail;
+    const int bn = block_n ? block_n : pick_pair_block_n(rows_main > 0 ? rows_main : 256, N, sms);
+    VGPT_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "vgpt_gemm_bf16: CTA-pair block_n must be 128, 192 or 256");
+    return gemm_bf16_pair(A, W, C, R, rows_main, N, K, lda, ldc, epilogue, bn, stream, tail);
+  }
+  if (cta_pair == 3) cta_pair = 1;
+  // Earlier form of the same idea, kept for A/B timing only (cta_pair == 2): the tail rows in a SEPARATE launch of the
+  // swapped-operand kernel -- it streams W a second time.
+  if (cta_pair == 2 && tail > 0 && tail <= 32 && M > 256 && N % 256 == 0 && block_n == 0) {
+    const int sms = device_sm_count();
+    const int rows_main = M - tail;
+    int rc = gemm_bf16_pair(A, W, C, R, rows_main, N, K, lda, ldc, epilogue, pick_pair_block_n(rows_main, N, sms), stream);
+    if (rc) return rc;
+    const __nv_bfloat16* a_tail = static_cast<const __nv_bfloat16*>(A) + (size_t)rows_main * lda;
+    __nv_bfloat16* c_tail = static_cast<__nv_bfloat16*>(C) + (size_t)rows_main * ldc;
+    const __nv_bfloat16* r_tail = R ? static_cast<const __nv_bfloat16*>(R) + (size_t)rows_main * ldc : nullptr;
+    return gemm_bf16_skinny(a_tail, W, c_tail, r_tail, tail, N, K, lda, ldc, epilogue, stream);
   }
   if (cta_pair == 2) cta_pair = 1;
   if (block_n == 0) block_n = cta_pair ? pick_pair_block_n(M, N, device_sm_count()) : ((N % 256 == 0) ? 256 : 128);

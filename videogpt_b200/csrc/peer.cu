@@ -60,7 +60,9 @@ int peer_close(void* p) {
 
 // ---------------------------------------------------------------------------------------------
 // Barrier across the ranks of a group.  flags.p[j] = rank j's flag words (uint32[n], peer mapped;
-// flags.p[rank] is local).  state (local): [0] = epoch counter, [1] = sticky time-out flag.
+// flags.p[rank] is local).  state (local uint32[4]): [0] = epoch counter, [1] = sticky time-out flag,
+// [2..3] = uint64 nanoseconds (globaltimer) spent inside barrier kernels so far -- waiting for the
+// slowest peer plus the NVLink flag round trip; bench.py reports it per Euler step.
 // Epochs advance by one per call on every rank, so the kernel is replayable from a CUDA graph.
 // All writes of earlier kernels in this stream (including stores into peer memory) are ordered
 // before the flag by the kernel boundary + the system-scope fence / release store.
@@ -68,7 +70,9 @@ int peer_close(void* p) {
 __global__ void peer_barrier_kernel(PeerPtrs flags, int n, int rank, uint32_t* __restrict__ state,
                                     long long timeout_cycles) {
   __shared__ uint32_t s_epoch;
+  unsigned long long t_in = 0;
   if (threadIdx.x == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_in));
     s_epoch = state[0] + 1;
     state[0] = s_epoch;
   }
@@ -92,6 +96,12 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int n, int rank, uint32_t* _
       }
     }
     __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t_out;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_out));
+    *reinterpret_cast<unsigned long long*>(state + 2) += t_out - t_in;
   }
 }
 

@@ -27,7 +27,7 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
               int ldc, int epilogue, int block_n, int cta_pair, cudaStream_t stream);
 int debug_gemm_flags();
 int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
-                   int epilogue, int block_n, cudaStream_t stream);
+                   int epilogue, int block_n, cudaStream_t stream, int tail_rows = 0);
 int pick_pair_block_n(int M, int N, int num_sms);
 int gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
                    int epilogue, float* row_ss, float eps, cudaStream_t stream);

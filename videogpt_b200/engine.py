@@ -246,15 +246,24 @@ def codes_dense_mask(spec_codes: np.ndarray, pad: int) -> np.ndarray:
     return qc[:, None] >= kc[None, :]
 
 
+SHARD_ALIGN = 128      # attention query tile; GEMM tiles are 256 rows (pairs of 128)
+
+
 def shard_rows(lo: int, hi: int, rank: int, world: int):
-    """Rows [lo, hi) dealt to ``world`` ranks as contiguous chunks (sizes differ by at most one),
-    like the reference's ``input_emb[:, r*L/P:(r+1)*L/P]`` (``LVM/model.py:459-464``) but without
-    its divisibility requirement: every row-wise op is independent of the partition and attention
-    sees all keys, so any partition gives the same numbers."""
+    """Rows [lo, hi) dealt to ``world`` ranks as contiguous chunks, like the reference's
+    ``input_emb[:, r*L/P:(r+1)*L/P]`` (``LVM/model.py:459-464``) but without its divisibility
+    requirement: every row-wise op is independent of the partition and attention sees all keys, so any
+    partition gives the same numbers.  When every rank gets at least one 128-row tile the chunk
+    boundaries are rounded down to multiples of 128 rows (the last rank takes the remainder): a shard
+    then starts on a tile boundary of the attention kernel (a 129-row shard would cost a second, almost
+    empty query tile on EVERY rank instead of on one) and the remainder rows meet the GEMM as one tail
+    (``gemm2_tcgen05.cu`` tail tiles).  Otherwise sizes differ by at most one."""
     n = hi - lo
-    a = lo + (n * rank) // world
-    b = lo + (n * (rank + 1)) // world
-    return a, b
+    if n >= SHARD_ALIGN * world:
+        cut = lambda r: n if r >= world else (n * r // world) // SHARD_ALIGN * SHARD_ALIGN
+    else:
+        cut = lambda r: (n * r) // world
+    return lo + cut(rank), lo + cut(rank + 1)
 
 
 def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int, lat_h: int,

@@ -18,9 +18,10 @@ class COMM_INFO:
         self.group = None
         self.world_size = 0
         self.rank = -1
-        # host-side rendezvous group of the same ranks (gloo) when VGPT_SP_HOST_BACKEND=gloo: the peer
-        # group's handle exchange and host barriers then launch no GPU kernels at all (an NCCL barrier
-        # is an all-reduce kernel that has to share the GPUs with spinning vgpt_peer_barrier kernels)
+        # host-side rendezvous group of the same ranks over gloo (default; VGPT_SP_HOST_BACKEND=nccl
+        # opts out): the peer group's handle exchange and host barriers then launch no GPU kernels at
+        # all (an NCCL barrier is an all-reduce kernel that has to share the GPUs with spinning
+        # vgpt_peer_barrier kernels, and NCCL's own set-up may block in the driver)
         self.host_group = None
 
 
@@ -53,7 +54,7 @@ def initialize_sequence_parallel_group(sequence_parallel_size: int):
     for i in range(world_size // sequence_parallel_size):
         ranks = list(range(i * sequence_parallel_size, (i + 1) * sequence_parallel_size))
         group = dist.new_group(ranks)
-        host_group = dist.new_group(ranks, backend="gloo") if os.getenv("VGPT_SP_HOST_BACKEND") == "gloo" else None
+        host_group = dist.new_group(ranks, backend="gloo") if os.getenv("VGPT_SP_HOST_BACKEND", "gloo") == "gloo" else None
         if rank in ranks:
             hccl_info.group, hccl_info.host_group = group, host_group
 

@@ -70,7 +70,7 @@ class PeerGroup:
         self._owned: List[int] = []
         self._imported: List[int] = []
         self._flags = self.alloc(4 * 8)
-        self._state = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._state = torch.zeros(4, dtype=torch.int32, device=self.device)   # epoch, timed out, uint64 ns in barriers
         self._flag_ptrs = self._flags.ptr_array()
 
     # ---- collective -------------------------------------------------------------------------------
@@ -159,8 +159,17 @@ class PeerGroup:
 
     def check(self):
         """Raise if any barrier timed out (a peer died); synchronises the stream."""
-        if int(self._state[1].item()) != 0:
-            raise RuntimeError("vgpt_peer_barrier timed out: a rank of the sequence-parallel group did not arrive")
+        st = self._state.cpu().tolist()
+        if st[1] != 0:
+            flags = self._flags.local[:4 * self.world].view(torch.int32).cpu().tolist()
+            raise RuntimeError(f"vgpt_peer_barrier timed out on rank {self.rank} of {self.world}: this rank is at barrier "
+                               f"epoch {st[0]}, the peers' last arrivals are {flags} (a rank of the sequence-parallel "
+                               f"group did not arrive within ~10 s; results of this clip are invalid)")
+
+    def barrier_seconds(self) -> float:
+        """Device time spent inside barrier kernels so far (waiting for the slowest peer + the NVLink flag
+        round trip); synchronises the stream."""
+        return float(self._state[2:4].view(torch.int64).item()) * 1e-9
 
     lockstep = False
 
