@@ -276,11 +276,9 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   attn_trace<VAR>(0, n_vis, kEvTableDone);
 
   if (warp >= 8) {
-    if constexpr (VAR != 0) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");    // the variants' extra state does not fit in 56 (256 x 224 + 128 x 64 = 64 K)
-    } else {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    }
+    // 256 x 224 + 128 x 56 = 64512 = the 384 x 168 registers the CTA was launched with.  (A first version gave the
+    // variants 64 here: 65536 > 64512, and setmaxnreg.inc of the softmax warps waited forever.)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 8) {
     // =================================== TMA producer ===================================
     // (whole warp runs the loop; one elected lane issues)
