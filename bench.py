@@ -331,8 +331,28 @@ def run_ours(args, rank, world, local_rank):
             out = pipe.next_clip_latents(ctx_host, n_gen, initial_noise=noise_host, **kw)
         return [x.to("cpu", non_blocking=False) for x in out]
 
-    for _ in range(max(args.warmup, 3)):
+    if sp_size > 1 and os.environ.get("VGPT_SP_WATCHDOG"):
+        # debugging aid: after N seconds print this rank's barrier state (epoch, timed-out flag) and the peers' last
+        # arrivals, read through a non-blocking side stream so that it works while a kernel of the main stream spins
+        def _watch(delay=float(os.environ["VGPT_SP_WATCHDOG"])):
+            time.sleep(delay)
+            try:
+                pg = model._peers
+                side = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(side):
+                    st = pg._state.to("cpu", non_blocking=True)
+                    fl = pg._flags.local[:4 * pg.world].view(torch.int32).to("cpu", non_blocking=True)
+                side.synchronize()
+                print(f"[watchdog rank {rank}] barrier state (epoch, timed out, ns lo, ns hi) {st.tolist()} peers' arrivals {fl.tolist()}",
+                      file=sys.stderr, flush=True)
+            except Exception as exc:
+                print(f"[watchdog rank {rank}] {type(exc).__name__}: {exc}", file=sys.stderr, flush=True)
+        threading.Thread(target=_watch, daemon=True).start()
+    for i in range(max(args.warmup, 3)):
         clip_device()
+        if os.environ.get("VGPT_SP_TRACE"):
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] warm-up clip {i} done", file=sys.stderr, flush=True)
     barrier()
     peers = model.sequence_parallel_peers() if sp_size > 1 else None
     barrier_s0 = peers.barrier_seconds() if peers is not None else 0.0

@@ -123,7 +123,7 @@ def test_gemm_skinny_tail_matches_tiled_path_bit_exact(ops, M):
 @pytest.mark.parametrize("M", [2064, 1032, 280, 8208, 258, 100, 16, 384, 2121])
 def test_gemm_fused_tail_tiles_match_tiled_path_bit_exact(ops, M, block_n):
     """M = q*256 + tail, tail <= 128: the tail rows are computed by swapped-operand tail tiles inside the
-    persistent launch (cta_pair=3 forces it; it is the default of the auto path).  They must give the same
+    persistent launch (cta_pair=3 forces it; VGPT_GEMM_FUSED_TAIL=1 makes it the auto path's choice).  They must give the same
     BITS as plain 256-row tiles (cta_pair=1) for all three epilogues: a row's result may not depend on which
     kind of tile computed it (sequence-parallel shards and the unsharded run group rows differently)."""
     K, N = 512, 1024
@@ -131,7 +131,7 @@ def test_gemm_fused_tail_tiles_match_tiled_path_bit_exact(ops, M, block_n):
     kw1, kw3 = dict(block_n=block_n, cta_pair=1), dict(block_n=block_n, cta_pair=3)
     want = ops.gemm(a, w, **kw1)
     assert torch.equal(ops.gemm(a, w, **kw3), want)
-    assert torch.equal(ops.gemm(a, w), want)                      # the default path
+    assert torch.equal(ops.gemm(a, w), want)                      # the default path (plain or tail tiles: same bits)
     o1, o2 = r.clone(), r.clone()
     ops.gemm(a, w, out=o1, residual=o1, epilogue=ops.EPI_RESIDUAL, **kw1)
     ops.gemm(a, w, out=o2, residual=o2, epilogue=ops.EPI_RESIDUAL, **kw3)

@@ -1,13 +1,26 @@
-"""Parity at BASELINE.json's FULL size (configs[1]: Phi-3-mini-class backbone, 4 + 4 frames 256x256,
-CFG) against the oracle on the same device, through the same measurement as tools/parity_report.py
-(profiles/r01a_parity.json): per-step velocity of ours vs the bf16 oracle, ours vs the fp32 oracle,
-and the bf16 oracle's own distance to fp32 (the noise floor of the reference's path).
+"""Parity at BASELINE.json's FULL size and FULL length (configs[1]: Phi-3-mini-class backbone, 4 + 4 frames
+256x256, CFG 1.5, 50 Euler steps) against the oracle on the same device, measured by tools/parity_floor.py
+(committed run: profiles/r02a_parity_floor.json).
 
-At this size two independent bf16 evaluations cannot agree to 1e-2 -- the reference against itself
-included (floor 2.7e-2 in x1 mode at step 0, 4.3e-2 in v mode) -- so the gate is
-BASELINE's 1e-2 wherever the floor allows it and 1.3 x the floor elsewhere, plus: ours is as close to
-fp32 as the reference's own bf16 path is (1.15 x floor), and the final-latent cosine holds.
-Sorts last: a full-size run takes a minute or two."""
+BASELINE states: per-step velocity rel-L2 <= 1e-2 (bf16) against the reference's own PyTorch path, final-latent
+cosine >= 0.999.  What is measured here, every run:
+
+  ours  the CUDA path                         A  oracle bf16, GPU eager, default SDPA backend (the gate's reference)
+  B     the SAME oracle, bf16, SDPA forced to the MATH backend          F  oracle fp32 (ground truth)
+
+* the bf16-vs-bf16 floor is MEASURED, not inferred: B vs A -- two evaluations of the reference's own bf16 path
+  that differ only in the attention backend -- disagree by 2.7e-2 (step 0) ... 8.9e-1 (step 49) in x1 mode and
+  4.3e-2 in v mode (the host-CPU evaluation of the same oracle: 2.7e-2 at steps 0 and 1).  The stated 1e-2
+  cannot be met at this size by the reference against itself; it is asserted wherever it can hold (reduced
+  size, tests/test_model_gpu.py);
+* gate 1 (per step): ours-vs-A <= 1.10 x (B-vs-A): the CUDA path is no further from the reference's bf16 path
+  than that path is from itself (measured ratio 0.98 ... 1.02 over all 50 steps);
+* gate 2 (per step): ours-vs-F <= 1.10 x (A-vs-F): the CUDA path is as close to fp32 as the reference's bf16 path;
+* gate 3: final-latent cosine ours-vs-A >= the measured B-vs-A cosine - 1e-4 (x1: 0.99911 vs 0.99912; the stated
+  0.999 holds in both modes), and ours-vs-F >= A-vs-F - 1e-4;
+* gate 4 (per decoder layer, first forward): hidden-state error of ours vs F <= 1.05 x that of A vs F at EVERY
+  layer, generated rows and context rows -- a kernel regression cannot hide inside the end-to-end floor.
+Sorts last: the 50-step fp32 oracle takes half a minute per mode."""
 import os
 import sys
 
@@ -16,21 +29,38 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STEPS = 4
+STEPS = 50
+COS_TOL = 0.999
 
 
-@pytest.mark.parametrize("pt", ["x1", "v"])
-def test_full_size_cfg2_velocity_and_final_latents_match_the_oracle(pt):
+@pytest.fixture(scope="module")
+def case():
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import parity_report
+    import parity_floor
     from videogpt_b200 import synth
-    r = parity_report.run(synth.FULL_SIZE, 4, 4, 256, 256, STEPS, pt)
+    return parity_floor, parity_floor.Case(synth.FULL_SIZE, 4, 4, 256, 256)
+
+
+@pytest.mark.timeout(900)
+def test_full_size_per_layer_hidden_state_error_is_the_reference_bf16_error(case):
+    pf, c = case
+    pl = pf.per_layer(c)
+    for name in ("gen", "ctx"):
+        for i, (a, b) in enumerate(zip(pl[f"{name}_ours_vs_F"], pl[f"{name}_A_vs_F"])):
+            assert a <= 1.05 * b + 1e-5, f"{name} rows, layer {i}: ours vs fp32 {a:.3e}, reference bf16 vs fp32 {b:.3e}"
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("pt", ["x1", "v"])
+def test_full_size_cfg2_50_steps_velocity_and_final_latents(case, pt):
+    pf, c = case
+    r = pf.trajectories(c, STEPS, pt, cpu_steps=0)
     for i in range(STEPS):
-        floor = r["velocity_rel_l2_oracle_bf16_vs_fp32"][i]
-        err = r["velocity_rel_l2_ours_vs_oracle_bf16"][i]
-        err32 = r["velocity_rel_l2_ours_vs_oracle_fp32"][i]
-        assert err <= max(1e-2, 1.3 * floor), f"step {i}: velocity rel-L2 vs bf16 oracle {err:.3e} (floor {floor:.3e})"
-        assert err32 <= 1.15 * floor + 1e-3, f"step {i}: vs fp32 oracle {err32:.3e} (reference bf16 {floor:.3e})"
-    cos, cos_floor = r["final_cosine_ours_vs_oracle_bf16"], r["final_cosine_oracle_bf16_vs_fp32"]
-    assert cos >= min(0.999, cos_floor - 2e-4), (cos, cos_floor)
-    assert r["final_cosine_ours_vs_oracle_fp32"] >= cos_floor - 2e-4
+        e_a, floor_bb = r["vel_ours_vs_A"][i], r["vel_B_vs_A"][i]
+        e_f, floor_f = r["vel_ours_vs_F"][i], r["vel_A_vs_F"][i]
+        assert e_a <= max(1e-2, 1.10 * floor_bb), f"step {i}: ours vs bf16 oracle {e_a:.3e}, bf16-vs-bf16 floor {floor_bb:.3e}"
+        assert e_f <= 1.10 * floor_f + 1e-3, f"step {i}: ours vs fp32 {e_f:.3e}, reference bf16 vs fp32 {floor_f:.3e}"
+    fc = r["final_cos"]
+    assert fc["ours_vs_A"] >= min(COS_TOL, fc["B_vs_A"]) - 1e-4, fc
+    assert fc["ours_vs_A"] >= COS_TOL, fc          # holds at this size in both modes (x1: 0.99911)
+    assert fc["ours_vs_F"] >= fc["A_vs_F"] - 1e-4, fc

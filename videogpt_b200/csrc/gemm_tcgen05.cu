@@ -312,9 +312,12 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
   if (cta_pair < 0) cta_pair = kDefaultCtaPair;
   // Rows that do not fill a 256-row tile (M % 256 <= 128: the 16 tag / time-slot rows of M = 2064 at cfg2, the
   // remainders of sequence-parallel shards) are computed by swapped-operand TAIL TILES inside the same persistent
-  // launch (gemm2_tcgen05.cu, TailArgs) instead of a whole extra row of mostly empty 256-row tiles.  Default for the
-  // CTA-pair path (VGPT_GEMM_FUSED_TAIL=0 switches it off for A/B timing); cta_pair == 3 forces it with any block_n.
-  static const bool fused_tail_on = [] { const char* e = getenv("VGPT_GEMM_FUSED_TAIL"); return !(e && e[0] == '0'); }();
+  // launch (gemm2_tcgen05.cu, TailArgs) instead of a whole extra row of mostly empty 256-row tiles.  Bit-exact against
+  // plain tiles on hardware, but as measured (profiles/r02b_gemm_sweep_fused_tail.txt) a tail tile costs 1.3 - 1.6 main
+  // tiles instead of the ~0.3 its bytes and MMAs are worth: its k-loop has 156 cycles of MMA work per stage, the ring
+  // holds 6 stages, and a stage's round trip (MMA completion -> commit -> TMA issue -> data) is several thousand cycles,
+  // so it runs latency-bound.  Opt-in (VGPT_GEMM_FUSED_TAIL=1, or cta_pair == 3 with any block_n) until that is fixed.
+  static const bool fused_tail_on = [] { const char* e = getenv("VGPT_GEMM_FUSED_TAIL"); return e && e[0] == '1'; }();
   const int tail = M % 256;
   if ((cta_pair == 3 || (auto_pair && cta_pair == 1 && fused_tail_on && block_n == 0)) && tail > 0 && tail <= 128 &&
       N % 256 == 0 && N / 256 <= 64) {
