@@ -43,29 +43,13 @@ const char* vgpt_last_error(void);
  * down_proj of transformers' Phi3MLP.  epilogue: VGPT_EPI_STORE; VGPT_EPI_RESIDUAL
  * (C = bf16(A W^T) + R, R may alias C: the in-place residual stream of Phi3DecoderLayer);
  * VGPT_EPI_SWIGLU (W packed by vgpt_pack_gate_up, C[M,N/2] = up * silu(gate)).
- * K % 64 == 0, N % 64 == 0.  cta_pair 1 = CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles,
- * block_n 128/192/256), 0 = single CTAs (128 x block_n, block_n 128/256), -1 = tuned default,
- * 2 = CTA pairs + the swapped-operand skinny kernel for an M % 256 <= 32 tail (EXPERIMENTAL, not yet
- * validated on hardware; needs N % 256 == 0 and block_n 0; the tuned default only uses it when
- * VGPT_GEMM_SKINNY_TAIL=1 is set); block_n 0 = tuned default. */
+ * K % 64 == 0, N % 64 == 0.  CTA pairs (tcgen05 cta_group::2) compute 256 x block_n tiles, block_n 128 / 192 / 256,
+ * 0 = tuned default.  tail_mode: when M = 256 q + t with q >= 1 and 0 < t <= 32, the t tail rows can be computed
+ * inside the k-loop of the last full tile row (operands swapped, from the W k-blocks already in shared memory)
+ * instead of by a (q+1)-th, almost empty row of tiles: 3 = do that, 1 = plain tiles only, -1 = tuned default.
+ * A row gets the same bits either way. */
 int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                   int ldc, int epilogue, int block_n, int cta_pair, void* stream);
-
-/* EXPERIMENTAL (never run on hardware; opt-in through VGPT_FOLD_RMSNORM=1 in the engine): Phi3RMSNorm
- * folded into the projections around it -- (x * rstd * w) W^T == rstd * (x (W diag(w))^T), so the
- * rmsnorm kernel and its [M, hidden] round trip disappear from Phi3DecoderLayer.  epilogue
- * VGPT_EPI_RESIDUAL_SS (3): the residual epilogue of o_proj / down_proj also writes, per row and per N tile,
- * the sum of squares of the bf16 values it stores into row_ss[M][VGPT_NORM_PARTS] (fixed slots, no atomics);
- * VGPT_EPI_STORE_SCALED (4) / VGPT_EPI_SWIGLU_SCALED (5): qkv_proj / gate_up_proj on the RAW hidden rows with
- * weights from vgpt_fold_norm_weight, every accumulator row scaled by rsqrt(sum(row_ss[row]) / K + eps)
- * before the bf16 rounding.  Rounding points differ from the reference's (no bf16 rounding of the
- * normalised activations).  CTA pairs only. */
-#define VGPT_NORM_PARTS 32
-int vgpt_gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                        int ldc, int epilogue, float* row_ss, float eps, void* stream);
-
-/* out[n][k] = bf16(w[n][k] * ln[k]): projection weight [N,K] with the preceding RMSNorm weight [K] folded in. */
-int vgpt_fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, void* stream);
+                   int ldc, int epilogue, int block_n, int tail_mode, void* stream);
 
 /* gate_up_proj.weight [2I,K] ([gate | up] rows, Phi3MLP chunk(2)) -> block-interleaved rows. */
 int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream);
@@ -180,25 +164,6 @@ int vgpt_cfg_combine(void* pred, int half_numel, float guidance, void* stream);
 /* out[q][k] = q_code[q] >= k_code[k] (uint8): the reference's dense mask
  * (LVM/processor.py:682-731) from the codes the attention kernel consumes. */
 int vgpt_mask_from_codes(const int32_t* q_code, const int32_t* k_code, void* out, int Lq, int Lk,
-                         void* stream);
-
-/* Test hook: run k_steps tcgen05.mma on raw shared-memory images with caller-built descriptors. */
-int vgpt_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
-                          uint64_t a_desc_base, uint64_t b_desc_base, uint32_t idesc, int k_steps,
-                          uint32_t a_step_bytes, uint32_t b_step_bytes, float* d_out, int n_cols,
-                          void* stream);
-
-/* Test hook: same with the A operand in tensor memory (a_words[128][a_cols] packed bf16x2). */
-int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes,
-                             uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t b_step_bytes,
-                             float* d_out, int n_cols, void* stream);
-
-/* Test / tuning hook: cycles per back-to-back tcgen05.mma (M = 128, cta_group::1, bf16) of width N.
- * mode 0 = SS K-major SW128, 1 = SS K-major SW64, 2 = TS + MN-major SW128 B, 3 = TS + MN-major SW64 B,
- * 4 = CTA pairs (cta_group::2, M = 256, SS K-major SW128; `ctas` = clusters; not yet run on hardware);
- * n_acc = 1 dependent chain, 2 alternating accumulators; commit_every = 0 / 1 / 2 / 4 / 8: a tcgen05.commit
- * after every that many MMAs; out[ctas] = cycles per MMA per CTA. */
-int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out,
                          void* stream);
 
 /* Diagnostic: with VGPT_ATTN_VARIANT=8 the attention kernel's CTA (0, 0, 0) records a clock64 time stamp

@@ -19,8 +19,6 @@ import torch
 import torch.nn.functional as F
 
 EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2
-EPI_RESIDUAL_SS, EPI_STORE_SCALED, EPI_SWIGLU_SCALED = 3, 4, 5
-NORM_PARTS = 32
 ROW_TOKEN, ROW_TIME, ROW_NOISY_PATCH, ROW_CONTEXT_PATCH = 0, 1, 2, 3
 PAGE_TOKENS = 128
 ATTN_KV_TILE = 64
@@ -40,7 +38,7 @@ def pack_gate_up(w):
     return w.clone()
 
 
-def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int = 0, cta_pair: int = -1):
+def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int = 0, tail_mode: int = -1):
     _log("gemm")
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
     y = a @ w.t()
@@ -57,34 +55,6 @@ def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int 
     assert out.shape == y.shape
     out.copy_(y)
     return out
-
-
-def gemm_norm(a, w, out, row_ss, eps: float, epilogue: int, residual=None):
-    """RMSNorm folded into the GEMMs: 3 = residual + per-row sums of squares (split over the slots the way
-    a 192-wide tiling would, the rest zero), 4 / 5 = rows scaled by rstd from those sums."""
-    _log("gemm_norm")
-    M, K = a.shape
-    y = a @ w.t()
-    if epilogue == EPI_RESIDUAL_SS:
-        y = y + residual
-        out.copy_(y)
-        o = out.float()
-        row_ss[:M].zero_()
-        for p, c0 in enumerate(range(0, o.shape[1], 192)):
-            row_ss[:M, p] = o[:, c0:c0 + 192].pow(2).sum(1)
-        return out
-    rstd = torch.rsqrt(row_ss[:M].sum(1) / K + eps)[:, None].to(y.dtype)
-    y = y * rstd
-    if epilogue == EPI_SWIGLU_SCALED:
-        gate, up = y.chunk(2, dim=-1)
-        y = up * F.silu(gate)
-    out.copy_(y)
-    return out
-
-
-def fold_norm_weight(w, ln):
-    _log("fold_norm_weight")
-    return (w.float() * ln.float()[None, :]).to(w.dtype)
 
 
 def rmsnorm(x, weight, eps: float, out=None):

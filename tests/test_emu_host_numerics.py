@@ -511,37 +511,6 @@ def test_rollout_window_smaller_than_two_clips_skips_frames_that_are_never_visib
     assert ro.prefilled_frames == n0 + 1 + 1            # per later round only the one frame inside the window
 
 
-@pytest.mark.parametrize("pt", ["x1", "v"])
-def test_rmsnorm_folded_into_the_gemms_is_the_same_function(emu, pt, monkeypatch):
-    """VGPT_FOLD_RMSNORM=1 (experimental): (x rstd w) W^T == rstd (x (W diag w)^T).  The engine's
-    folded layer loop -- sums of squares handed from the residual epilogues to the next projection,
-    folded weights, layer 0 and the final norm on the plain path -- reproduces the oracle like the
-    plain loop does (fp32), and launches no rmsnorm inside the layers."""
-    from videogpt_b200 import LVMScheduler
-    monkeypatch.setenv("VGPT_FOLD_RMSNORM", "1")
-    m, sd = _model()
-    with torch.no_grad():                      # make the norm weights non-trivial
-        for k in list(sd):
-            if k.endswith("layernorm.weight") or k == "llm.norm.weight":
-                sd[k] = torch.empty_like(sd[k]).uniform_(0.5, 1.5, generator=torch.Generator().manual_seed(len(k)))
-    m.load_state_dict(sd)
-    m.float().eval()
-    mk, z0 = _mk(3, 2, 64, 96)
-    with torch.no_grad():
-        want = so.euler_sample([x.clone() for x in z0] * 2,
-                               lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
-                               mk, num_steps=3, prediction_type=pt)
-    emu.calls.clear()
-    got = LVMScheduler(num_steps=3)([x.clone() for x in z0] * 2, m.frame_block_forward_with_cfg, mk,
-                                    use_kv_cache=False, prediction_type=pt)
-    assert m._engine.fold_norm
-    assert _maxerr(got, want) < 5 * TOL
-    L = synth.REDUCED.num_hidden_layers
-    # per predict: layer 0's input norm + the final norm; per prefill: layer 0's input norm (+ ln2 never: folded)
-    assert emu.calls.count("rmsnorm") == 3 * 2 + 1
-    assert emu.calls.count("gemm_norm") == 3 * (4 * L - 1) + (4 * (L - 1))
-
-
 def test_model_helper_methods_match_the_oracle(emu):
     """The reference model's public helpers (LVM/model.py:255-327) on the drop-in: ``cropped_pos_embed``
     and ``unpatchify`` are index arithmetic; ``patch_multiple_resolutions`` goes through the assembly

@@ -43,10 +43,10 @@ def _rel(a, b):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (16, 512, 3072), (2064, 1536, 512),
                                    (300, 3072, 1024), (1032, 9216, 3072)])
-@pytest.mark.parametrize("block_n,cta_pair", [(256, 0), (192, 0), (128, 0), (256, 1), (192, 1), (128, 1)])
-def test_gemm_store(ops, M, N, K, block_n, cta_pair):
+@pytest.mark.parametrize("block_n,tail_mode", [(256, 1), (192, 1), (128, 1), (0, -1)])
+def test_gemm_store(ops, M, N, K, block_n, tail_mode):
     a, w = _rand((M, K), 1), _rand((N, K), 2, 0.05)
-    c = ops.gemm(a, w, block_n=block_n, cta_pair=cta_pair)
+    c = ops.gemm(a, w, block_n=block_n, tail_mode=tail_mode)
     ref = a.float() @ w.float().t()
     # fp32 accumulation of exact bf16 products, one final rounding: <= 2^-8 of the row scale
     err = (c.float() - ref).abs().max().item()
@@ -54,33 +54,33 @@ def test_gemm_store(ops, M, N, K, block_n, cta_pair):
     assert _rel(c, ref) < 4e-3
 
 
-@pytest.mark.parametrize("block_n,cta_pair", [(256, 0), (192, 0), (256, 1), (192, 1), (128, 1)])
-def test_gemm_identity_layout(ops, block_n, cta_pair):
+@pytest.mark.parametrize("block_n,tail_mode", [(256, 1), (192, 1), (128, 1)])
+def test_gemm_identity_layout(ops, block_n, tail_mode):
     """W = I picks out columns of A exactly: catches any operand layout / swizzle / pair-split mix-up."""
     M, K = 520, 384
     a = _rand((M, K), 3)
     w = torch.eye(K, device=DEV, dtype=BF)
-    c = ops.gemm(a, w, block_n=block_n, cta_pair=cta_pair)
+    c = ops.gemm(a, w, block_n=block_n, tail_mode=tail_mode)
     assert torch.equal(c, a)
     perm = torch.randperm(K, generator=torch.Generator().manual_seed(0)).to(DEV)
-    c = ops.gemm(a, w[perm], block_n=block_n, cta_pair=cta_pair)
+    c = ops.gemm(a, w[perm], block_n=block_n, tail_mode=tail_mode)
     assert torch.equal(c, a[:, perm])
 
 
-@pytest.mark.parametrize("cta_pair,block_n", [(0, 0), (1, 256), (1, 192)])
+@pytest.mark.parametrize("tail_mode,block_n", [(-1, 0), (1, 256), (1, 192)])
 @pytest.mark.parametrize("M,N,K", [(2064, 512, 1024), (130, 3072, 8192)])
-def test_gemm_residual_in_place(ops, M, N, K, cta_pair, block_n):
+def test_gemm_residual_in_place(ops, M, N, K, tail_mode, block_n):
     a, w, r = _rand((M, K), 4), _rand((N, K), 5, 0.03), _rand((M, N), 6)
     want = (a.float() @ w.float().t()).to(BF).float() + r.float()     # bf16(o_proj) + residual, rounded
     out = r.clone()
-    ops.gemm(a, w, out=out, residual=out, epilogue=ops.EPI_RESIDUAL, block_n=block_n, cta_pair=cta_pair)
+    ops.gemm(a, w, out=out, residual=out, epilogue=ops.EPI_RESIDUAL, block_n=block_n, tail_mode=tail_mode)
     assert (out.float() - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
     assert _rel(out, want) < 4e-3
 
 
-@pytest.mark.parametrize("cta_pair,block_n", [(0, 0), (0, 192), (1, 256), (1, 192)])
+@pytest.mark.parametrize("tail_mode,block_n", [(-1, 0), (1, 256), (1, 192)])
 @pytest.mark.parametrize("M,I,K", [(2064, 1024, 512), (257, 8192, 3072)])
-def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K, cta_pair, block_n):
+def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K, tail_mode, block_n):
     """gate_up GEMM + SwiGLU epilogue on the packed weight == Phi3MLP's chunk / silu / mul."""
     x, wgu = _rand((M, K), 7), _rand((2 * I, K), 8, 0.03)
     packed = ops.pack_gate_up(wgu)
@@ -88,7 +88,7 @@ def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K, cta_pair, block_n):
     blk = torch.arange(2 * I, device=DEV).view(-1, 64)
     src = torch.where(blk % 64 < 32, (blk // 64) * 32 + blk % 64, I + (blk // 64) * 32 + blk % 64 - 32)
     assert torch.equal(packed, wgu[src.view(-1)])
-    h = ops.gemm(x, packed, epilogue=ops.EPI_SWIGLU, block_n=block_n, cta_pair=cta_pair)
+    h = ops.gemm(x, packed, epilogue=ops.EPI_SWIGLU, block_n=block_n, tail_mode=tail_mode)
     gu = (x.float() @ wgu.float().t()).to(BF)
     gate, up = gu.chunk(2, dim=-1)
     want = (up * torch.nn.functional.silu(gate)).float()
@@ -96,42 +96,22 @@ def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K, cta_pair, block_n):
     assert _rel(h, want) < 6e-3
 
 
-@pytest.mark.skipif(os.environ.get("VGPT_TEST_EXPERIMENTAL") != "1",
-                    reason="skinny tail kernel: written after the round's GPU budget was spent, never run on "
-                           "hardware; set VGPT_TEST_EXPERIMENTAL=1 to validate it")
-@pytest.mark.parametrize("M", [2064, 1032, 280, 8208])
-def test_gemm_skinny_tail_matches_tiled_path_bit_exact(ops, M):
-    """M = q*256 + tail (tail <= 32): the swapped-operand tail kernel (cta_pair=2) must give the same
-    BITS as the 256-row tiles for all three epilogues -- row results may not depend on which kernel
-    computed them (sequence-parallel shards and the unsharded run group rows differently)."""
-    K, N = 512, 1024
-    a, w, r = _rand((M, K), 21), _rand((N, K), 22, 0.05), _rand((M, N), 23)
-    assert torch.equal(ops.gemm(a, w, cta_pair=2), ops.gemm(a, w, cta_pair=1))
-    o1, o2 = r.clone(), r.clone()
-    ops.gemm(a, w, out=o1, residual=o1, epilogue=ops.EPI_RESIDUAL, cta_pair=1)
-    ops.gemm(a, w, out=o2, residual=o2, epilogue=ops.EPI_RESIDUAL, cta_pair=2)
-    assert torch.equal(o1, o2)
-    packed = ops.pack_gate_up(w)
-    assert torch.equal(ops.gemm(a, packed, epilogue=ops.EPI_SWIGLU, cta_pair=2),
-                       ops.gemm(a, packed, epilogue=ops.EPI_SWIGLU, cta_pair=1))
-    ref = a.float() @ w.float().t()
-    assert _rel(ops.gemm(a, w, cta_pair=2), ref) < 4e-3
-
-
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("block_n", [0, 256, 192])
-@pytest.mark.parametrize("M", [2064, 1032, 280, 8208, 258, 100, 16, 384, 2121])
-def test_gemm_fused_tail_tiles_match_tiled_path_bit_exact(ops, M, block_n):
-    """M = q*256 + tail, tail <= 128: the tail rows are computed by swapped-operand tail tiles inside the
-    persistent launch (cta_pair=3 forces it; VGPT_GEMM_FUSED_TAIL=1 makes it the auto path's choice).  They must give the same
-    BITS as plain 256-row tiles (cta_pair=1) for all three epilogues: a row's result may not depend on which
-    kind of tile computed it (sequence-parallel shards and the unsharded run group rows differently)."""
+@pytest.mark.parametrize("block_n", [0, 256, 192, 128])
+@pytest.mark.parametrize("M", [2064, 1032, 280, 8208, 258, 272, 100, 16, 384, 2121, 544])
+def test_gemm_tail_rows_in_the_k_loop_match_plain_tiles_bit_exact(ops, M, block_n):
+    """M = q*256 + tail with q >= 1, tail <= 32: the tail rows are computed inside the k-loop of the last full
+    tile row (special pieces, operands swapped; tail_mode=3 forces it wherever the shape allows, and it is the
+    default of the auto path).  They -- and the rows of the narrower special pieces -- must get the same BITS
+    as from plain 256-row tiles (tail_mode=1), for all three epilogues: a row's result may not depend on which
+    kind of tile computed it (sequence-parallel shards and the unsharded run group rows differently).  Shapes
+    the special path does not take (tail > 32, M < 256) fall back to plain tiles and trivially agree."""
     K, N = 512, 1024
     a, w, r = _rand((M, K), 21), _rand((N, K), 22, 0.05), _rand((M, N), 23)
-    kw1, kw3 = dict(block_n=block_n, cta_pair=1), dict(block_n=block_n, cta_pair=3)
+    kw1, kw3 = dict(block_n=block_n, tail_mode=1), dict(block_n=block_n, tail_mode=3)
     want = ops.gemm(a, w, **kw1)
     assert torch.equal(ops.gemm(a, w, **kw3), want)
-    assert torch.equal(ops.gemm(a, w), want)                      # the default path (plain or tail tiles: same bits)
+    assert torch.equal(ops.gemm(a, w), want)                      # the default path
     o1, o2 = r.clone(), r.clone()
     ops.gemm(a, w, out=o1, residual=o1, epilogue=ops.EPI_RESIDUAL, **kw1)
     ops.gemm(a, w, out=o2, residual=o2, epilogue=ops.EPI_RESIDUAL, **kw3)
@@ -143,9 +123,10 @@ def test_gemm_fused_tail_tiles_match_tiled_path_bit_exact(ops, M, block_n):
 
 
 @pytest.mark.timeout(300)
-def test_gemm_fused_tail_full_size_projections(ops):
+def test_gemm_tail_in_loop_full_size_projections(ops):
     """The four projection shapes of the model at M = 2064 (cfg2) and at a sequence-parallel shard (M = 1040):
-    fused tail tiles vs plain tiles, bit for bit; K = 8192 exercises the long k loop of a tail tile."""
+    special pieces with the tail in the k-loop vs plain tiles, bit for bit (N = 9216 -> 41 pieces of 224 + one of 32;
+    N = 16384 SwiGLU -> 85 of 192 + one of 64; N = 3072 -> 16 of 192)."""
     for M in (2064, 1040):
         for N, K, epi in ((9216, 3072, ops.EPI_STORE), (3072, 3072, ops.EPI_RESIDUAL), (16384, 3072, ops.EPI_SWIGLU),
                           (3072, 8192, ops.EPI_RESIDUAL)):
@@ -154,9 +135,9 @@ def test_gemm_fused_tail_full_size_projections(ops):
             r = _rand((M, n_out), 33)
             o1, o2 = r.clone(), r.clone()
             res = dict(residual=o1) if epi == ops.EPI_RESIDUAL else {}
-            ops.gemm(a, w, out=o1, epilogue=epi, cta_pair=1, **res)
+            ops.gemm(a, w, out=o1, epilogue=epi, tail_mode=1, **res)
             res = dict(residual=o2) if epi == ops.EPI_RESIDUAL else {}
-            ops.gemm(a, w, out=o2, epilogue=epi, cta_pair=3, **res)
+            ops.gemm(a, w, out=o2, epilogue=epi, tail_mode=3, **res)
             assert torch.equal(o1, o2), (M, N, K, epi)
 
 
@@ -449,48 +430,3 @@ def test_attention_cfg3_geometry(ops, phase):
     """BASELINE configs[2] at full frame size: 32 context frames of 258 tokens + 4 generated, 73 pages per
     sequence (the conditional CTA of a generated query pair walks 73 KV tiles, a context CTA up to 65)."""
     _attention_case(ops, 32, 4, 256, 256, 1, 96, phase, 450)
-
-
-# ---------------------------------------------------------------------------------------------
-# experimental attention variants (VGPT_ATTN_VARIANT; csrc/attention_pair_tcgen05.cu kVar*)
-# ---------------------------------------------------------------------------------------------
-def _attention_out(ops, n_ctx, n_gen, H_px, W_px, heads, D, phase, seed):
-    from videogpt_b200 import engine as eng
-    d = po.frame_block_inputs(n_ctx, n_gen, H_px, W_px, True, 1)
-    specs, n_lat, n_c = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
-                                              d["denoise_image_sizes"], d["time_emb_inx"])
-    plan = eng.build_plan(specs, n_lat, n_c, H_px // 8, W_px // 8, DEV)
-    k_pool = _rand((plan.total_pages, heads, 128, D), seed + 1)
-    v_pool = _rand((plan.total_pages, heads, 128, D), seed + 2)
-    ph = plan.prefix if phase == "prefix" else plan.step
-    q = _rand((ph.rows, 3 * heads * D), seed + 3)
-    out = torch.zeros(ph.rows, heads * D, device=DEV, dtype=BF)
-    ops.attention(q[:, :heads * D], out, k_pool, v_pool, plan.page_table, ph.seqs, ph.max_q_rows, ph.q_code,
-                  plan.k_code, plan.k_tile_minmax, heads, D, 1.0 / math.sqrt(D))
-    torch.cuda.synchronize()
-    return out
-
-
-@pytest.mark.skipif(os.environ.get("VGPT_TEST_EXPERIMENTAL") != "1",
-                    reason="attention variants: written after the round's GPU budget was spent, never run on "
-                           "hardware; set VGPT_TEST_EXPERIMENTAL=1 to validate them")
-@pytest.mark.parametrize("geom", [(4, 4, 256, 256, 4), (3, 5, 176, 320, 2), (2, 2, 64, 96, 2), (32, 4, 64, 64, 2)])
-@pytest.mark.parametrize("phase", ["step", "prefix"])
-def test_attention_variants_against_the_validated_kernel(ops, geom, phase, monkeypatch):
-    """Variant 1 (ragged last KV tile issued with N = ceil16(tail) and tail/16 k-steps) only skips
-    products with zeros: BIT-identical to variant 0.  Variant 2 (every fourth exponential by a
-    degree-3 polynomial on the FMA pipe, relative error 1e-4 before the bf16 rounding of P): within
-    one bf16 ulp of the output scale of variant 0, and still inside the SDPA tolerance."""
-    n_ctx, n_gen, H_px, W_px, heads = geom
-    outs = {}
-    for var in (0, 1, 2, 3, 4, 5):
-        monkeypatch.setenv("VGPT_ATTN_VARIANT", str(var))
-        outs[var] = _attention_out(ops, n_ctx, n_gen, H_px, W_px, heads, 96, phase, 500)
-    monkeypatch.setenv("VGPT_ATTN_VARIANT", "0")
-    assert torch.isfinite(outs[0].float()).all()
-    assert torch.equal(outs[1], outs[0]), "trimmed ragged tile changed bits"
-    assert torch.equal(outs[3], outs[2]) and torch.equal(outs[5], outs[4]), "trimmed ragged tile changed bits (with the polynomial)"
-    scale = outs[0].float().abs().max().item()
-    for var in (2, 4):
-        assert (outs[var].float() - outs[0].float()).abs().max().item() <= 2.0 ** -7 * scale
-        assert _rel(outs[var].float(), outs[0].float()) < 2e-3

@@ -241,34 +241,3 @@ def test_replace_attention_operator_seam():
     bad = mo.additive_mask(anti[None].expand(B, L, L), BF)
     with pytest.raises(ValueError):
         holder.attn(x, attention_mask=bad, position_ids=pos)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("VGPT_TEST_EXPERIMENTAL") != "1",
-                    reason="RMSNorm folded into the GEMMs: written after the round's GPU budget was spent, never "
-                           "run on hardware; set VGPT_TEST_EXPERIMENTAL=1 to validate it")
-@pytest.mark.parametrize("pt", ["x1", "v"])
-def test_rmsnorm_folding_stays_inside_the_parity_gates(pt, monkeypatch):
-    """VGPT_FOLD_RMSNORM=1: same function, different rounding points (no bf16 rounding of the normalised
-    activations, norm weight rounded into the projection weight).  Gate: the folded path must pass
-    the SAME per-step velocity / final-latent gates against the bf16 oracle as the plain path, and
-    the two must agree with each other to the bf16 noise floor."""
-    n_ctx, n_gen, H, W, steps = 4, 4, 256, 256, 4
-    dims = synth.REDUCED
-    mk, z0 = _inputs(n_ctx, n_gen, H, W, DEV, BF)
-    model, sd = _build(dims)
-    plain, plain_vel = _cuda_run(model, mk, z0, steps, pt)
-    monkeypatch.setenv("VGPT_FOLD_RMSNORM", "1")
-    folded_model, _ = _build(dims)
-    folded, folded_vel = _cuda_run(folded_model, mk, z0, steps, pt)
-    assert folded_model.engine().fold_norm
-    want, want_vel = _oracle_run(sd, dims, mk, z0, steps, pt, BF)
-    _, alt_vel = _oracle_run(sd, dims, mk, z0, steps, pt, BF, sdpa_backend="MATH")
-    mk32, z32 = _inputs(n_ctx, n_gen, H, W, DEV, torch.float32)
-    _, true_vel = _oracle_run(sd, dims, mk32, z32, steps, pt, torch.float32)
-    for i in range(steps):
-        v_ref, v_true = torch.cat(want_vel[i][:n_gen], 0), torch.cat(true_vel[i][:n_gen], 0)
-        floor = rel_l2(v_ref, v_true)
-        assert rel_l2(folded_vel[i], v_ref) <= _gate(floor), f"step {i}"
-        assert rel_l2(folded_vel[i], v_true) <= 1.15 * floor + 1e-3, f"step {i}"
-        assert rel_l2(folded_vel[i], plain_vel[i]) <= _gate(floor), f"step {i}: folded vs plain"
-    assert cosine(torch.cat(folded[:n_gen], 0), torch.cat(want[:n_gen], 0)) >= COS_TOL

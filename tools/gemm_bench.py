@@ -20,15 +20,12 @@ for name, (N, K, epi) in shapes.items():
     a = torch.randn(M, K, device=dev).to(torch.bfloat16)
     n_out = N // 2 if epi == ops.EPI_SWIGLU else N
     out = torch.zeros(M, n_out, device=dev, dtype=torch.bfloat16)
-    # (0, -1) = the library's own choice (with VGPT_GEMM_SKINNY_TAIL=1: main tiles + skinny tail kernel);
-    # (0, 2) = skinny tail forced (experimental)
-    # pair: 1 = plain 256-row tiles, 3 = tail rows as swapped-operand tail tiles inside the launch, -1 = library default,
-    # 2 = tail rows in a separate skinny launch (superseded)
-    variants = ((256, 1), (192, 1), (256, 3), (192, 3), (0, -1)) + (((0, 2),) if os.environ.get("VGPT_GEMM_SKINNY_TAIL") == "1" else ())
+    # tail_mode: 1 = plain 256-row tiles, 3 = tail rows in the k-loop of the last full tile row, -1 = library default
+    variants = ((256, 1), (192, 1), (256, 3), (192, 3), (0, -1))
     for bn, pair in variants:
         def run():
             for w in ws:
-                ops.gemm(a, w, out=out, residual=out if epi == ops.EPI_RESIDUAL else None, epilogue=epi, block_n=bn, cta_pair=pair)
+                ops.gemm(a, w, out=out, residual=out if epi == ops.EPI_RESIDUAL else None, epilogue=epi, block_n=bn, tail_mode=pair)
         run(); torch.cuda.synchronize()
         s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()

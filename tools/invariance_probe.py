@@ -20,7 +20,7 @@ for name, N, K, epi in (("qkv", 3 * h, h, ops.EPI_STORE), ("o", h, h, ops.EPI_RE
         same = torch.equal(part, full[lo:hi])
         print(f"gemm {name:8s} rows [{lo},{hi}): bit-equal {same}" + ("" if same else f"  max diff {float((part.float() - full[lo:hi].float()).abs().max()):.4g}, rows differing {int((part != full[lo:hi]).any(1).sum())}"), flush=True)
     for bn in (128, 192, 256):
-        alt = ops.gemm(a, w, residual=r, epilogue=epi, block_n=bn, cta_pair=1)
+        alt = ops.gemm(a, w, residual=r, epilogue=epi, block_n=bn, tail_mode=1)
         print(f"gemm {name:8s} block_n {bn}: bit-equal {torch.equal(alt, full)}", flush=True)
 
 # attention: cfg2 geometry, sharded q rows vs all rows

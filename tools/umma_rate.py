@@ -13,7 +13,7 @@ for mode in (0, 1, 2, 3):
         for N in (32, 64, 96, 128, 192, 256):
             if n_acc == 2 and N > 128:
                 continue
-            _lib.call("vgpt_debug_umma_rate", mode, N, 4096, n_acc, ce, ctas, ctypes.c_void_p(out.data_ptr()), torch.cuda.current_stream().cuda_stream)
+            _lib.call_probe("vgpt_debug_umma_rate", mode, N, 4096, n_acc, ce, ctas, ctypes.c_void_p(out.data_ptr()), torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             row.append(f"N={N}: {out.mean().item():6.1f}")
         print(f"{names[mode]:24s} acc={n_acc} commit_every={ce}  " + "  ".join(row) + "   (floor N/2)", flush=True)
@@ -22,7 +22,7 @@ for mode in (0, 1, 2, 3):
 out2 = torch.zeros(74, device="cuda")
 row = []
 for N in (32, 64, 128, 192, 256):
-    _lib.call("vgpt_debug_umma_rate", 4, N, 4096, 1, 0, 74, ctypes.c_void_p(out2.data_ptr()), torch.cuda.current_stream().cuda_stream)
+    _lib.call_probe("vgpt_debug_umma_rate", 4, N, 4096, 1, 0, 74, ctypes.c_void_p(out2.data_ptr()), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     row.append(f"N={N}: {out2.mean().item():6.1f}")
 print("SS cta_group::2 (M=256)      " + "  ".join(row) + "   (floor N/2)", flush=True)

@@ -39,15 +39,21 @@ SIGNATURES = {
     "vgpt_cfg_euler": [P, P, P, I, I, I, F, F, F, P, P],
     "vgpt_cfg_combine": [P, I, F, P],
     "vgpt_mask_from_codes": [P, P, P, I, I, P],
-    "vgpt_debug_umma_rate": [I, I, I, I, I, I, P, P],
     "vgpt_debug_attn_trace": [P, I, P, P],
-    "vgpt_gemm_bf16_norm": [P, P, P, P, I, I, I, I, I, I, P, F, P],
-    "vgpt_fold_norm_weight": [P, P, P, I, I, P],
+}
+
+# libvgpt_b200_probe.so (include/vgpt_b200_probe.h): descriptor / issue-rate probes for tests and tools, kept out of
+# the product library
+PROBE_LIB_PATH = os.path.join(_HERE, "libvgpt_b200_probe.so")
+PROBE_SIGNATURES = {
+    "vgpt_probe_last_error": [],
+    "vgpt_debug_umma_rate": [I, I, I, I, I, I, P, P],
     "vgpt_debug_umma_probe_ts": [P, I, P, I, c_uint64, c_uint32, I, c_uint32, P, I, P],
     "vgpt_debug_umma_probe": [P, I, P, I, c_uint64, c_uint64, c_uint32, I, c_uint32, c_uint32, P, I, P],
 }
 
 _lib = None
+_probe = None
 
 
 class VgptError(RuntimeError):
@@ -78,4 +84,27 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.vgpt_last_error()
+        raise VgptError(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def load_probe(path: str = PROBE_LIB_PATH) -> ctypes.CDLL:
+    global _probe
+    if _probe is not None:
+        return _probe
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: run `python -m videogpt_b200.build`")
+    lib = ctypes.CDLL(path)
+    for name, argtypes in PROBE_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_char_p if name == "vgpt_probe_last_error" else c_int
+    _probe = lib
+    return lib
+
+
+def call_probe(name: str, *args) -> None:
+    lib = load_probe()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.vgpt_probe_last_error()
         raise VgptError(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")

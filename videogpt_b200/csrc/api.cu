@@ -13,8 +13,8 @@ int vgpt_abi_version(void) { return VGPT_ABI_VERSION; }
 const char* vgpt_last_error(void) { return vgpt::last_error(); }
 
 int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                   int ldc, int epilogue, int block_n, int cta_pair, void* stream) {
-  return vgpt::gemm_bf16(A, W, C, R, M, N, K, lda, ldc, epilogue, block_n, cta_pair, S(stream));
+                   int ldc, int epilogue, int block_n, int tail_mode, void* stream) {
+  return vgpt::gemm_bf16(A, W, C, R, M, N, K, lda, ldc, epilogue, block_n, tail_mode, S(stream));
 }
 int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream) {
   return vgpt::pack_gate_up(w, packed, I, K, S(stream));
@@ -58,12 +58,6 @@ int vgpt_attn_clip_causal(const void* q, int q_ld, int q_rows, void* out, int ou
                           const VgptAttnSeq* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
                           const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H,
                           int D, float scale, void* stream) {
-  // VGPT_ATTN_V1=1 selects the earlier one-query-tile kernel (attention_tcgen05.cu) for A/B timing
-  static const bool v1 = [] { const char* e = getenv("VGPT_ATTN_V1"); return e && e[0] == '1'; }();
-  if (v1)
-    return vgpt::attn_clip_causal_tc(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,
-                                     max_pages, seqs, num_seqs, max_q_rows, q_code, k_code, k_tile_minmax,
-                                     max_k_tiles, H, D, scale, S(stream));
   return vgpt::attn_clip_causal_pair(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,
                                      max_pages, seqs, num_seqs, max_q_rows, q_code, k_code, k_tile_minmax,
                                      max_k_tiles, H, D, scale, S(stream));
@@ -113,33 +107,6 @@ int vgpt_cfg_combine(void* pred, int half_numel, float guidance, void* stream) {
 int vgpt_mask_from_codes(const int32_t* q_code, const int32_t* k_code, void* out, int Lq, int Lk,
                          void* stream) {
   return vgpt::mask_from_codes(q_code, k_code, out, Lq, Lk, S(stream));
-}
-int vgpt_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes,
-                          uint64_t a_desc_base, uint64_t b_desc_base, uint32_t idesc, int k_steps,
-                          uint32_t a_step_bytes, uint32_t b_step_bytes, float* d_out, int n_cols,
-                          void* stream) {
-  return vgpt::umma_probe(a_img, a_bytes, b_img, b_bytes, a_desc_base, b_desc_base, idesc, k_steps,
-                          a_step_bytes, b_step_bytes, d_out, n_cols, S(stream));
-}
-
-int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes,
-                             uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t b_step_bytes,
-                             float* d_out, int n_cols, void* stream) {
-  return vgpt::umma_probe_ts(a_words, a_cols, b_img, b_bytes, b_desc_base, idesc, k_steps, b_step_bytes,
-                             d_out, n_cols, S(stream));
-}
-
-int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out,
-                         void* stream) {
-  return vgpt::umma_rate(mode, N, iters, n_acc, commit_every, ctas, out, S(stream));
-}
-
-int vgpt_gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                        int ldc, int epilogue, float* row_ss, float eps, void* stream) {
-  return vgpt::gemm_bf16_norm(A, W, C, R, M, N, K, lda, ldc, epilogue, row_ss, eps, S(stream));
-}
-int vgpt_fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, void* stream) {
-  return vgpt::fold_norm_weight(w, ln, out, N, K, S(stream));
 }
 int vgpt_debug_attn_trace(void* out, int max_events, int* n_events, void* stream) {
   return vgpt::attn_trace_read(out, max_events, n_events, S(stream));

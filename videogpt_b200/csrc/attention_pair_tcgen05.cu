@@ -52,6 +52,7 @@ struct PairCfg {
   static constexpr int kTileBytes = kChunks * kChunkBytes;    // Q, K or V tile = 128 * D * 2
   static constexpr int kStages = (D == 128) ? 2 : (D == 96 ? 3 : 4);
   static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + 1024;   // tiles + barriers + tile table + align
+  static constexpr int kSmemTrace = kSmem + 4 * 512 * 8;       // + the diagnostic instantiation's stamp rings
   static constexpr int kTmemO = 256;                          // O_A at 256, O_B at 256 + D
   // 64 spare TMEM columns (head_dim <= 96): P gets its own buffer, shared by the two tiles, and
   // S_x(j+1) is issued as soon as the softmax warps have read S_x(j) -- it runs under softmax(j).
@@ -85,66 +86,17 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
       : "f"(a0), "f"(a1));
 }
 
-// 2^x on the FMA pipe (variant 2): x = n + f with n = rint(x), f in [-0.5, 0.5]; 2^f by a degree-3
-// minimax polynomial (max relative error 1.0e-4, far below the bf16 rounding of P), scaled by 2^n
-// through the exponent field.  The magic-number add leaves n in the low mantissa bits of t.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;                 // 1.5 * 2^23
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(0.055008664727211f, f, 0.24221056699752808f);
-  p = fmaf(p, f, 0.6932829022407532f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-// Two exponentials at once with the packed fp32x2 instructions (variant 4): 2 FMNMX + 6 packed + 4 integer
-// instructions per pair instead of 2 x 9.
-__device__ __forceinline__ void ex2_poly2(float& x0, float& x1) {
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  float t0, t1, p0, p1;
-  asm("{\n\t.reg .b64 rx, rt, rn, rf, rp, rk;\n\t"
-      "mov.b64 rx, {%4, %5};\n\t"
-      "mov.b64 rk, {%6, %6};\n\t"                    // +magic
-      "add.rn.f32x2 rt, rx, rk;\n\t"                 // t = x + 1.5 * 2^23
-      "mov.b64 rk, {%7, %7};\n\t"                    // -magic
-      "add.rn.f32x2 rn, rt, rk;\n\t"                 // n = rint(x)
-      "mov.b64 rk, {%8, %8};\n\t"                    // -1
-      "fma.rn.f32x2 rf, rn, rk, rx;\n\t"             // f = x - n
-      "mov.b64 rp, {%9, %9};\n\t"
-      "mov.b64 rk, {%10, %10};\n\t"
-      "fma.rn.f32x2 rp, rp, rf, rk;\n\t"             // c3 f + c2
-      "mov.b64 rk, {%11, %11};\n\t"
-      "fma.rn.f32x2 rp, rp, rf, rk;\n\t"             // (..) f + c1
-      "mov.b64 rk, {%12, %12};\n\t"
-      "fma.rn.f32x2 rp, rp, rf, rk;\n\t"             // (..) f + 1
-      "mov.b64 {%0, %1}, rt;\n\t"
-      "mov.b64 {%2, %3}, rp;\n\t}"
-      : "=f"(t0), "=f"(t1), "=f"(p0), "=f"(p1)
-      : "f"(x0), "f"(x1), "f"(12582912.0f), "f"(-12582912.0f), "f"(-1.0f), "f"(0.055008664727211f),
-        "f"(0.24221056699752808f), "f"(0.6932829022407532f), "f"(1.0f));
-  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
-
-// Experimental variants of the kernel (bit mask in VGPT_ATTN_VARIANT, head_dim 96 only; 0 = the
-// kernel that was validated and measured on hardware, and its SASS is unchanged by their presence):
-//   1  ragged last KV tile: keys beyond kv_len are masked for every query, so S is issued with
-//      N = ceil16(tail) columns and P V with tail / 16 k-steps instead of 128 / 8 (exact: the
-//      skipped products are zeros);
-//   2  every fourth exponential (key column % 4 == 3, a function of the column only, so row results
-//      stay independent of the row partition) is computed on the FMA pipe by ex2_poly instead of
-//      the MUFU unit, which is as loaded as the tensor pipe in this kernel;
-//   4  every second PAIR of exponentials (key columns 4k+2, 4k+3) by ex2_poly2 (packed fp32x2): MUFU
-//      1024 cycles per pair of tiles and KV tile instead of 2048, ~6 more FMA-pipe instructions per
-//      element moved.
-//   8  (diagnostic) CTA (0, 0, 0) records a clock64 time stamp at every hand-over between its roles
-//      into a device buffer (vgpt_debug_attn_trace, tools/attn_trace.py): which of the tensor pipe,
-//      the softmax warps and the loads actually waits for which.
-constexpr int kVarTrimRagged = 1, kVarPolyExp = 2, kVarPolyExpHalf = 4, kVarTrace = 8;
-
-constexpr int kTraceMax = 8192;
+// Diagnostic instantiation (VGPT_ATTN_VARIANT=8, tools/attn_trace.py): lane 0 of four warps of CTA (0, 0, 0) -- softmax
+// A quad 0, softmax B quad 0, the TMA producer and the MMA issuer -- stamp the SM clock at every hand-over between the
+// roles into a per-warp ring in SHARED memory (a clock read and one st.shared: tens of cycles; a first version stamped
+// through a global atomic counter and cost ~900 cycles per event, which distorted the very timeline it recorded:
+// profiles/r02b_attn_trace_atomic_stamps.txt); the rings are copied to global memory when the CTA is done.  The default
+// instantiation contains none of it.  (The opt-in variants of round 1 -- ragged last KV tile trimmed to ceil16(tail),
+// every fourth / every second exponential as a polynomial on the FMA pipe -- were validated and timed in round 2:
+// bit-exact / within 2^-7, and 0.3 - 2.8 us SLOWER than the default at cfg2 (profiles/r02b_attn_variants.txt): the MUFU
+// unit is 39 % busy, not the limit.  They were deleted.)
+constexpr int kTraceRoles = 4, kTracePerRole = 512;
+constexpr int kTraceMax = kTraceRoles * kTracePerRole;
 __device__ unsigned long long g_attn_trace[2 * kTraceMax];     // (clock, warp << 40 | tile << 32 | j << 8 | event)
 __device__ unsigned int g_attn_trace_n;
 
@@ -155,23 +107,22 @@ enum : int {   // trace events
   kEvStart = 30, kEvTableDone = 31, kEvEnd = 32
 };
 
-template <int VAR>
-__device__ __forceinline__ void attn_trace(int tile, int j, int ev) {
-  if constexpr ((VAR & kVarTrace) != 0) {
-    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0) {
-      const unsigned i = atomicAdd(&g_attn_trace_n, 1u);
-      if (i < (unsigned)kTraceMax) {
-        g_attn_trace[2 * i] = (unsigned long long)clock64();
-        g_attn_trace[2 * i + 1] = ((unsigned long long)(threadIdx.x >> 5) << 40) | ((unsigned long long)(tile & 0xff) << 32) |
-                                  ((unsigned long long)(j & 0xffffff) << 8) | (unsigned long long)ev;
+template <bool TRACE>
+struct Tracer {
+  uint2* ring = nullptr;       // this warp's ring in shared memory (null: this thread does not record)
+  int n = 0;
+  __device__ __forceinline__ void operator()(int tile, int j, int ev) {
+    if constexpr (TRACE) {
+      if (ring != nullptr && n < kTracePerRole) {
+        ring[n++] = make_uint2((unsigned)clock(), ((unsigned)(tile & 0xff) << 28) | ((unsigned)(j & 0xfffff) << 8) | (unsigned)ev);
       }
     }
   }
-}
+};
 
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
-template <int D, int VAR>
+template <int D, bool TRACE>
 __global__ void __launch_bounds__(kPairThreads, 1)
 attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int out_ld,
@@ -216,6 +167,13 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int rows_cta = min(2 * kPairBM, sq.n_q - q0);          // valid rows of A and B together
   const bool has_b = rows_cta > kPairBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Tracer<TRACE> tr;
+  [[maybe_unused]] uint2* trace_rings = reinterpret_cast<uint2*>(t_kt + kPairMaxTiles);
+  __shared__ int s_trace_n[kTraceRoles];
+  if constexpr (TRACE) {
+    const int role = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : warp == 9 ? 3 : -1;
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && role >= 0) tr.ring = trace_rings + role * kTracePerRole;
+  }
 
   // ---- CTA-wide max of the valid query codes (tile classification) -----------------------------
   if (threadIdx.x == 0) { s_qmin = 0x7fffffff; s_qmax = (int)0x80000000; s_nvis = 0; }
@@ -236,7 +194,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const int n_kt = (sq.kv_len + kPairBN - 1) / kPairBN;
-  attn_trace<VAR>(0, 0, kEvStart);
+  tr(0, 0, kEvStart);
   if (warp == 8) {                        // Q does not need the table: start its load now
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_q, (has_b ? 2 : 1) * C::kTileBytes);
@@ -273,7 +231,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   }
   __syncthreads();
   const int n_vis = s_nvis;
-  attn_trace<VAR>(0, n_vis, kEvTableDone);
+  tr(0, n_vis, kEvTableDone);
 
   if (warp >= 8) {
     // 256 x 224 + 128 x 56 = 64512 = the 384 x 168 registers the CTA was launched with.  (A first version gave the
@@ -286,7 +244,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     for (int i = 0; i < n_vis; ++i) {
       const int row = (t_page[i] * H + head) * kPairBN;         // pool viewed as [(page*H + head)*128 + tok][D]
       mbar_wait(bar_kv_empty(stage), phase ^ 1);
-      attn_trace<VAR>(0, i, kEvKvEmpty);
+      tr(0, i, kEvKvEmpty);
       if ((dbg & 8) && i >= kStages) {                          // timing probe: operands not refreshed
         if (elect_one_sync()) mbar_arrive(bar_kv_full(stage));
       } else if (elect_one_sync()) {
@@ -298,7 +256,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int c = 0; c < C::kChunks; ++c) tma_load_2d(sv + c * C::kChunkBytes, &tmap_v, bar_kv_full(stage), c * C::kCW, row);
       }
       __syncwarp();
-      attn_trace<VAR>(0, i, kEvKvIssued);
+      tr(0, i, kEvKvIssued);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 9) {
@@ -306,24 +264,16 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
     constexpr uint32_t idesc_s = make_idesc_bf16(128, kPairBN);        // S = Q K^T (both K-major)
     constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O = P V   (V MN-major)
-    // variant 1: width of S / depth of P V for the LAST visible tile when it is the ragged one
-    int n_last = kPairBN;
-    if constexpr (VAR & kVarTrimRagged) {
-      const int tail = sq.kv_len & (kPairBN - 1);
-      if (tail != 0 && n_vis > 0 && t_kt[n_vis - 1] == n_kt - 1) n_last = (tail + 15) & ~15;
-    }
-    auto issue_s = [&](int x, int stage, bool last = false) {
+    auto issue_s = [&](int x, int stage) {
       if (elect_one_sync()) {
         const uint32_t sk = s_kv + 2 * stage * C::kTileBytes, sqx = s_q + x * C::kTileBytes;
-        uint32_t idesc = idesc_s;
-        if constexpr (VAR & kVarTrimRagged) idesc = last ? make_idesc_bf16(128, n_last) : idesc_s;
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
 #pragma unroll
           for (int ks = 0; ks < C::kCW / 16; ++ks) {
             const uint64_t da = make_smem_desc(sqx + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
             const uint64_t db = make_smem_desc(sk + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
-            umma_f16_ss(tmem + x * 128, da, db, idesc, (c | ks) ? 1u : 0u);
+            umma_f16_ss(tmem + x * 128, da, db, idesc_s, (c | ks) ? 1u : 0u);
           }
         }
         if (!(dbg & 32)) umma_commit(bar_s_full(x));          // (dbg & 32: timing probe, fewer commits)
@@ -335,9 +285,6 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const uint32_t sv = s_kv + 2 * stage * C::kTileBytes + C::kTileBytes;
 #pragma unroll
         for (int ks = 0; ks < kPairBN / 16; ++ks) {
-          if constexpr (VAR & kVarTrimRagged) {
-            if (j == n_vis - 1 && ks >= (n_last >> 4)) continue;   // P is zero in these columns
-          }
           const uint64_t db = make_smem_desc(sv + ks * 16 * C::kRowBytes, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);
           umma_f16_ts(tmem + C::kTmemO + x * D, tmem + (C::kEarlyS ? C::kTmemP : x * 128) + ks * 8, db, idesc_o,
                       (j > 0 || ks > 0) ? 1u : 0u);
@@ -353,8 +300,8 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     if (n_vis > 0) {                            // prologue: S_A(0), S_B(0)
       mbar_wait(bar_kv_full(stage_s), phase_s);
       tc_fence_after();
-      issue_s(0, stage_s, n_vis == 1);
-      if (has_b) issue_s(1, stage_s, n_vis == 1);
+      issue_s(0, stage_s);
+      if (has_b) issue_s(1, stage_s);
       if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
     }
     if constexpr (C::kEarlyS) {
@@ -368,16 +315,16 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           if (has_next) {
             if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
             if (x == 0) mbar_wait(bar_kv_full(stage_s), phase_s);
-            attn_trace<VAR>(x, j + 1, kEvSFree);
+            tr(x, j + 1, kEvSFree);
             tc_fence_after();
-            issue_s(x, stage_s, j + 2 == n_vis);
-            attn_trace<VAR>(x, j + 1, kEvSIssued);
+            issue_s(x, stage_s);
+            tr(x, j + 1, kEvSIssued);
           }
           if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
-          attn_trace<VAR>(x, j, kEvPFull);
+          tr(x, j, kEvPFull);
           tc_fence_after();
           issue_pv(x, stage_o, j, x == (has_b ? 1 : 0));
-          attn_trace<VAR>(x, j, kEvPVIssued);
+          tr(x, j, kEvPVIssued);
         }
         if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
         if (++stage_o == kStages) stage_o = 0;
@@ -391,13 +338,13 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (has_next) {
           mbar_wait(bar_kv_full(stage_s), phase_s);
           tc_fence_after();
-          issue_s(0, stage_s, j + 2 == n_vis);    // S_A(j+1) overwrites P_A(j): behind P V_A(j) in pipe order
+          issue_s(0, stage_s);    // S_A(j+1) overwrites P_A(j): behind P V_A(j) in pipe order
         }
         if (has_b) {
           mbar_wait(bar_p_full(1), j & 1);
           tc_fence_after();
           issue_pv(1, stage_o, j, true);
-          if (has_next) issue_s(1, stage_s, j + 2 == n_vis);
+          if (has_next) issue_s(1, stage_s);
         }
         if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
         if (++stage_o == kStages) stage_o = 0;
@@ -426,7 +373,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
         const int tmax = t_tmax[j], kt = t_kt[j];                 // (shared memory, before the wait)
         mbar_wait(bar_s_full(x), j & 1);
-        if (quad == 0) attn_trace<VAR>(x, j, kEvSFull);
+        if (quad == 0) tr(x, j, kEvSFull);
         tc_fence_after();
         if (dbg & 1) {                                            // timing probe: tensor-pipe chain only
           tc_fence_before();
@@ -466,7 +413,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_s_free(x));
         }
-        if (quad == 0) attn_trace<VAR>(x, j, kEvSRead);
+        if (quad == 0) tr(x, j, kEvSRead);
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -489,23 +436,11 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         for (int i = 0; i < 64; ++i) {
           float p0, p1;
           ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), scale_log2, nsub);
-          if constexpr (VAR & kVarPolyExpHalf) {
-            if (i & 1) {                                          // key columns 4k+2, 4k+3: FMA pipe, packed
-              ex2_poly2(p0, p1);
-            } else {
-              p0 = ex2_ftz(p0);
-              p1 = ex2_ftz(p1);
-            }
-          } else if constexpr (VAR & kVarPolyExp) {
-            p0 = ex2_ftz(p0);
-            p1 = (i & 1) ? ex2_poly(p1) : ex2_ftz(p1);            // key column 2i + 1 = 3 (mod 4): FMA pipe
-          } else {
-            if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
-          }
+          if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
           fadd2(sum0, sum1, p0, p1);
           s[i] = pack_bf16x2(p0, p1);                             // P overwrites the dead half of s[]
         }
-        if (quad == 0) attn_trace<VAR>(x, j, kEvExpDone);
+        if (quad == 0) tr(x, j, kEvExpDone);
         if constexpr (C::kEarlyS) {
           // the P buffer is shared: its previous reader is P V of the other tile (B: tile j of A;
           // A: tile j-1 of B), or of this tile when it is alone
@@ -515,7 +450,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             mbar_wait(bar_o_full(y), need & 1);
             tc_fence_after();
           }
-          if (quad == 0) attn_trace<VAR>(x, j, kEvPBufFree);
+          if (quad == 0) tr(x, j, kEvPBufFree);
           tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
           tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
         } else {
@@ -542,14 +477,14 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 per tile)
-        if (quad == 0) attn_trace<VAR>(x, j, kEvPWritten);
+        if (quad == 0) tr(x, j, kEvPWritten);
       }
       // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------
       if (n_vis > 0) {
         mbar_wait(bar_o_full(x), (n_vis - 1) & 1);
         tc_fence_after();
       }
-      if (quad == 0) attn_trace<VAR>(x, n_vis, kEvEpilogue);
+      if (quad == 0) tr(x, n_vis, kEvEpilogue);
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __nv_bfloat16* orow = out + (size_t)grow * out_ld + head * D;
 #pragma unroll
@@ -576,9 +511,29 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
   }
 
+  tr(0, 0, kEvEnd);
+  if constexpr (TRACE) {
+    if (tr.ring != nullptr) s_trace_n[(tr.ring - trace_rings) / kTracePerRole] = tr.n;
+  }
   tc_fence_before();
   __syncthreads();
-  attn_trace<VAR>(0, 0, kEvEnd);
+  if constexpr (TRACE) {
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0) {       // rings -> global memory, role after role
+      const int role_warp[kTraceRoles] = {0, 4, 8, 9};
+      int base = 0;
+      for (int r = 0; r < kTraceRoles; ++r) {
+        const int n = s_trace_n[r];
+        for (int i = threadIdx.x; i < n; i += kPairThreads) {
+          const uint2 e = trace_rings[r * kTracePerRole + i];
+          g_attn_trace[2 * (base + i)] = e.x;
+          g_attn_trace[2 * (base + i) + 1] = ((unsigned long long)role_warp[r] << 40) | ((unsigned long long)(e.y >> 28) << 32) |
+                                             (unsigned long long)(e.y & 0x0fffffffu);
+        }
+        base += n;
+      }
+      if (threadIdx.x == 0) g_attn_trace_n = (unsigned)base;
+    }
+  }
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
@@ -593,13 +548,12 @@ static int debug_attn_flags() {     // VGPT_DEBUG_ATTN_FLAGS: timing probes only
   return f;
 }
 
-static int attn_variant() {         // VGPT_ATTN_VARIANT: experimental kernel variants (see kVar* above), default 0.
-  const char* e = getenv("VGPT_ATTN_VARIANT");   // read at every launch so that one process can compare variants
-  const int v = e ? atoi(e) : 0;
-  return ((v >= 0 && v <= 5) || v == kVarTrace) ? v : 0;
+static bool attn_trace_on() {      // VGPT_ATTN_VARIANT=8: the diagnostic instantiation (head_dim 96); read at every launch
+  const char* e = getenv("VGPT_ATTN_VARIANT");
+  return e && atoi(e) == 8;
 }
 
-template <int D, int VAR>
+template <int D, bool TRACE>
 static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                             const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                             const void* seqs, int num_seqs, int q_pairs, const int32_t* q_code,
@@ -624,14 +578,12 @@ static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int 
     rc = encode_tensor_map(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(v_pool), dims, strides, box, estr, swz);
     if (rc) return rc;
   }
-  auto kern = attn_pair_tcgen05_kernel<D, VAR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    attr_set = true;
-  }
+  auto kern = attn_pair_tcgen05_kernel<D, TRACE>;
+  constexpr int smem = TRACE ? C::kSmemTrace : C::kSmem;
+  // per launch: the attribute is per device, and a process may drive several devices (cheap, capture-safe)
+  VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(H, q_pairs, num_seqs);
-  kern<<<grid, kPairThreads, C::kSmem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
+  kern<<<grid, kPairThreads, smem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
                                             (const AttnSeqP*)seqs, q_code, k_code, k_tile_minmax,
                                             max_k_tiles64, H, scale * 1.4426950408889634f, debug_attn_flags());
   VGPT_CHECK_LAUNCH();
@@ -674,21 +626,16 @@ int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int ou
   VGPT_CHECK_ARG(max_pages <= kPairMaxTiles, "vgpt_attn_clip_causal: %d pages per sequence (at most %d)", max_pages, kPairMaxTiles);
   if (num_seqs <= 0 || max_q_rows <= 0) return 0;
   const int q_pairs = (max_q_rows + 2 * kPairBM - 1) / (2 * kPairBM);
-  const int var = (D == 96) ? attn_variant() : 0;
-#define VGPT_ATTN_CASE(D_, V_)                                                                              \
-  if (D == D_ && var == V_)                                                                                  \
-    return launch_attn_pair<D_, V_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,  \
+  const bool trace = D == 96 && attn_trace_on();
+#define VGPT_ATTN_CASE(D_, T_)                                                                              \
+  if (D == D_ && trace == T_)                                                                                \
+    return launch_attn_pair<D_, T_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,  \
                                     max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,      \
                                     max_k_tiles, H, scale, s);
-  VGPT_ATTN_CASE(64, 0)
-  VGPT_ATTN_CASE(96, 0)
-  VGPT_ATTN_CASE(96, 1)
-  VGPT_ATTN_CASE(96, 2)
-  VGPT_ATTN_CASE(96, 3)
-  VGPT_ATTN_CASE(96, 4)
-  VGPT_ATTN_CASE(96, 5)
-  VGPT_ATTN_CASE(96, 8)
-  VGPT_ATTN_CASE(128, 0)
+  VGPT_ATTN_CASE(64, false)
+  VGPT_ATTN_CASE(96, false)
+  VGPT_ATTN_CASE(96, true)
+  VGPT_ATTN_CASE(128, false)
 #undef VGPT_ATTN_CASE
   return -1;
 }

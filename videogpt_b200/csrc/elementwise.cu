@@ -365,12 +365,8 @@ int linear_small(const void* in, const void* W, const void* bias, void* out, int
                  kSmallMaxRows);
   if (n == 0) return 0;
   const size_t smem = (size_t)n * K * sizeof(__nv_bfloat16);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    VGPT_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024)       // per launch: the attribute is per device (cheap, capture-safe)
+    VGPT_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   linear_small_kernel<<<(N + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, smem, s>>>(
       (const __nv_bfloat16*)in, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias,
       (__nv_bfloat16*)out, n, N, K, pre_silu, post_silu);
@@ -587,14 +583,15 @@ int cfg_combine(void* pred, int half_numel, float guidance, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// SwiGLU weight repack: gate_up_proj [2I, K] = [gate(I) | up(I)] rows  ->  per 64 packed rows
-// [gate x32 | up x32] of 32 consecutive outputs, so one accumulator tile holds matching pairs.
+// SwiGLU weight repack: gate_up_proj [2I, K] = [gate(I) | up(I)] rows  ->  per 32 packed rows
+// [gate x16 | up x16] of 16 consecutive outputs, so one 32-column accumulator chunk holds matching pairs (and, for
+// the transposed tail accumulator of gemm_pair_tcgen05.cu, one 32-lane TMEM quadrant does).
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_gate_up_kernel(const uint4* __restrict__ w, uint4* __restrict__ out, int I,
                                     int kchunks) {
   const int prow = blockIdx.x;                       // packed row
-  const int blk = prow >> 6, r = prow & 63;
-  const int src = (r < 32) ? (blk * 32 + r) : (I + blk * 32 + (r - 32));
+  const int blk = prow >> 5, r = prow & 31;
+  const int src = (r < 16) ? (blk * 16 + r) : (I + blk * 16 + (r - 16));
   for (int c = threadIdx.x; c < kchunks; c += blockDim.x)
     out[(size_t)prow * kchunks + c] = w[(size_t)src * kchunks + c];
 }
@@ -603,30 +600,6 @@ int pack_gate_up(const void* w, void* packed, int I, int K, cudaStream_t s) {
   VGPT_CHECK_ARG(w && packed && w != packed, "vgpt_pack_gate_up: bad pointers");
   VGPT_CHECK_ARG(I > 0 && I % 32 == 0 && K % 8 == 0, "vgpt_pack_gate_up: I=%d K=%d unsupported", I, K);
   pack_gate_up_kernel<<<2 * I, 128, 0, s>>>((const uint4*)w, (uint4*)packed, I, K / 8);
-  VGPT_CHECK_LAUNCH();
-  return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// RMSNorm weight folded into the following projection (vgpt_gemm_bf16_norm): out[n][k] = w[n][k] * ln[k],
-// product in fp32, rounded to bf16 once.  One-time weight preparation, like pack_gate_up.
-// ---------------------------------------------------------------------------------------------
-__global__ void fold_norm_weight_kernel(const uint4* __restrict__ w, const uint4* __restrict__ ln,
-                                        uint4* __restrict__ out, int kchunks) {
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < kchunks; c += blockDim.x) {
-    float a[8], b[8];
-    unpack8(w[(size_t)n * kchunks + c], a);
-    unpack8(ln[c], b);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] *= b[i];
-    out[(size_t)n * kchunks + c] = pack8(a);
-  }
-}
-
-int fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, cudaStream_t s) {
-  VGPT_CHECK_ARG(w && ln && out && N > 0 && K > 0 && K % 8 == 0, "vgpt_fold_norm_weight: bad arguments (N=%d K=%d)", N, K);
-  fold_norm_weight_kernel<<<N, 128, 0, s>>>((const uint4*)w, (const uint4*)ln, (uint4*)out, K / 8);
   VGPT_CHECK_LAUNCH();
   return 0;
 }

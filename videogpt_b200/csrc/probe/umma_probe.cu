@@ -2,11 +2,19 @@
 // memory images and descriptor fields, and returns the fp32 accumulator tile.  It exists so the
 // shared-memory layouts / descriptor encodings the production kernels rely on (K-major and
 // MN-major operands, 32/64/128-byte swizzles, K-advance strides) are pinned by a test on the GPU
-// (tests/test_umma_layouts.py) instead of being assumed.  Not on the hot path.
-#include "common.cuh"
-#include "vgpt_internal.h"
+// (tests/test_umma_layouts.py) instead of being assumed.  Built into libvgpt_b200_probe.so (tests and
+// tools/umma_rate.py only), NOT into the product library.
+#include "../common.cuh"
+#include "../vgpt_internal.h"
 
 namespace vgpt {
+
+int umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes, uint64_t b_desc_base,
+                  uint32_t idesc, int k_steps, uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s);
+int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t a_desc_base,
+               uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t a_step_bytes,
+               uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s);
+int umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out, cudaStream_t s);
 
 __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const uint4* __restrict__ a_img, int a_bytes, const uint4* __restrict__ b_img,
@@ -284,3 +292,24 @@ int umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas,
 }
 
 }  // namespace vgpt
+
+// ---------------------------------------------------------------------------------------------
+// C ABI of the probe library (include/vgpt_b200_probe.h)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+const char* vgpt_probe_last_error(void) { return vgpt::last_error(); }
+int vgpt_debug_umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t a_desc_base,
+                          uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t a_step_bytes,
+                          uint32_t b_step_bytes, float* d_out, int n_cols, void* stream) {
+  return vgpt::umma_probe(a_img, a_bytes, b_img, b_bytes, a_desc_base, b_desc_base, idesc, k_steps, a_step_bytes,
+                          b_step_bytes, d_out, n_cols, static_cast<cudaStream_t>(stream));
+}
+int vgpt_debug_umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes, uint64_t b_desc_base,
+                             uint32_t idesc, int k_steps, uint32_t b_step_bytes, float* d_out, int n_cols, void* stream) {
+  return vgpt::umma_probe_ts(a_words, a_cols, b_img, b_bytes, b_desc_base, idesc, k_steps, b_step_bytes, d_out, n_cols,
+                             static_cast<cudaStream_t>(stream));
+}
+int vgpt_debug_umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out, void* stream) {
+  return vgpt::umma_rate(mode, N, iters, n_acc, commit_every, ctas, out, static_cast<cudaStream_t>(stream));
+}
+}  // extern "C"

@@ -24,16 +24,9 @@ int encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank
 const char* last_error();
 
 int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-              int ldc, int epilogue, int block_n, int cta_pair, cudaStream_t stream);
+              int ldc, int epilogue, int block_n, int tail_mode, cudaStream_t stream);
 int debug_gemm_flags();
-int gemm_bf16_pair(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
-                   int epilogue, int block_n, cudaStream_t stream, int tail_rows = 0);
 int pick_pair_block_n(int M, int N, int num_sms);
-int gemm_bf16_norm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
-                   int epilogue, float* row_ss, float eps, cudaStream_t stream);
-int fold_norm_weight(const void* w, const void* ln, void* out, int N, int K, cudaStream_t s);
-int gemm_bf16_skinny(const void* A_tail, const void* W, void* C_tail, const void* R_tail, int rows, int N, int K,
-                     int lda, int ldc, int epilogue, cudaStream_t stream);
 int pack_gate_up(const void* w, void* packed, int I, int K, cudaStream_t s);
 int rmsnorm(const void* x, const void* w, void* y, int rows, int hidden, float eps, cudaStream_t s);
 int rope_table(const float* inv_freq, void* tab, int max_pos, int head_dim, cudaStream_t s);
@@ -45,11 +38,6 @@ int attn_clip_causal(const void* q, int q_ld, void* out, int out_ld, const void*
                      int num_seqs, int max_q_rows, const int32_t* q_code, const int32_t* k_code,
                      const int32_t* k_tile_minmax, int max_k_tiles, int H, int D, float scale,
                      cudaStream_t s);
-int attn_clip_causal_tc(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
-                        const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
-                        const void* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
-                        const int32_t* k_code, const int32_t* k_tile_minmax, int max_k_tiles, int H, int D,
-                        float scale, cudaStream_t s);
 int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                           const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                           const void* seqs, int num_seqs, int max_q_rows, const int32_t* q_code,
@@ -78,12 +66,6 @@ int cfg_euler(void* z, const void* pred, void* vel_out, int half_numel, int use_
               cudaStream_t s);
 int cfg_combine(void* pred, int half_numel, float guidance, cudaStream_t s);
 int mask_from_codes(const int32_t* qc, const int32_t* kc, void* out, int Lq, int Lk, cudaStream_t s);
-int umma_probe_ts(const void* a_words, int a_cols, const void* b_img, int b_bytes, uint64_t b_desc_base,
-                  uint32_t idesc, int k_steps, uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s);
 int attn_trace_read(void* out, int max_events, int* n_events, cudaStream_t s);
-int umma_rate(int mode, int N, int iters, int n_acc, int commit_every, int ctas, float* out, cudaStream_t s);
-int umma_probe(const void* a_img, int a_bytes, const void* b_img, int b_bytes, uint64_t a_desc_base,
-               uint64_t b_desc_base, uint32_t idesc, int k_steps, uint32_t a_step_bytes,
-               uint32_t b_step_bytes, float* d_out, int n_cols, cudaStream_t s);
 
 }  // namespace vgpt

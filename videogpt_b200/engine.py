@@ -65,19 +65,8 @@ class EngineWeights:
             self.layers.append(dict(
                 ln1=g(p + "input_layernorm.weight"), qkv=g(p + "self_attn.qkv_proj.weight"),
                 o=g(p + "self_attn.o_proj.weight"), ln2=g(p + "post_attention_layernorm.weight"),
-                gate_up=ops.pack_gate_up(gate_up), gate_up_raw=gate_up, down=g(p + "mlp.down_proj.weight")))
+                gate_up=ops.pack_gate_up(gate_up), down=g(p + "mlp.down_proj.weight")))
         self.pos_embed = sd.get("pos_embed")          # optional full table [1, max*max, h]
-        self._folded = False
-
-    def fold_norms(self):
-        """Projection weights with the preceding RMSNorm weight folded in (``ops.fold_norm_weight``):
-        ``qkv_n`` = qkv * ln1 and ``gate_up_n`` = pack(gate_up * ln2), for ``NextClipEngine.fold_norm``.
-        Built once, on first use (one extra copy of the qkv and gate_up weights)."""
-        if not self._folded:
-            for lw in self.layers:
-                lw["qkv_n"] = ops.fold_norm_weight(lw["qkv"], lw["ln1"])
-                lw["gate_up_n"] = ops.pack_gate_up(ops.fold_norm_weight(lw["gate_up_raw"], lw["ln2"]))
-            self._folded = True
 
 
 # --------------------------------------------------------------------------------------------
@@ -397,13 +386,6 @@ class NextClipEngine:
         # then run on ONE row and the result is replicated -- identical numbers, 1/n of the work.
         self.uniform_t = False
         self._graph_uniform = None
-        # EXPERIMENTAL (never run on hardware): RMSNorm folded into the projections around it -- the
-        # residual epilogue of o / down hands every row's sum of squares to the following qkv / gate_up
-        # GEMM, which reads the raw hidden rows, uses weights pre-multiplied by the norm weight and
-        # scales its rows by rstd.  64 rmsnorm launches per step disappear; rounding points differ from
-        # the reference's (no bf16 rounding of the normalised activations).  Not with sequence parallelism.
-        import os
-        self.fold_norm = os.environ.get("VGPT_FOLD_RMSNORM") == "1" and peers is None
         self.plan: Optional[ClipPlan] = None
         # diagnostic tap (tools/parity_floor.py): a list that receives a copy of the hidden rows after every
         # decoder layer of eager (non-graph) passes; None in production
@@ -455,9 +437,6 @@ class NextClipEngine:
         self.qkv = torch.empty(rows, 3 * self.hs, device=dev, dtype=bf)
         self.attn = torch.empty(rows, self.hs, device=dev, dtype=bf)
         self.mlp_h = torch.empty(rows, self.inter, device=dev, dtype=bf)
-        if self.fold_norm:
-            self.w.fold_norms()
-            self.row_ss = torch.zeros(2, rows, ops.NORM_PARTS, device=dev, dtype=torch.float32)
         # paged KV pools: [layer][k|v][page][H][128][D]
         n = max(plan.n_latents, 1)
         self.z = torch.zeros(n, 4, plan.lat_h, plan.lat_w, device=dev, dtype=bf)
@@ -554,14 +533,10 @@ class NextClipEngine:
         n, plan = ph.rows, self.plan
         hidden, xn, qkv, attn, mlp_h = (self.hidden[:n], self.xn[:n], self.qkv[:n], self.attn[:n], self.mlp_h[:n])
         scale = 1.0 / math.sqrt(self.D)
-        fold = self.fold_norm and self.peers is None
         for li, lw in enumerate(self.w.layers):
             if n:
-                if fold and li > 0:       # rows scaled by rstd from the sums of squares the previous down_proj left
-                    ops.gemm_norm(hidden, lw["qkv_n"], qkv, self.row_ss[1, :n], self.eps, ops.EPI_STORE_SCALED)
-                else:
-                    ops.rmsnorm(hidden, lw["ln1"], self.eps, out=xn)
-                    ops.gemm(xn, lw["qkv"], out=qkv)
+                ops.rmsnorm(hidden, lw["ln1"], self.eps, out=xn)
+                ops.gemm(xn, lw["qkv"], out=qkv)
                 if self.peers is None:
                     ops.rope_kv_append(qkv, ph.row_pos, ph.row_slot, self._rope_tab, self.kv[li, 0], self.kv[li, 1],
                                        self.H, self.D)
@@ -576,15 +551,10 @@ class NextClipEngine:
                 continue
             ops.attention(qkv[:, :self.hs], attn, self.kv[li, 0], self.kv[li, 1], plan.page_table, ph.seqs,
                           ph.max_q_rows, ph.q_code, plan.k_code, plan.k_tile_minmax, self.H, self.D, scale)
-            if fold:
-                ops.gemm_norm(attn, lw["o"], hidden, self.row_ss[0, :n], self.eps, ops.EPI_RESIDUAL_SS, residual=hidden)
-                ops.gemm_norm(hidden, lw["gate_up_n"], mlp_h, self.row_ss[0, :n], self.eps, ops.EPI_SWIGLU_SCALED)
-                ops.gemm_norm(mlp_h, lw["down"], hidden, self.row_ss[1, :n], self.eps, ops.EPI_RESIDUAL_SS, residual=hidden)
-            else:
-                ops.gemm(attn, lw["o"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
-                ops.rmsnorm(hidden, lw["ln2"], self.eps, out=xn)
-                ops.gemm(xn, lw["gate_up"], out=mlp_h, epilogue=ops.EPI_SWIGLU)
-                ops.gemm(mlp_h, lw["down"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
+            ops.gemm(attn, lw["o"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
+            ops.rmsnorm(hidden, lw["ln2"], self.eps, out=xn)
+            ops.gemm(xn, lw["gate_up"], out=mlp_h, epilogue=ops.EPI_SWIGLU)
+            ops.gemm(mlp_h, lw["down"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
             if self.layer_tap is not None:
                 self.layer_tap.append(hidden.clone())
 

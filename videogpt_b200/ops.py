@@ -14,8 +14,6 @@ import torch
 from . import _lib
 
 EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU = 0, 1, 2
-EPI_RESIDUAL_SS, EPI_STORE_SCALED, EPI_SWIGLU_SCALED = 3, 4, 5      # RMSNorm folded into the GEMMs (experimental)
-NORM_PARTS = 32
 ROW_TOKEN, ROW_TIME, ROW_NOISY_PATCH, ROW_CONTEXT_PATCH = 0, 1, 2, 3
 PAGE_TOKENS = 128
 ATTN_KV_TILE = 64
@@ -43,8 +41,9 @@ def _req(t: torch.Tensor, dtype, name: str, contiguous: bool = True):
     return t
 
 
-def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int = 0, cta_pair: int = -1):
-    """``out[M,N(/2)] = a[M,K] @ w[N,K]^T`` (+ epilogue).  ``a`` may be row-strided."""
+def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int = 0, tail_mode: int = -1):
+    """``out[M,N(/2)] = a[M,K] @ w[N,K]^T`` (+ epilogue).  ``a`` may be row-strided.  ``tail_mode``: -1 tuned default,
+    1 plain 256-row tiles, 3 the ``M % 256 <= 32`` tail rows inside the k-loop of the last full tile row (same bits)."""
     _req(a, BF16, "a", contiguous=False)
     _req(w, BF16, "w")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and a.shape[1] == w.shape[1]
@@ -59,38 +58,7 @@ def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int 
         _req(residual, BF16, "residual", contiguous=False)
         assert residual.shape == out.shape and residual.stride(0) == out.stride(0)
     _lib.call("vgpt_gemm_bf16", _p(a), _p(w), _p(out), _p(residual), M, N, K, a.stride(0),
-              out.stride(0), epilogue, block_n, cta_pair, _stream())
-    return out
-
-
-def gemm_norm(a, w, out, row_ss, eps: float, epilogue: int, residual=None):
-    """EXPERIMENTAL (``vgpt_gemm_bf16_norm``): GEMM with the neighbouring RMSNorm folded in.
-    ``EPI_RESIDUAL_SS``: ``out = bf16(a w^T) + residual`` and ``row_ss[M, NORM_PARTS]`` receives the
-    per-tile sums of squares of the stored rows; ``EPI_STORE_SCALED`` / ``EPI_SWIGLU_SCALED``: ``a`` is
-    the RAW hidden matrix, ``w`` carries the norm weight (``fold_norm_weight``), rows are scaled by
-    ``rsqrt(sum(row_ss[row]) / K + eps)``."""
-    _req(a, BF16, "a", contiguous=False); _req(w, BF16, "w"); _req(out, BF16, "out", contiguous=False)
-    _req(row_ss, F32, "row_ss")
-    M, K = a.shape
-    N = w.shape[0]
-    n_out = N // 2 if epilogue == EPI_SWIGLU_SCALED else N
-    assert a.stride(1) == 1 and w.shape[1] == K and out.shape == (M, n_out) and out.stride(1) == 1
-    assert row_ss.shape[0] >= M and row_ss.shape[1] == NORM_PARTS
-    assert epilogue in (EPI_RESIDUAL_SS, EPI_STORE_SCALED, EPI_SWIGLU_SCALED)
-    if epilogue == EPI_RESIDUAL_SS:
-        _req(residual, BF16, "residual", contiguous=False)
-        assert residual.shape == out.shape and residual.stride(0) == out.stride(0)
-    _lib.call("vgpt_gemm_bf16_norm", _p(a), _p(w), _p(out), _p(residual), M, N, K, a.stride(0), out.stride(0),
-              epilogue, _p(row_ss), float(eps), _stream())
-    return out
-
-
-def fold_norm_weight(w, ln):
-    """``w[N, K] * ln[K]`` rounded to bf16 once (projection weight with the preceding RMSNorm weight)."""
-    _req(w, BF16, "w"); _req(ln, BF16, "ln")
-    assert w.dim() == 2 and ln.numel() == w.shape[1]
-    out = torch.empty_like(w)
-    _lib.call("vgpt_fold_norm_weight", _p(w), _p(ln), _p(out), w.shape[0], w.shape[1], _stream())
+              out.stride(0), epilogue, block_n, tail_mode, _stream())
     return out
 
 
@@ -262,7 +230,7 @@ def umma_probe(a_img, b_img, a_desc_base: int, b_desc_base: int, idesc: int, k_s
     """Test hook (tests/test_umma_layouts.py): raw smem images (uint8 CUDA tensors) -> fp32 [128, n_cols]."""
     assert a_img.is_cuda and b_img.is_cuda and a_img.dtype == torch.uint8 and b_img.dtype == torch.uint8
     out = torch.zeros(128, n_cols, device=a_img.device, dtype=F32)
-    _lib.call("vgpt_debug_umma_probe", _p(a_img), a_img.numel(), _p(b_img), b_img.numel(),
+    _lib.call_probe("vgpt_debug_umma_probe", _p(a_img), a_img.numel(), _p(b_img), b_img.numel(),
               ctypes.c_uint64(a_desc_base), ctypes.c_uint64(b_desc_base), ctypes.c_uint32(idesc), k_steps,
               ctypes.c_uint32(a_step_bytes), ctypes.c_uint32(b_step_bytes), _p(out), n_cols, _stream())
     return out
@@ -272,7 +240,7 @@ def umma_probe_ts(a_words, b_img, b_desc_base: int, idesc: int, k_steps: int, b_
     """Test hook: A operand in tensor memory.  a_words: int32 CUDA tensor [128, cols] (packed bf16x2)."""
     assert a_words.is_cuda and a_words.dtype == torch.int32 and a_words.shape[0] == 128 and a_words.is_contiguous()
     out = torch.zeros(128, n_cols, device=a_words.device, dtype=F32)
-    _lib.call("vgpt_debug_umma_probe_ts", _p(a_words), a_words.shape[1], _p(b_img), b_img.numel(),
+    _lib.call_probe("vgpt_debug_umma_probe_ts", _p(a_words), a_words.shape[1], _p(b_img), b_img.numel(),
               ctypes.c_uint64(b_desc_base), ctypes.c_uint32(idesc), k_steps, ctypes.c_uint32(b_step_bytes), _p(out),
               n_cols, _stream())
     return out

@@ -78,11 +78,6 @@ class LVMPipeline:
             vae = AutoencoderKL.from_pretrained(vae_path if vae_path is not None else "stabilityai/sdxl-vae")
         return cls(vae, model, processor)
 
-    def merge_lora(self, lora_path: str):
-        """pipeline.py:97-101 (peft).  Out of scope here: merge the adapter into the checkpoint with the
-        reference tooling and load the merged weights (same state-dict names)."""
-        raise NotImplementedError("merge_lora is out of scope (DESIGN.md section 8): load an already merged checkpoint")
-
     def to(self, device: Union[str, torch.device]):
         if isinstance(device, str):
             device = torch.device(device)
@@ -117,15 +112,6 @@ class LVMPipeline:
         if isinstance(data, list):
             return [x.to(self.device) for x in data]
         return data.to(self.device)
-
-    def enable_model_cpu_offload(self):
-        raise NotImplementedError("CPU offload is out of scope: a B200 holds the full model (SURVEY.md 2b)")
-
-    def disable_model_cpu_offload(self):
-        self.model_cpu_offload = False
-        self.model.to(self.device)
-        if self.vae is not None:
-            self.vae.to(self.device)
 
     # ---- latent-space next-clip prediction (the hot path) ----------------------------------------
     @torch.no_grad()

@@ -25,32 +25,6 @@ class LVMScheduler:
         self.sigma = t / (t + time_shifting_factor - time_shifting_factor * t)
         self.record_velocity: Optional[list] = None     # tests: per-step velocity of the cond half
 
-    # ---- cache-cropping helpers of the reference (scheduler.py:132-159; unused by its own __call__, kept
-    # for callers that do use them: pure slicing, no arithmetic) --------------------------------------
-    def crop_kv_cache(self, past_key_values, num_tokens_for_img):
-        from transformers.cache_utils import DynamicCache
-        cropped = tuple((k[..., :-(num_tokens_for_img + 1), :], v[..., :-(num_tokens_for_img + 1), :])
-                        for k, v in (layer[:2] for layer in past_key_values))
-        return DynamicCache.from_legacy_cache(cropped) if hasattr(DynamicCache, "from_legacy_cache") else cropped
-
-    def crop_position_ids_for_cache(self, position_ids, num_tokens_for_img):
-        if isinstance(position_ids, list):
-            for i in range(len(position_ids)):
-                position_ids[i] = position_ids[i][:, -(num_tokens_for_img + 1):]
-            return position_ids
-        return position_ids[:, -(num_tokens_for_img + 1):]
-
-    def crop_attention_mask_for_cache(self, attention_mask, num_tokens_for_img):
-        if isinstance(attention_mask, list):
-            return [x[..., -(num_tokens_for_img + 1):, :] for x in attention_mask]
-        return attention_mask[..., -(num_tokens_for_img + 1):, :]
-
-    def crop_cache(self, cache, num_tokens_for_img):
-        for i in range(len(cache.key_cache)):
-            cache.key_cache[i] = cache.key_cache[i][..., :-(num_tokens_for_img + 1), :]
-            cache.value_cache[i] = cache.value_cache[i][..., :-(num_tokens_for_img + 1), :]
-        return cache
-
     # step scalars exactly as the reference forms them (fp32 tensor arithmetic, scheduler.py:178-204)
     def _scalars(self, i: int):
         sigma, sigma_next = self.sigma[i], self.sigma[i + 1]
