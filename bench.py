@@ -392,7 +392,9 @@ def run_ours(args, rank, world, local_rank):
     e2e = videos * tokens_per_clip * args.steps / dt_e2e
     step_fl, prefill_fl, clip_fl = algorithmic_flops(dims, n_ctx, n_gen, block, euler)
     e = model.engine()
-    launches = args.steps * rounds * (e.launches_per_prefill + euler * (e.launches_per_predict + 1))
+    # per Euler step: the engine's kernels (the scheduler update rides in the final-layer kernel on one GPU; a separate
+    # vgpt_cfg_euler launch per step in sequence-parallel groups and CFG-branch pairs)
+    launches = args.steps * rounds * (e.launches_per_prefill + euler * (e.launches_per_predict + (1 if (sp_size > 1 or cfg_split) else 0)))
     if vids_rank:
         launches *= vids_rank // args.batch
 

@@ -114,19 +114,25 @@ int vgpt_timestep_sinusoid(const float* t, const float* freqs, void* out, int n,
 int vgpt_linear_small(const void* in, const void* W, const void* bias, void* out, int n, int N, int K,
                       int pre_silu, int post_silu, void* stream);
 
-/* FinalLayer + unpatchify (LVM/model.py:79-83, 255-265, 478-486): for latent j the image-token
- * rows hidden[lat_row0[j] .. +tokens) -> pred[j, C, lat_h, lat_w]; mod[j] = [shift | scale]. */
-int vgpt_final_layer(const void* hidden, int hidden_size, const int32_t* lat_row0, const void* mod,
-                     const void* w, const void* bias, void* pred, int n_lat, int channels, int lat_h,
-                     int lat_w, void* stream);
+/* [llm.norm ->] FinalLayer + unpatchify [-> scheduler update] (OmniGen/transformer.py:214, LVM/model.py:79-83,
+ * 255-265, 478-486, LVM/scheduler.py:178-204): for latent j the image-token rows hidden[lat_row0[j] .. +tokens)
+ * -> pred[j, C, lat_h, lat_w]; mod[j] = [shift | scale].  norm_weight != NULL: `hidden` holds the RAW residual
+ * stream and the final Phi3RMSNorm (weight norm_weight, eps rms_eps) is applied first.  z_euler != NULL: the step's
+ * x1 -> v / CFG / Euler update of vgpt_cfg_euler is applied to z_euler right behind the prediction (latents laid out
+ * [cond | uncond], scalars_dev = device float[3] {1 - sigma, d sigma, guidance}; vel_out optional) -- one launch
+ * instead of three at the end of every Euler step, same bits. */
+int vgpt_final_layer(const void* hidden, int hidden_size, const void* norm_weight, float rms_eps,
+                     const int32_t* lat_row0, const void* mod, const void* w, const void* bias, void* pred,
+                     int n_lat, int channels, int lat_h, int lat_w, void* z_euler, void* vel_out,
+                     const float* scalars_dev, int use_cfg, int x1_mode, void* stream);
 
 /* Row-driven FinalLayer + unpatchify for row-sharded plans: local row r is an image token of
  * latent row_a[r], patch row_b[r] when row_kind[r] == VGPT_ROW_NOISY_PATCH (other rows are
  * skipped); the 16 outputs per row are stored into every destination preds[0..n_preds) (own +
- * peers), replacing the hidden-state all-gather of LVM/model.py:466-474. */
-int vgpt_final_layer_rows(const void* hidden, int rows, int hidden_size, const int32_t* row_kind,
-                          const int32_t* row_a, const int32_t* row_b, const void* mod, const void* w,
-                          const void* bias, void* const* preds, int n_preds, int channels, int lat_h,
+ * peers), replacing the hidden-state all-gather of LVM/model.py:466-474.  norm_weight as in vgpt_final_layer. */
+int vgpt_final_layer_rows(const void* hidden, int rows, int hidden_size, const void* norm_weight, float rms_eps,
+                          const int32_t* row_kind, const int32_t* row_a, const int32_t* row_b, const void* mod,
+                          const void* w, const void* bias, void* const* preds, int n_preds, int channels, int lat_h,
                           int lat_w, void* stream);
 
 /* Peer memory for the sequence-parallel path (one process per GPU, NVLink/NVSwitch).  These five

@@ -139,8 +139,12 @@ def rope_kv_append_peers(qkv, row_pos, row_slot, table, k_pool_ptrs, v_pool_ptrs
         rope_kv_append(qkv, row_pos, row_slot, table, k, v, heads, head_dim)
 
 
-def final_layer_rows(hidden, row_kind, row_a, row_b, mod, w, bias, pred_ptrs, n_preds: int, lat_h: int, lat_w: int):
+def final_layer_rows(hidden, row_kind, row_a, row_b, mod, w, bias, pred_ptrs, n_preds: int, lat_h: int, lat_w: int,
+                     norm_weight=None, rms_eps: float = 0.0):
     _log("final_layer_rows")
+    if norm_weight is not None:
+        hidden = rmsnorm(hidden, norm_weight, rms_eps)
+        calls.pop()
     rows, hs = hidden.shape
     C, pw = 4, lat_w // 2
     preds = [_from_ptr(int(pred_ptrs[g]), hidden.dtype) for g in range(n_preds)]
@@ -241,8 +245,11 @@ def _final_rows(x, shift, scale, w, bias):
     return F.linear(y, w, bias)                      # [tokens, 16], feature order (p, q, c)
 
 
-def final_layer(hidden, lat_row0, mod, w, bias, pred):
+def final_layer(hidden, lat_row0, mod, w, bias, pred, norm_weight=None, rms_eps: float = 0.0, euler=None):
     _log("final_layer")
+    if norm_weight is not None:
+        hidden = rmsnorm(hidden, norm_weight, rms_eps)
+        calls.pop()
     n_lat, C, lat_h, lat_w = pred.shape
     hs = hidden.shape[1]
     tokens = (lat_h // 2) * (lat_w // 2)
@@ -253,6 +260,10 @@ def final_layer(hidden, lat_row0, mod, w, bias, pred):
         y = _final_rows(hidden[r0:r0 + tokens], mod[j, :hs], mod[j, hs:], w, bias)
         y = y.reshape(lat_h // 2, lat_w // 2, 2, 2, C)
         pred[j] = torch.einsum("hwpqc->chpwq", y).reshape(C, lat_h, lat_w).to(pred.dtype)
+    if euler is not None:
+        z, sc, use_cfg, x1, vel = euler
+        cfg_euler(z, pred, bool(use_cfg), bool(x1), scalars_dev=sc, vel_out=vel)
+        calls.pop()
     return pred
 
 

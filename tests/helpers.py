@@ -54,3 +54,47 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
 def cosine(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().flatten(), b.double().flatten()
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+class FakeVAE:
+    """Stands in for diffusers' AutoencoderKL (outside the hot path): 8x8 average pooling of the
+    three colour channels into 4 latent channels and its nearest-neighbour inverse; records what
+    it is asked to decode."""
+    class config:
+        shift_factor = None
+        scaling_factor = 0.5
+
+    def __init__(self):
+        self.decoded = []
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def encode(self, x):
+        lat = torch.nn.functional.avg_pool2d(x, 8)
+        lat = torch.cat([lat, lat.mean(1, keepdim=True)], 1)
+
+        class _D:
+            class latent_dist:
+                @staticmethod
+                def sample():
+                    return lat.clone()
+        return _D
+
+    def decode(self, lat):
+        self.decoded.append(lat.clone())
+        img = torch.nn.functional.interpolate(lat[:, :3], scale_factor=8, mode="nearest")
+
+        class _S:
+            sample = img
+        return _S
+
+
+def random_pil(seed, size=64):
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    return Image.fromarray(rng.integers(0, 256, (size, size, 3), dtype=np.uint8))

@@ -10,6 +10,8 @@ import torch
 from oracle import model_oracle as mo, processor_oracle as po, scheduler_oracle as so
 from videogpt_b200 import synth
 
+from helpers import FakeVAE as _FakeVAE, random_pil as _pil
+
 TOL = 2e-5
 
 
@@ -156,50 +158,6 @@ def test_batched_videos_reproduce_the_oracle_and_the_per_video_runs(emu, guidanc
     assert _maxerr([x for g in got for x in g], want[:n_videos * n_gen]) < TOL
 
 
-class _FakeVAE:
-    """Stands in for diffusers' AutoencoderKL (outside the hot path): 8x8 average pooling of the
-    three colour channels into 4 latent channels and its nearest-neighbour inverse; records what
-    it is asked to decode."""
-    class config:
-        shift_factor = None
-        scaling_factor = 0.5
-
-    def __init__(self):
-        self.decoded = []
-
-    def eval(self):
-        return self
-
-    def to(self, *a, **k):
-        return self
-
-    def encode(self, x):
-        lat = torch.nn.functional.avg_pool2d(x, 8)
-        lat = torch.cat([lat, lat.mean(1, keepdim=True)], 1)
-
-        class _D:
-            class latent_dist:
-                @staticmethod
-                def sample():
-                    return lat.clone()
-        return _D
-
-    def decode(self, lat):
-        self.decoded.append(lat.clone())
-        img = torch.nn.functional.interpolate(lat[:, :3], scale_factor=8, mode="nearest")
-
-        class _S:
-            sample = img
-        return _S
-
-
-def _pil(seed, size=64):
-    import numpy as np
-    from PIL import Image
-    rng = np.random.default_rng(seed)
-    return Image.fromarray(rng.integers(0, 256, (size, size, 3), dtype=np.uint8))
-
-
 def test_pipeline_call_one_frame_at_a_time_reproduces_the_oracle(emu):
     """``LVMPipeline.__call__`` (reference pipeline.py:136-343): two input images, two generated
     frames; the latent handed to the VAE decoder for every generated frame must be what the
@@ -229,6 +187,41 @@ def test_pipeline_call_one_frame_at_a_time_reproduces_the_oracle(emu):
                                    mk, num_steps=2, prediction_type="v")[:1]
         got = vae.decoded[2 + k] * vae.config.scaling_factor
         assert _maxerr([got], [want]) < TOL
+
+
+def test_frame_block_autoregressive_entry_point_reproduces_the_oracle(emu):
+    """``LVMPipeline.prompt_condition_frame_block_autoregressive_inference`` (reference pipeline.py:346-595, the entry
+    point of the shipped inference script): two rounds of two generated frames from three context images through a
+    fake VAE.  Every latent handed to the VAE decoder must be what the oracle's frame-block sampler gives for the same
+    context latents (re-encoded from the PIL frames of the previous round, like the reference) and the same seeded noise;
+    the second round also exercises the ``max_frame_window`` cut (pipeline.py:421-422)."""
+    m, sd = _model()
+    pipe = _pipe(m)
+    pipe.vae = vae = _FakeVAE()
+    imgs = [_pil(11), _pil(12), _pil(13)]
+    out = pipe.prompt_condition_frame_block_autoregressive_inference(
+        input_images=imgs, height=64, width=64, gen_nums=[2, 2], num_inference_steps=2, img_guidance_scale=1.5,
+        use_input_image_size_as_output=True, dtype=torch.float32, seed=9, prediction_type="x1",
+        clean_image_noise_level=0.0, max_frame_window=6)
+    assert len(out) == 3 + 2 + 2 and all(im.size == (64, 64) for im in out)
+    assert len(vae.decoded) == 7                     # 3 context reconstructions, then 2 + 2 generated frames
+    frames = list(imgs)
+    for k in range(2):
+        if k == 1:
+            frames = out[:5][-4:]                    # window 6 - 2 generated = the last 4 frames so far
+        ctx = [pipe.vae_encode(pipe.processor.process_image(im).unsqueeze(0), torch.float32) for im in frames]
+        d = po.frame_block_inputs(len(ctx), 2, 64, 64, True, 1)
+        mk = dict(input_ids=d["input_ids"], input_img_latents=ctx, input_image_sizes=d["input_image_sizes"],
+                  attention_mask=d["attention_mask"], position_ids=d["position_ids"],
+                  denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
+                  use_img_cfg=True)
+        g = torch.Generator().manual_seed(9)
+        noise = [torch.randn(1, 4, 8, 8, generator=g) for _ in range(2)]
+        with torch.no_grad():
+            want = so.euler_sample(noise * 2, lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                                   mk, num_steps=2, prediction_type="x1")[:2]
+        got = [vae.decoded[3 + 2 * k + i] * vae.config.scaling_factor for i in range(2)]
+        assert _maxerr(got, want) < TOL, k
 
 
 def test_pipeline_call_without_input_images_generates_unconditionally(emu):

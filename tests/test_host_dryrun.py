@@ -41,7 +41,7 @@ class StubOps:
     def rmsnorm(self, x, w, eps, out=None):
         self._log("rmsnorm"); assert out.shape == x.shape and w.numel() == x.shape[1]; return out
 
-    def gemm(self, a, w, out=None, residual=None, epilogue=0, block_n=0):
+    def gemm(self, a, w, out=None, residual=None, epilogue=0, block_n=0, tail_mode=-1):
         self._log("gemm")
         n_out = w.shape[0] // 2 if epilogue == 2 else w.shape[0]
         assert a.shape[1] == w.shape[1] and out.shape == (a.shape[0], n_out)
@@ -59,8 +59,11 @@ class StubOps:
         assert int(seqs[:, 1].sum()) == q.shape[0] and int(seqs[:, 1].max()) == max_q_rows
         return out
 
-    def final_layer(self, hidden, lat_row0, mod, w, bias, pred):
-        self._log("final_layer"); assert mod.shape[0] == pred.shape[0]; pred.zero_(); return pred
+    def final_layer(self, hidden, lat_row0, mod, w, bias, pred, norm_weight=None, rms_eps=0.0, euler=None):
+        self._log("final_layer"); assert mod.shape[0] == pred.shape[0] and norm_weight.numel() == hidden.shape[1]
+        if euler is not None:
+            self._log("euler_fused"); assert euler[0].shape == pred.shape and euler[1].numel() == 3
+        pred.zero_(); return pred
 
     def cfg_euler(self, z, pred, use_cfg, x1_mode, *a, **k):
         self._log("cfg_euler"); assert z.shape == pred.shape; return z
@@ -122,14 +125,14 @@ def test_scheduler_engine_loop_call_sequence(dry):
     L = 2
     e = m._engine
     assert dry.calls.count("mask_from_codes") == 2                      # mask validated once per row
-    assert dry.calls.count("cfg_euler") == 3
+    assert dry.calls.count("cfg_euler") == 0 and dry.calls.count("euler_fused") == 3     # the update rides in the final kernel
     assert dry.calls.count("final_layer") == 3
     assert dry.calls.count("attention") == (L - 1) + 3 * L              # prefill skips the last layer's attention
     assert dry.calls.count("gemm") == 4 * (L - 1) + 1 + 3 * 4 * L
     assert dry.calls.count("rope_kv_append") == L + 3 * L
     n_predict = dry.calls.count("timestep_sinusoid")
-    per_predict = (len(dry.calls) - dry.calls.index("timestep_sinusoid")) // n_predict
-    assert e.launches_per_predict + 1 == per_predict                    # + the scheduler update
+    step_calls = [c for c in dry.calls[dry.calls.index("timestep_sinusoid"):] if c != "euler_fused"]
+    assert e.launches_per_predict == len(step_calls) // n_predict       # the scheduler update is part of the final kernel
     # a second clip with the same layout reuses the plan (no new mask check), new context -> new prefill
     before = len(dry.calls)
     mk2 = dict(mk); mk2["input_img_latents"] = [x.clone() for x in mk["input_img_latents"]]
@@ -195,7 +198,7 @@ class StubOpsSP(StubOps):
         self._log("rope_kv_append_peers")
         assert row_pos.numel() == row_slot.numel() == qkv.shape[0] and len(k_ptrs) == len(v_ptrs) == n_pools
 
-    def final_layer_rows(self, hidden, kind, a, b, mod, w, bias, pred_ptrs, n_preds, lat_h, lat_w):
+    def final_layer_rows(self, hidden, kind, a, b, mod, w, bias, pred_ptrs, n_preds, lat_h, lat_w, norm_weight=None, rms_eps=0.0):
         self._log("final_layer_rows")
         assert kind.numel() == hidden.shape[0] and len(pred_ptrs) == n_preds
 

@@ -85,8 +85,8 @@ def test_gemm_swiglu_matches_phi3_mlp(ops, M, I, K, tail_mode, block_n):
     x, wgu = _rand((M, K), 7), _rand((2 * I, K), 8, 0.03)
     packed = ops.pack_gate_up(wgu)
     # packing is a pure row permutation
-    blk = torch.arange(2 * I, device=DEV).view(-1, 64)
-    src = torch.where(blk % 64 < 32, (blk // 64) * 32 + blk % 64, I + (blk // 64) * 32 + blk % 64 - 32)
+    blk = torch.arange(2 * I, device=DEV).view(-1, 32)          # [gate x 16 | up x 16] per 32 packed rows
+    src = torch.where(blk % 32 < 16, (blk // 32) * 16 + blk % 32, I + (blk // 32) * 16 + blk % 32 - 16)
     assert torch.equal(packed, wgu[src.view(-1)])
     h = ops.gemm(x, packed, epilogue=ops.EPI_SWIGLU, block_n=block_n, tail_mode=tail_mode)
     gu = (x.float() @ wgu.float().t()).to(BF)
@@ -280,6 +280,41 @@ def test_final_layer_and_unpatchify(ops):
         assert _rel(pred[j:j + 1], want) < 8e-3, j
         y32 = mo.final_layer({k: v.float() for k, v in sd.items()}, x.float(), c[j:j + 1].float())
         assert _rel(pred[j:j + 1], mo.unpatchify(y32, lat_h, lat_w, cfg)) < 2e-2, j
+
+
+@pytest.mark.parametrize("mode", ["x1", "v"])
+@pytest.mark.parametrize("use_cfg", [True, False])
+def test_final_layer_fused_with_norm_and_scheduler_update_is_bit_exact(ops, mode, use_cfg):
+    """One launch (final RMSNorm + FinalLayer + unpatchify + x1 -> v / CFG / Euler) == the three kernels it replaces at
+    the end of every Euler step, bit for bit: prediction, updated latents and applied velocity."""
+    d = synth.REDUCED
+    sd = {k: v.to(DEV, BF) for k, v in synth.init_state_dict(d, seed=0, with_pos_embed=False).items()}
+    lat_h, lat_w, n_lat = 8, 12, 4
+    n_tok = (lat_h // 2) * (lat_w // 2)
+    rows = 3 + n_lat * (n_tok + 2)
+    hidden = _rand((rows, d.hidden_size), 60, 2.0)
+    norm_w = (1.0 + 0.1 * _rand((d.hidden_size,), 61).float()).to(BF)
+    mod = _rand((n_lat, 2 * d.hidden_size), 62, 0.5)
+    row0 = torch.tensor([3 + j * (n_tok + 2) + 2 for j in range(n_lat)], dtype=torch.int32, device=DEV)
+    w, b = sd["final_layer.linear.weight"], sd["final_layer.linear.bias"]
+    z0 = _rand((n_lat, 4, lat_h, lat_w), 63)
+    if use_cfg:
+        z0[n_lat // 2:] = z0[:n_lat // 2]
+    scal = torch.tensor([0.7, 0.02, 1.5], dtype=torch.float32, device=DEV)
+    n_half = n_lat // 2 if use_cfg else n_lat
+    # three kernels
+    pred_a, z_a, vel_a = torch.zeros_like(z0), z0.clone(), torch.zeros_like(z0[:n_half])
+    ops.final_layer(ops.rmsnorm(hidden, norm_w, 1e-5), row0, mod, w, b, pred_a)
+    ops.cfg_euler(z_a, pred_a, use_cfg, mode == "x1", scalars_dev=scal, vel_out=vel_a)
+    # norm fused only
+    pred_b = torch.zeros_like(z0)
+    ops.final_layer(hidden, row0, mod, w, b, pred_b, norm_weight=norm_w, rms_eps=1e-5)
+    assert torch.equal(pred_b, pred_a)
+    # everything in one launch
+    pred_c, z_c, vel_c = torch.zeros_like(z0), z0.clone(), torch.zeros_like(z0[:n_half])
+    ops.final_layer(hidden, row0, mod, w, b, pred_c, norm_weight=norm_w, rms_eps=1e-5, euler=(z_c, scal, use_cfg, mode == "x1", vel_c))
+    torch.cuda.synchronize()
+    assert torch.equal(pred_c, pred_a) and torch.equal(z_c, z_a) and torch.equal(vel_c, vel_a)
 
 
 @pytest.mark.parametrize("mode", ["x1", "v"])

@@ -14,7 +14,7 @@ import torch
 from oracle import model_oracle as mo, processor_oracle as po, scheduler_oracle as so
 from videogpt_b200 import synth
 
-from helpers import FakeTokenizer, cosine, load_npz, rel_l2
+from helpers import FakeTokenizer, FakeVAE, cosine, load_npz, random_pil, rel_l2
 
 pytestmark = pytest.mark.gpu
 DEV, BF = "cuda", torch.bfloat16
@@ -241,3 +241,128 @@ def test_replace_attention_operator_seam():
     bad = mo.additive_mask(anti[None].expand(B, L, L), BF)
     with pytest.raises(ValueError):
         holder.attn(x, attention_mask=bad, position_ids=pos)
+
+
+# ---------------------------------------------------------------------------------------------
+# the one-frame-at-a-time path (LVM.forward_with_cfg, reference LVM/model.py:330-397, 503-516) and the
+# two user entry points of the pipeline (reference LVM/pipeline.py:136-343, 346-595) on the GPU
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("geom", [(2, 64, 64, 1), (3, 48, 80, 4), (4, 256, 256, 1)])
+@pytest.mark.parametrize("pt", ["x1", "v"])
+def test_single_frame_forward_with_cfg_matches_oracle_bf16(geom, pt):
+    """``pipeline.__call__``'s layout: condition tokens (cached prefix) + [time | image] rows, the 1-token
+    unconditional row left-padded by the reference.  Same gates as the next-clip path."""
+    from videogpt_b200 import LVMScheduler
+    n_ctx, H, W, sp = geom
+    steps = 4
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    d = po.single_frame_inputs(n_ctx, H, W, True, sp)
+    lat = synth.synthetic_latents(n_ctx + 1, H, W, seed=7)
+
+    def mk_for(dtype):
+        return dict(input_ids=d["input_ids"].to(DEV), input_img_latents=[x.to(DEV, dtype) for x in lat[:n_ctx]],
+                    input_image_sizes=d["input_image_sizes"], attention_mask=d["attention_mask"].to(DEV),
+                    position_ids=d["position_ids"].to(DEV), img_cfg_scale=1.5, use_img_cfg=True, use_kv_cache=False,
+                    offload_model=False)
+
+    def oracle(dtype, backend=None):
+        import contextlib
+        w = {k: v.to(DEV, dtype) for k, v in sd.items()}
+        rec = []
+        ctx = contextlib.nullcontext()
+        if backend is not None:
+            from torch.nn.attention import SDPBackend, sdpa_kernel
+            ctx = sdpa_kernel(getattr(SDPBackend, backend))
+        with torch.no_grad(), ctx:
+            out = so.euler_sample(torch.cat([lat[n_ctx]] * 2, 0).to(DEV, dtype),
+                                  lambda z, t, **kw: mo.single_frame_forward_with_cfg(w, _oracle_cfg(dims), z, t, **kw),
+                                  mk_for(dtype), num_steps=steps, prediction_type=pt, record=rec)
+        return out[:1], [r[:1] for r in rec]
+
+    want, want_vel = oracle(BF)
+    _, alt_vel = oracle(BF, "MATH")
+    true, true_vel = oracle(torch.float32)
+    sch = LVMScheduler(num_steps=steps)
+    sch.record_velocity = []
+    got = sch(torch.cat([lat[n_ctx]] * 2, 0).to(DEV, BF), model.forward_with_cfg, mk_for(BF), use_kv_cache=False,
+              prediction_type=pt)
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], got[1])                                     # cond / uncond duplicates stay identical (q7)
+    for i in range(steps):
+        floor, floor_bb = rel_l2(want_vel[i], true_vel[i]), rel_l2(alt_vel[i], want_vel[i])
+        err, err_true = rel_l2(sch.record_velocity[i], want_vel[i]), rel_l2(sch.record_velocity[i], true_vel[i])
+        assert err <= _gate(floor, floor_bb), f"step {i}: {err:.3e} (bf16-vs-fp32 {floor:.3e}, bf16-vs-bf16 {floor_bb:.3e})"
+        assert err_true <= 1.15 * floor + 1e-3, f"step {i}: vs fp32 oracle {err_true:.3e} (reference bf16: {floor:.3e})"
+        if i == 0 or pt == "v":
+            assert err <= VEL_TOL, f"step {i}: velocity rel-L2 {err:.3e}"
+    assert cosine(got[:1], want) >= COS_TOL
+
+
+def _pipeline(model):
+    from videogpt_b200 import LVMPipeline, LVMProcessor
+    pipe = LVMPipeline(None, model, LVMProcessor(FakeTokenizer()), device=DEV)
+    pipe.vae = FakeVAE()
+    return pipe
+
+
+def test_pipeline_frame_block_autoregressive_entry_point_on_gpu():
+    """``prompt_condition_frame_block_autoregressive_inference`` (reference pipeline.py:346-595, what the shipped
+    inference script calls): PIL frames in, two rounds of two frames out through a fake VAE; every latent handed to
+    the decoder against the oracle's frame-block sampler in bf16 on the same context latents and seeded noise."""
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    pipe = _pipeline(model)
+    vae = pipe.vae
+    imgs = [random_pil(11), random_pil(12), random_pil(13)]
+    out = pipe.prompt_condition_frame_block_autoregressive_inference(
+        input_images=imgs, height=64, width=64, gen_nums=[2, 2], num_inference_steps=3, img_guidance_scale=1.5,
+        use_input_image_size_as_output=True, dtype=BF, seed=9, prediction_type="x1", clean_image_noise_level=0.0,
+        max_frame_window=6)
+    assert len(out) == 7 and len(vae.decoded) == 7
+    w = {k: v.to(DEV, BF) for k, v in sd.items()}
+    frames = list(imgs)
+    for k in range(2):
+        if k == 1:
+            frames = out[:5][-4:]
+        ctx = [pipe.vae_encode(pipe.processor.process_image(im).unsqueeze(0).to(DEV), BF) for im in frames]
+        d = po.frame_block_inputs(len(ctx), 2, 64, 64, True, 1)
+        mk = dict(input_ids=d["input_ids"].to(DEV), input_img_latents=ctx, input_image_sizes=d["input_image_sizes"],
+                  attention_mask=d["attention_mask"].to(DEV), position_ids=d["position_ids"].to(DEV),
+                  denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
+                  use_img_cfg=True)
+        g = torch.Generator(device=DEV).manual_seed(9)
+        noise = [torch.randn(1, 4, 8, 8, device=DEV, generator=g).to(BF) for _ in range(2)]
+        with torch.no_grad():
+            want = so.euler_sample(noise * 2, lambda z, t, **kw: mo.frame_block_forward_with_cfg(w, _oracle_cfg(dims), z, t, **kw),
+                                   mk, num_steps=3, prediction_type="x1")[:2]
+        got = [vae.decoded[3 + 2 * k + i].to(DEV) * vae.config.scaling_factor for i in range(2)]
+        assert cosine(torch.cat(got, 0), torch.cat(want, 0).float()) >= COS_TOL, k
+
+
+def test_pipeline_call_one_frame_at_a_time_on_gpu():
+    """``LVMPipeline.__call__`` (reference pipeline.py:136-343) on the GPU through a fake VAE."""
+    dims = synth.REDUCED
+    model, sd = _build(dims)
+    pipe = _pipeline(model)
+    vae = pipe.vae
+    imgs = [random_pil(1), random_pil(2)]
+    out = pipe(input_images=imgs, height=64, width=64, gen_num=2, num_inference_steps=3, img_guidance_scale=1.5,
+               use_input_image_size_as_output=True, dtype=BF, seed=5, prediction_type="v", clean_image_noise_level=0.0)
+    assert len(out) == 4 and len(vae.decoded) == 4
+    w = {k: v.to(DEV, BF) for k, v in sd.items()}
+    ctx = [pipe.vae_encode(pipe.processor.process_image(im).unsqueeze(0).to(DEV), BF) for im in imgs]
+    for k in range(2):
+        if k == 1:
+            ctx.append(pipe.vae_encode(pipe.processor.process_image(out[2]).unsqueeze(0).to(DEV), BF))
+        d = po.single_frame_inputs(len(ctx), 64, 64, True, 1)
+        mk = dict(input_ids=d["input_ids"].to(DEV), input_img_latents=ctx, input_image_sizes=d["input_image_sizes"],
+                  attention_mask=d["attention_mask"].to(DEV), position_ids=d["position_ids"].to(DEV), img_cfg_scale=1.5,
+                  use_img_cfg=True)
+        noise = torch.randn(1, 4, 8, 8, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5)).to(BF)
+        with torch.no_grad():
+            want = so.euler_sample(torch.cat([noise] * 2, 0),
+                                   lambda z, t, **kw: mo.single_frame_forward_with_cfg(w, _oracle_cfg(dims), z, t, **kw),
+                                   mk, num_steps=3, prediction_type="v")[:1]
+        got = vae.decoded[2 + k].to(DEV) * vae.config.scaling_factor
+        assert cosine(got, want.float()) >= COS_TOL, k

@@ -21,7 +21,7 @@ for mode in (0, 1, 2, 3):
 # CTA pairs (the GEMM's instruction): 74 clusters
 out2 = torch.zeros(74, device="cuda")
 row = []
-for N in (32, 64, 128, 192, 256):
+for N in (16, 32, 48, 64, 128, 192, 224, 256):
     _lib.call_probe("vgpt_debug_umma_rate", 4, N, 4096, 1, 0, 74, ctypes.c_void_p(out2.data_ptr()), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     row.append(f"N={N}: {out2.mean().item():6.1f}")

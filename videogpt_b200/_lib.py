@@ -23,7 +23,7 @@ SIGNATURES = {
     "vgpt_rope_table": [P, P, I, I, P],
     "vgpt_rope_kv_append": [P, P, P, P, P, P, I, I, I, P],
     "vgpt_rope_kv_append_peers": [P, P, P, P, P, P, I, I, I, I, P],
-    "vgpt_final_layer_rows": [P, I, I, P, P, P, P, P, P, P, I, I, I, I, P],
+    "vgpt_final_layer_rows": [P, I, I, P, F, P, P, P, P, P, P, P, I, I, I, I, P],
     "vgpt_peer_alloc": [P, c_uint64],
     "vgpt_peer_free": [P],
     "vgpt_peer_export": [P, P],
@@ -35,7 +35,7 @@ SIGNATURES = {
     "vgpt_embed_assemble": [P, I, I, P, P, P, P, P, P, P, I, I, I, P, P, P, P, P, P],
     "vgpt_timestep_sinusoid": [P, P, P, I, I, P],
     "vgpt_linear_small": [P, P, P, P, I, I, I, I, I, P],
-    "vgpt_final_layer": [P, I, P, P, P, P, P, I, I, I, I, P],
+    "vgpt_final_layer": [P, I, P, F, P, P, P, P, P, I, I, I, I, P, P, P, I, I, P],
     "vgpt_cfg_euler": [P, P, P, I, I, I, F, F, F, P, P],
     "vgpt_cfg_combine": [P, I, F, P],
     "vgpt_mask_from_codes": [P, P, P, I, I, P],

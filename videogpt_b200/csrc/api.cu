@@ -38,12 +38,12 @@ int vgpt_rope_kv_append_peers(void* qkv, const int32_t* row_pos, const int32_t* 
   return vgpt::rope_kv_append(qkv, row_pos, row_slot, table, k_pools, v_pools, n_pools, rows, H, D,
                               VGPT_PAGE_TOKENS, S(stream));
 }
-int vgpt_final_layer_rows(const void* hidden, int rows, int hidden_size, const int32_t* row_kind,
-                          const int32_t* row_a, const int32_t* row_b, const void* mod, const void* w,
-                          const void* bias, void* const* preds, int n_preds, int channels, int lat_h,
+int vgpt_final_layer_rows(const void* hidden, int rows, int hidden_size, const void* norm_weight, float rms_eps,
+                          const int32_t* row_kind, const int32_t* row_a, const int32_t* row_b, const void* mod,
+                          const void* w, const void* bias, void* const* preds, int n_preds, int channels, int lat_h,
                           int lat_w, void* stream) {
-  return vgpt::final_layer_rows(hidden, rows, hidden_size, row_kind, row_a, row_b, mod, w, bias, preds,
-                                n_preds, channels, lat_h, lat_w, S(stream));
+  return vgpt::final_layer_rows(hidden, rows, hidden_size, norm_weight, rms_eps, row_kind, row_a, row_b, mod, w, bias,
+                                preds, n_preds, channels, lat_h, lat_w, S(stream));
 }
 int vgpt_peer_alloc(void** out, uint64_t bytes) { return vgpt::peer_alloc(out, bytes); }
 int vgpt_peer_free(void* p) { return vgpt::peer_free(p); }
@@ -89,11 +89,12 @@ int vgpt_linear_small(const void* in, const void* W, const void* bias, void* out
                       int pre_silu, int post_silu, void* stream) {
   return vgpt::linear_small(in, W, bias, out, n, N, K, pre_silu, post_silu, S(stream));
 }
-int vgpt_final_layer(const void* hidden, int hidden_size, const int32_t* lat_row0, const void* mod,
-                     const void* w, const void* bias, void* pred, int n_lat, int channels, int lat_h,
-                     int lat_w, void* stream) {
-  return vgpt::final_layer(hidden, hidden_size, lat_row0, mod, w, bias, pred, n_lat, channels, lat_h,
-                           lat_w, S(stream));
+int vgpt_final_layer(const void* hidden, int hidden_size, const void* norm_weight, float rms_eps,
+                     const int32_t* lat_row0, const void* mod, const void* w, const void* bias, void* pred,
+                     int n_lat, int channels, int lat_h, int lat_w, void* z_euler, void* vel_out,
+                     const float* scalars_dev, int use_cfg, int x1_mode, void* stream) {
+  return vgpt::final_layer(hidden, hidden_size, norm_weight, rms_eps, lat_row0, mod, w, bias, pred, n_lat, channels,
+                           lat_h, lat_w, z_euler, vel_out, scalars_dev, use_cfg, x1_mode, S(stream));
 }
 int vgpt_cfg_euler(void* z, const void* pred, void* vel_out, int half_numel, int use_cfg, int x1_mode,
                    float one_minus_sigma, float dsigma, float guidance, const float* scalars_dev,

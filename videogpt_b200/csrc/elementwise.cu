@@ -208,10 +208,13 @@ int rope_kv_append(void* qkv, const int32_t* row_pos, const int32_t* row_slot, c
 //   kind 2: x_embedder(z[a]) patch b + pos_embed[b]        (noisy latent; PatchEmbedMR 138-154)
 //   kind 3: input_x_embedder(ctx[a]) patch b + pos_embed[b] (context latent)
 // Conv2d(k=2,s=2) == per-patch linear over the (c,ph,pw)-flattened 16-vector (K=16: FMA, not
-// tensor cores); conv output (+bias) rounded to bf16, then + pos_embed rounded to bf16.
+// tensor cores); conv output (+bias) rounded to bf16, then + pos_embed rounded to bf16.  One CTA per 8 rows: a thread keeps
+// the 16 x 8 weights of its output chunk in registers across the rows (one CTA per row read the 98 KB weight 2064 times).
 // ---------------------------------------------------------------------------------------------
+constexpr int kEmbedRows = 8;      // rows per CTA: the 98 KB conv weight is read once per 8 rows instead of once per row
+
 __global__ void __launch_bounds__(kRowThreads)
-embed_assemble_kernel(__nv_bfloat16* __restrict__ hidden, int hs, const int32_t* __restrict__ kind,
+embed_assemble_kernel(__nv_bfloat16* __restrict__ hidden, int rows, int hs, const int32_t* __restrict__ kind,
                       const int32_t* __restrict__ arg_a, const int32_t* __restrict__ arg_b,
                       const __nv_bfloat16* __restrict__ embed_tokens,
                       const __nv_bfloat16* __restrict__ time_tokens,
@@ -219,47 +222,66 @@ embed_assemble_kernel(__nv_bfloat16* __restrict__ hidden, int hs, const int32_t*
                       int C, int lat_h, int lat_w, const __nv_bfloat16* __restrict__ wx,
                       const __nv_bfloat16* __restrict__ bx, const __nv_bfloat16* __restrict__ wc,
                       const __nv_bfloat16* __restrict__ bc, const __nv_bfloat16* __restrict__ pos) {
-  const int row = blockIdx.x;
-  const int kd = kind[row], a = arg_a[row], b = arg_b[row];
-  const int chunks = hs >> 3;
-  uint4* out = reinterpret_cast<uint4*>(hidden + (size_t)row * hs);
-  if (kd <= 1) {
-    const uint4* src = reinterpret_cast<const uint4*>((kd == 0 ? embed_tokens : time_tokens) +
-                                                      (size_t)a * hs);
-    for (int c = threadIdx.x; c < chunks; c += kRowThreads) out[c] = src[c];
-    return;
-  }
-  __shared__ float patch[16];
-  const int pw = lat_w >> 1;
-  const int py = b / pw, px = b % pw;
-  const __nv_bfloat16* lat = (kd == 2 ? z : ctx) + (size_t)a * C * lat_h * lat_w;
-  if (threadIdx.x < C * 4) {     // (c, ph, pw) order of the flattened conv weight
-    const int c = threadIdx.x >> 2, ph = (threadIdx.x >> 1) & 1, pq = threadIdx.x & 1;
-    patch[threadIdx.x] =
-        __bfloat162float(lat[((size_t)c * lat_h + 2 * py + ph) * lat_w + 2 * px + pq]);
+  __shared__ int s_kind[kEmbedRows], s_a[kEmbedRows], s_b[kEmbedRows];
+  __shared__ float s_patch[kEmbedRows][16];
+  const int row0 = blockIdx.x * kEmbedRows;
+  const int nrows = min(kEmbedRows, rows - row0);
+  if ((int)threadIdx.x < nrows) {
+    s_kind[threadIdx.x] = kind[row0 + threadIdx.x];
+    s_a[threadIdx.x] = arg_a[row0 + threadIdx.x];
+    s_b[threadIdx.x] = arg_b[row0 + threadIdx.x];
   }
   __syncthreads();
-  const __nv_bfloat16* w = (kd == 2) ? wx : wc;
-  const __nv_bfloat16* bias = (kd == 2) ? bx : bc;
-  const uint4* posr = reinterpret_cast<const uint4*>(pos + (size_t)b * hs);
-  for (int c = threadIdx.x; c < chunks; c += kRowThreads) {
-    float bv[8], pv[8], o[8];
-    unpack8(reinterpret_cast<const uint4*>(bias)[c], bv);
-    unpack8(posr[c], pv);
-    const uint4* wr = reinterpret_cast<const uint4*>(w + (size_t)c * 8 * 16);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float w0[8], w1[8];
-      unpack8(wr[2 * j], w0);
-      unpack8(wr[2 * j + 1], w1);
-      float acc = 0.f;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) acc = fmaf(w0[t], patch[t], acc);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) acc = fmaf(w1[t], patch[8 + t], acc);
-      o[j] = rbf(rbf(acc + bv[j]) + pv[j]);
+  const int pw = lat_w >> 1;
+  {    // the 16 inputs (c, ph, pw) of every patch row of this CTA
+    const int r = threadIdx.x >> 4, t = threadIdx.x & 15;
+    if (r < nrows && s_kind[r] >= 2) {
+      const int b = s_b[r], py = b / pw, px = b % pw;
+      const __nv_bfloat16* lat = (s_kind[r] == 2 ? z : ctx) + (size_t)s_a[r] * C * lat_h * lat_w;
+      const int c = t >> 2, ph = (t >> 1) & 1, pq = t & 1;
+      s_patch[r][t] = __bfloat162float(lat[((size_t)c * lat_h + 2 * py + ph) * lat_w + 2 * px + pq]);
     }
-    out[c] = pack8(o);
+  }
+  __syncthreads();
+  bool any2 = false, any3 = false;
+  for (int r = 0; r < nrows; ++r) { any2 |= s_kind[r] == 2; any3 |= s_kind[r] == 3; }
+  const int chunks = hs >> 3;
+  for (int c = threadIdx.x; c < chunks; c += kRowThreads) {
+    for (int r = 0; r < nrows; ++r) {      // rows that are plain copies (tag / pad tokens, time slots)
+      if (s_kind[r] <= 1) {
+        const uint4* src = reinterpret_cast<const uint4*>((s_kind[r] == 0 ? embed_tokens : time_tokens) + (size_t)s_a[r] * hs);
+        reinterpret_cast<uint4*>(hidden + (size_t)(row0 + r) * hs)[c] = src[c];
+      }
+    }
+#pragma unroll 1
+    for (int kd = 2; kd <= 3; ++kd) {      // patch rows of either embedder: weights of this chunk held in registers
+      if (!(kd == 2 ? any2 : any3)) continue;
+      const __nv_bfloat16* w = (kd == 2) ? wx : wc;
+      float bv[8];
+      unpack8(reinterpret_cast<const uint4*>((kd == 2) ? bx : bc)[c], bv);
+      uint4 wv[16];
+      const uint4* wr = reinterpret_cast<const uint4*>(w + (size_t)c * 8 * 16);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wv[i] = wr[i];
+      for (int r = 0; r < nrows; ++r) {
+        if (s_kind[r] != kd) continue;
+        float pv[8], o[8];
+        unpack8(reinterpret_cast<const uint4*>(pos + (size_t)s_b[r] * hs)[c], pv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float w0[8], w1[8];
+          unpack8(wv[2 * j], w0);
+          unpack8(wv[2 * j + 1], w1);
+          float acc = 0.f;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc = fmaf(w0[t], s_patch[r][t], acc);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc = fmaf(w1[t], s_patch[r][8 + t], acc);
+          o[j] = rbf(rbf(acc + bv[j]) + pv[j]);
+        }
+        reinterpret_cast<uint4*>(hidden + (size_t)(row0 + r) * hs)[c] = pack8(o);
+      }
+    }
   }
 }
 
@@ -271,8 +293,8 @@ int embed_assemble(void* hidden, int rows, int hs, const int32_t* kind, const in
   VGPT_CHECK_ARG(hs % 8 == 0 && C == 4 && lat_h % 2 == 0 && lat_w % 2 == 0,
                  "vgpt_embed_assemble: unsupported hs=%d C=%d latent %dx%d", hs, C, lat_h, lat_w);
   if (rows <= 0) return 0;
-  embed_assemble_kernel<<<rows, kRowThreads, 0, s>>>(
-      (__nv_bfloat16*)hidden, hs, kind, a, b, (const __nv_bfloat16*)embed_tokens,
+  embed_assemble_kernel<<<(rows + kEmbedRows - 1) / kEmbedRows, kRowThreads, 0, s>>>(
+      (__nv_bfloat16*)hidden, rows, hs, kind, a, b, (const __nv_bfloat16*)embed_tokens,
       (const __nv_bfloat16*)time_tokens, (const __nv_bfloat16*)z, (const __nv_bfloat16*)ctx, C,
       lat_h, lat_w, (const __nv_bfloat16*)wx, (const __nv_bfloat16*)bx, (const __nv_bfloat16*)wc,
       (const __nv_bfloat16*)bc, (const __nv_bfloat16*)pos);
@@ -307,52 +329,79 @@ int timestep_sinusoid(const float* t, const float* freqs, void* out, int n, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small-batch linear: out[n,N] = post( pre(in[n,K]) @ W[N,K]^T + bias ), n <= 16.  Bound by the
-// single pass over W (TimestepEmbedder MLPs and adaLN modulation: LVM/model.py:32-36, 74-77).
-// One warp per output column, inputs staged once per CTA in shared memory as fp32.
+// Small-batch linear: out[n,N] = post( pre(in[n,K]) @ W[N,K]^T + bias ), n <= 16 (TimestepEmbedder MLPs and adaLN
+// modulation: LVM/model.py:32-36, 74-77; one row under the sampler's uniform timestep).  A weight-streaming GEMV: bound
+// by the single pass over W (78.6 MB per Euler step for the five launches).  One warp per TWO output columns, every lane
+// keeps eight 16-byte weight loads in flight (two columns x four k-chunks), inputs staged once per CTA in shared
+// memory; R = rows rounded up to a power of two keeps the accumulators in registers.  (The first version -- one column
+// per warp, one load in flight, 16 row slots whatever n -- reached 0.37 TB/s.)
 // ---------------------------------------------------------------------------------------------
 constexpr int kSmallMaxRows = 16;
 constexpr int kSmallWarps = 8;
+constexpr int kSmallCols = 2;          // output columns per warp
 
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
+  acc = fmaf(bf16lo(w.x), bf16lo(x.x), acc); acc = fmaf(bf16hi(w.x), bf16hi(x.x), acc);
+  acc = fmaf(bf16lo(w.y), bf16lo(x.y), acc); acc = fmaf(bf16hi(w.y), bf16hi(x.y), acc);
+  acc = fmaf(bf16lo(w.z), bf16lo(x.z), acc); acc = fmaf(bf16hi(w.z), bf16hi(x.z), acc);
+  acc = fmaf(bf16lo(w.w), bf16lo(x.w), acc); acc = fmaf(bf16hi(w.w), bf16hi(x.w), acc);
+  return acc;
+}
+
+template <int R>
 __global__ void __launch_bounds__(kSmallWarps * 32)
 linear_small_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ W,
                     const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int n,
                     int N, int K, int pre_silu, int post_silu) {
-  extern __shared__ __nv_bfloat16 sin_[];                 // [n][K] bf16 (after optional SiLU)
-  for (int i = threadIdx.x; i < n * K; i += blockDim.x) {
-    float v = __bfloat162float(in[i]);
+  extern __shared__ __nv_bfloat16 sin_[];                 // [R][K] bf16 (after optional SiLU; rows >= n are zero)
+  for (int i = threadIdx.x; i < R * K; i += blockDim.x) {
+    float v = i < n * K ? __bfloat162float(in[i]) : 0.f;
     if (pre_silu) v = rbf(silu_f(v));
     sin_[i] = __float2bfloat16_rn(v);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = blockIdx.x * kSmallWarps + warp;
-  if (col >= N) return;
-  float acc[kSmallMaxRows];
+  const int col0 = (blockIdx.x * kSmallWarps + warp) * kSmallCols;
+  if (col0 >= N) return;
+  const bool two = col0 + 1 < N;
+  float acc[R][kSmallCols];
 #pragma unroll
-  for (int r = 0; r < kSmallMaxRows; ++r) acc[r] = 0.f;
-  const uint4* wr = reinterpret_cast<const uint4*>(W + (size_t)col * K);
-  for (int c = lane; c < (K >> 3); c += 32) {
-    float wv[8];
-    unpack8(wr[c], wv);
+  for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = 0.f;
+  const int kch = K >> 3;
+  const uint4* w0 = reinterpret_cast<const uint4*>(W + (size_t)col0 * K);
+  const uint4* w1 = reinterpret_cast<const uint4*>(W + (size_t)(two ? col0 + 1 : col0) * K);
+  const uint4* xs = reinterpret_cast<const uint4*>(sin_);
+  for (int c0 = lane; c0 < kch; c0 += 4 * 32) {
+    uint4 wa[4], wb[4];
 #pragma unroll
-    for (int r = 0; r < kSmallMaxRows; ++r) {
-      if (r < n) {
-        float xv[8];
-        unpack8(*reinterpret_cast<const uint4*>(sin_ + (size_t)r * K + c * 8), xv);
+    for (int u = 0; u < 4; ++u) {                         // eight independent loads before the first use
+      const int c = c0 + u * 32;
+      wa[u] = c < kch ? __ldg(w0 + c) : make_uint4(0, 0, 0, 0);
+      wb[u] = c < kch ? __ldg(w1 + c) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[r] = fmaf(wv[j], xv[j], acc[r]);
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + u * 32;
+      if (c < kch) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint4 xv = xs[(size_t)r * kch + c];
+          acc[r][0] = dot8(wa[u], xv, acc[r][0]);
+          acc[r][1] = dot8(wb[u], xv, acc[r][1]);
+        }
       }
     }
   }
-  const float bv = bias ? __bfloat162float(bias[col]) : 0.f;
 #pragma unroll
-  for (int r = 0; r < kSmallMaxRows; ++r) {
-    if (r < n) {
-      float v = warp_sum(acc[r]);
-      v = rbf(v + bv);
-      if (post_silu) v = rbf(silu_f(v));
-      if (lane == 0) out[(size_t)r * N + col] = __float2bfloat16_rn(v);
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int j = 0; j < kSmallCols; ++j) {
+      float v = warp_sum(acc[r][j]);
+      if (lane == 0 && r < n && (j == 0 || two)) {
+        v = rbf(v + (bias ? __bfloat162float(bias[col0 + j]) : 0.f));
+        if (post_silu) v = rbf(silu_f(v));
+        out[(size_t)r * N + col0 + j] = __float2bfloat16_rn(v);
+      }
     }
   }
 }
@@ -363,49 +412,115 @@ int linear_small(const void* in, const void* W, const void* bias, void* out, int
   VGPT_CHECK_ARG(n >= 0 && n <= kSmallMaxRows && N > 0 && K > 0 && K % 8 == 0,
                  "vgpt_linear_small: unsupported n=%d N=%d K=%d (n <= %d, K %% 8 == 0)", n, N, K,
                  kSmallMaxRows);
+  VGPT_CHECK_ARG(((uintptr_t)in & 15) == 0 && ((uintptr_t)W & 15) == 0, "vgpt_linear_small: pointers must be 16-byte aligned");
   if (n == 0) return 0;
-  const size_t smem = (size_t)n * K * sizeof(__nv_bfloat16);
-  if (smem > 48 * 1024)       // per launch: the attribute is per device (cheap, capture-safe)
-    VGPT_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  linear_small_kernel<<<(N + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, smem, s>>>(
-      (const __nv_bfloat16*)in, (const __nv_bfloat16*)W, (const __nv_bfloat16*)bias,
-      (__nv_bfloat16*)out, n, N, K, pre_silu, post_silu);
+  const int R = n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : 16;
+  const size_t smem = (size_t)R * K * sizeof(__nv_bfloat16);
+  const int grid = (N + kSmallWarps * kSmallCols - 1) / (kSmallWarps * kSmallCols);
+#define VGPT_SMALL_CASE(R_)                                                                                              \
+  if (R == R_) {                                                                                                         \
+    if (smem > 48 * 1024)       /* per launch: the attribute is per device (cheap, capture-safe) */                      \
+      VGPT_CHECK_CUDA(cudaFuncSetAttribute(linear_small_kernel<R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    linear_small_kernel<R_><<<grid, kSmallWarps * 32, smem, s>>>((const __nv_bfloat16*)in, (const __nv_bfloat16*)W,     \
+                                                                (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, n, N, K, \
+                                                                pre_silu, post_silu);                                     \
+  }
+  VGPT_SMALL_CASE(1)
+  VGPT_SMALL_CASE(2)
+  VGPT_SMALL_CASE(4)
+  VGPT_SMALL_CASE(8)
+  VGPT_SMALL_CASE(16)
+#undef VGPT_SMALL_CASE
   VGPT_CHECK_LAUNCH();
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Final layer (FinalLayer.forward + unpatchify, LVM/model.py:79-83, 255-265, 478-486): per image
-// token of latent j:  LN(no affine, eps 1e-6) -> * (1 + scale_j) + shift_j -> Linear(h -> p*p*C)
-// -> scatter feature (p,q,c) of patch (py,px) to pred[j][c][2py+p][2px+q].   One CTA per token.
+// CFG + flow-matching Euler update (LVM/scheduler.py:178-204, LVM/model.py:554-562) of ONE element pair.
+//   x1 mode : v = (pred - z) / (1 - sigma)  for both branches, then CFG on v
+//   v  mode : CFG on pred
+//   CFG     : c = u + g * (c - u); both halves take c (the reference returns cond + cond)
+//   Euler   : z += (sigma_next - sigma) * v
+// Shared by cfg_euler_kernel and the fused final-layer kernel so that both round identically.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowThreads)
-final_layer_kernel(const __nv_bfloat16* __restrict__ hidden, int hs,
-                   const int32_t* __restrict__ lat_row0, const int32_t* __restrict__ row_kind,
-                   const int32_t* __restrict__ row_a, const int32_t* __restrict__ row_b,
-                   const __nv_bfloat16* __restrict__ mod, const __nv_bfloat16* __restrict__ w,
-                   const __nv_bfloat16* __restrict__ bias, PeerPtrs preds, int n_preds,
-                   int tokens_per_lat, int C, int lat_h, int lat_w) {
-  __shared__ float red[32];
-  __shared__ float outs[16][kRowThreads / 32];
-  int j, tkn, row;
-  if (lat_row0) {                    // latent-driven: CTA = (latent, token), rows contiguous per latent
-    j = blockIdx.x / tokens_per_lat; tkn = blockIdx.x % tokens_per_lat;
-    row = lat_row0[j] + tkn;
-  } else {                           // row-driven (any row partition): CTA = row, image-token rows only
-    row = blockIdx.x;
-    if (row_kind[row] != 2 /* VGPT_ROW_NOISY_PATCH */) return;
-    j = row_a[row]; tkn = row_b[row];
+struct StepScalars { float one_minus_sigma, dsigma, guidance; };
+
+__device__ __forceinline__ void cfg_euler_element(__nv_bfloat16* __restrict__ z, float c, float u,
+                                                  __nv_bfloat16* __restrict__ vel_out, int i, int half_numel,
+                                                  int use_cfg, int x1_mode, const StepScalars& sc) {
+  // torch divides a CUDA tensor by a CPU scalar as a * (1 / b) in fp32 (BinaryDivTrueKernel.cu);
+  // the reference's `(pred - z) / (1.0 - sigma)` (scheduler.py:184) therefore rounds this way.
+  const float inv = 1.0f / sc.one_minus_sigma;
+  const float zc = __bfloat162float(z[i]);
+  if (x1_mode) c = rbf(rbf(c - zc) * inv);
+  float zu = 0.f;
+  if (use_cfg) {
+    zu = __bfloat162float(z[half_numel + i]);
+    if (x1_mode) u = rbf(rbf(u - zu) * inv);
+    c = rbf(u + rbf(sc.guidance * rbf(c - u)));
   }
+  if (vel_out) vel_out[i] = __float2bfloat16_rn(c);
+  const float step = rbf(sc.dsigma * c);
+  z[i] = __float2bfloat16_rn(zc + step);
+  if (use_cfg) z[half_numel + i] = __float2bfloat16_rn(zu + step);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final layer (llm.norm + FinalLayer.forward + unpatchify, OmniGen/transformer.py:214, LVM/model.py:79-83,
+// 255-265, 478-486) -- and, in the sampler's fused loop, the scheduler update behind it -- per image token
+// of latent j:  [Phi3RMSNorm ->] LN(no affine, eps 1e-6) -> * (1 + scale_j) + shift_j -> Linear(h -> p*p*C)
+// -> scatter feature (p,q,c) of patch (py,px) to pred[j][c][2py+p][2px+q]  [-> x1 -> v, CFG, Euler on z].
+// One CTA per token (per cond / uncond token pair when the Euler update is fused).
+// ---------------------------------------------------------------------------------------------
+struct EulerFuse {          // z == nullptr: not fused
+  __nv_bfloat16* z;
+  __nv_bfloat16* vel;       // optional: applied velocity of the cond half
+  const StepScalars* sc;    // device scalars (the step's 1 - sigma, d sigma, guidance): graph replayable
+  int n_half;               // latents per CFG branch
+  int use_cfg, x1_mode;
+};
+
+// the 16 output features of one row; valid in threads 0..15 (fp32, bias added, before the bf16 rounding)
+__device__ __forceinline__ float final_row(const __nv_bfloat16* __restrict__ hidden, int row, int hs,
+                                           const __nv_bfloat16* __restrict__ norm_w, float rms_eps,
+                                           const __nv_bfloat16* __restrict__ mod_j, const __nv_bfloat16* __restrict__ w,
+                                           const __nv_bfloat16* __restrict__ bias, float* red,
+                                           float (*outs)[kRowThreads / 32]) {
   const int chunks = hs >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(hidden + (size_t)row * hs);
   float xv[kMaxChunksPerThread][8];
+#pragma unroll
+  for (int i = 0; i < kMaxChunksPerThread; ++i) {
+    const int c = threadIdx.x + i * kRowThreads;
+    if (c < chunks) unpack8(xr[c], xv[i]);
+  }
+  if (norm_w != nullptr) {             // llm.norm (Phi3RMSNorm): y = w * bf16(x * rstd), rounded to bf16
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxChunksPerThread; ++i) {
+      const int c = threadIdx.x + i * kRowThreads;
+      if (c < chunks) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) ss += xv[i][t] * xv[i][t];
+      }
+    }
+    const float rstd = rsqrtf(block_sum(ss, red) / (float)hs + rms_eps);
+#pragma unroll
+    for (int i = 0; i < kMaxChunksPerThread; ++i) {
+      const int c = threadIdx.x + i * kRowThreads;
+      if (c < chunks) {
+        float g[8];
+        unpack8(reinterpret_cast<const uint4*>(norm_w)[c], g);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) xv[i][t] = rbf(g[t] * rbf(xv[i][t] * rstd));
+      }
+    }
+  }
   float s1 = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxChunksPerThread; ++i) {
     const int c = threadIdx.x + i * kRowThreads;
     if (c < chunks) {
-      unpack8(xr[c], xv[i]);
 #pragma unroll
       for (int t = 0; t < 8; ++t) s1 += xv[i][t];
     }
@@ -421,8 +536,8 @@ final_layer_kernel(const __nv_bfloat16* __restrict__ hidden, int hs,
     }
   }
   const float rstd = rsqrtf(block_sum(s2, red) / (float)hs + 1e-6f);
-  const uint4* shift = reinterpret_cast<const uint4*>(mod + (size_t)j * 2 * hs);
-  const uint4* scale = reinterpret_cast<const uint4*>(mod + (size_t)j * 2 * hs + hs);
+  const uint4* shift = reinterpret_cast<const uint4*>(mod_j);
+  const uint4* scale = reinterpret_cast<const uint4*>(mod_j + hs);
   float acc[16];
 #pragma unroll
   for (int f = 0; f < 16; ++f) acc[f] = 0.f;
@@ -449,43 +564,94 @@ final_layer_kernel(const __nv_bfloat16* __restrict__ hidden, int hs,
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                                        // outs[] may still be read from the previous row
 #pragma unroll
   for (int f = 0; f < 16; ++f) {
     const float v = warp_sum(acc[f]);
     if (lane == 0) outs[f][warp] = v;
   }
   __syncthreads();
+  float v = 0.f;
+  if (threadIdx.x < 16) {
+#pragma unroll
+    for (int k = 0; k < kRowThreads / 32; ++k) v += outs[threadIdx.x][k];
+    v += __bfloat162float(bias[threadIdx.x]);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+final_layer_kernel(const __nv_bfloat16* __restrict__ hidden, int hs, const __nv_bfloat16* __restrict__ norm_w,
+                   float rms_eps, const int32_t* __restrict__ lat_row0, const int32_t* __restrict__ row_kind,
+                   const int32_t* __restrict__ row_a, const int32_t* __restrict__ row_b,
+                   const __nv_bfloat16* __restrict__ mod, const __nv_bfloat16* __restrict__ w,
+                   const __nv_bfloat16* __restrict__ bias, PeerPtrs preds, int n_preds,
+                   int tokens_per_lat, int C, int lat_h, int lat_w, EulerFuse eu) {
+  __shared__ float red[32];
+  __shared__ float outs[16][kRowThreads / 32];
+  int j, tkn, row;
+  if (lat_row0) {                    // latent-driven: CTA = (latent, token), rows contiguous per latent
+    j = blockIdx.x / tokens_per_lat; tkn = blockIdx.x % tokens_per_lat;
+    row = lat_row0[j] + tkn;
+  } else {                           // row-driven (any row partition): CTA = row, image-token rows only
+    row = blockIdx.x;
+    if (row_kind[row] != 2 /* VGPT_ROW_NOISY_PATCH */) return;
+    j = row_a[row]; tkn = row_b[row];
+  }
+  const float v = final_row(hidden, row, hs, norm_w, rms_eps, mod + (size_t)j * 2 * hs, w, bias, red, outs);
+  float vu = 0.f;
+  if (eu.z != nullptr && eu.use_cfg) {                    // the unconditional twin of this token (latent j + n_half)
+    const int ju = j + eu.n_half;
+    vu = final_row(hidden, lat_row0[ju] + tkn, hs, norm_w, rms_eps, mod + (size_t)ju * 2 * hs, w, bias, red, outs);
+  }
   if (threadIdx.x < 16) {
     const int f = threadIdx.x;
-    float v = 0.f;
-#pragma unroll
-    for (int k = 0; k < kRowThreads / 32; ++k) v += outs[f][k];
-    v += __bfloat162float(bias[f]);
     const int pw = lat_w >> 1;
     const int py = tkn / pw, px = tkn % pw;
     const int p = f / (2 * C), q = (f / C) & 1, c = f % C;     // feature order (p, q, c)
-    const size_t o = (((size_t)j * C + c) * lat_h + 2 * py + p) * lat_w + 2 * px + q;
+    const size_t numel_lat = (size_t)C * lat_h * lat_w;
+    const size_t off = ((size_t)c * lat_h + 2 * py + p) * lat_w + 2 * px + q;
     const __nv_bfloat16 r = __float2bfloat16_rn(v);
 #pragma unroll
     for (int g = 0; g < kMaxPeers; ++g)
-      if (g < n_preds) static_cast<__nv_bfloat16*>(preds.p[g])[o] = r;
+      if (g < n_preds) static_cast<__nv_bfloat16*>(preds.p[g])[(size_t)j * numel_lat + off] = r;
+    if (eu.z != nullptr) {
+      const __nv_bfloat16 ru = __float2bfloat16_rn(vu);
+      if (eu.use_cfg) static_cast<__nv_bfloat16*>(preds.p[0])[(size_t)(j + eu.n_half) * numel_lat + off] = ru;
+      const StepScalars sc = *eu.sc;
+      cfg_euler_element(eu.z, __bfloat162float(r), __bfloat162float(ru), eu.vel, (int)((size_t)j * numel_lat + off),
+                        (int)(eu.n_half * numel_lat), eu.use_cfg, eu.x1_mode, sc);
+    }
   }
 }
 
-int final_layer(const void* hidden, int hs, const int32_t* lat_row0, const void* mod, const void* w,
-                const void* bias, void* pred, int n_lat, int C, int lat_h, int lat_w,
-                cudaStream_t s) {
+int final_layer(const void* hidden, int hs, const void* norm_w, float rms_eps, const int32_t* lat_row0, const void* mod,
+                const void* w, const void* bias, void* pred, int n_lat, int C, int lat_h, int lat_w, void* z_euler,
+                void* vel_out, const float* scalars_dev, int use_cfg, int x1_mode, cudaStream_t s) {
   VGPT_CHECK_ARG(hidden && lat_row0 && mod && w && bias && pred, "vgpt_final_layer: null pointer");
   VGPT_CHECK_ARG(hs % 8 == 0 && hs <= kRowThreads * kMaxChunksPerThread * 8 && C == 4 &&
                      lat_h % 2 == 0 && lat_w % 2 == 0,
                  "vgpt_final_layer: unsupported hs=%d C=%d latent %dx%d", hs, C, lat_h, lat_w);
+  VGPT_CHECK_ARG(!z_euler || (scalars_dev && (!use_cfg || n_lat % 2 == 0)),
+                 "vgpt_final_layer: the fused scheduler update needs device scalars and, with CFG, an even number of latents");
   if (n_lat <= 0) return 0;
   const int tokens = (lat_h / 2) * (lat_w / 2);
   PeerPtrs pp = {};
   pp.p[0] = pred;
-  final_layer_kernel<<<n_lat * tokens, kRowThreads, 0, s>>>(
-      (const __nv_bfloat16*)hidden, hs, lat_row0, nullptr, nullptr, nullptr, (const __nv_bfloat16*)mod,
-      (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, pp, 1, tokens, C, lat_h, lat_w);
+  EulerFuse eu = {};
+  int ctas = n_lat * tokens;
+  if (z_euler) {
+    eu.z = static_cast<__nv_bfloat16*>(z_euler);
+    eu.vel = static_cast<__nv_bfloat16*>(vel_out);
+    eu.sc = reinterpret_cast<const StepScalars*>(scalars_dev);
+    eu.use_cfg = use_cfg;
+    eu.x1_mode = x1_mode;
+    eu.n_half = use_cfg ? n_lat / 2 : n_lat;
+    ctas = eu.n_half * tokens;            // one CTA per cond / uncond token pair
+  }
+  final_layer_kernel<<<ctas, kRowThreads, 0, s>>>(
+      (const __nv_bfloat16*)hidden, hs, (const __nv_bfloat16*)norm_w, rms_eps, lat_row0, nullptr, nullptr, nullptr,
+      (const __nv_bfloat16*)mod, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, pp, 1, tokens, C, lat_h, lat_w, eu);
   VGPT_CHECK_LAUNCH();
   return 0;
 }
@@ -493,9 +659,9 @@ int final_layer(const void* hidden, int hs, const int32_t* lat_row0, const void*
 // Row-driven variant for row-sharded (sequence-parallel) plans: `rows` local rows described by the
 // plan's (kind, a = latent, b = token) arrays; the prediction is stored into every rank's pred
 // buffer (preds[0..n_preds), NVLink stores), so no gather follows.
-int final_layer_rows(const void* hidden, int rows, int hs, const int32_t* kind, const int32_t* a,
-                     const int32_t* b, const void* mod, const void* w, const void* bias, void* const* preds,
-                     int n_preds, int C, int lat_h, int lat_w, cudaStream_t s) {
+int final_layer_rows(const void* hidden, int rows, int hs, const void* norm_w, float rms_eps, const int32_t* kind,
+                     const int32_t* a, const int32_t* b, const void* mod, const void* w, const void* bias,
+                     void* const* preds, int n_preds, int C, int lat_h, int lat_w, cudaStream_t s) {
   VGPT_CHECK_ARG(hidden && kind && a && b && mod && w && bias && preds, "vgpt_final_layer_rows: null pointer");
   VGPT_CHECK_ARG(n_preds >= 1 && n_preds <= kMaxPeers, "vgpt_final_layer_rows: %d destinations (1..%d)", n_preds, kMaxPeers);
   VGPT_CHECK_ARG(hs % 8 == 0 && hs <= kRowThreads * kMaxChunksPerThread * 8 && C == 4 &&
@@ -508,46 +674,25 @@ int final_layer_rows(const void* hidden, int rows, int hs, const int32_t* kind, 
   }
   if (rows <= 0) return 0;
   final_layer_kernel<<<rows, kRowThreads, 0, s>>>(
-      (const __nv_bfloat16*)hidden, hs, nullptr, kind, a, b, (const __nv_bfloat16*)mod,
-      (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, pp, n_preds, (lat_h / 2) * (lat_w / 2), C, lat_h,
-      lat_w);
+      (const __nv_bfloat16*)hidden, hs, (const __nv_bfloat16*)norm_w, rms_eps, nullptr, kind, a, b,
+      (const __nv_bfloat16*)mod, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, pp, n_preds,
+      (lat_h / 2) * (lat_w / 2), C, lat_h, lat_w, EulerFuse{});
   VGPT_CHECK_LAUNCH();
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// CFG + flow-matching Euler update (LVM/scheduler.py:178-204, LVM/model.py:554-562).
+// Stand-alone scheduler update (any callback through the S2 seam, CFG-branch pairs, sequence-parallel groups).
 // z, pred: [n_branches * n_cond * numel] bf16 laid out [cond latents..., uncond latents...].
-//   x1 mode : v = (pred - z) / (1 - sigma)  for both branches, then CFG on v
-//   v  mode : CFG on pred
-//   CFG     : c = u + g * (c - u); both halves take c (the reference returns cond + cond)
-//   Euler   : z += (sigma_next - sigma) * v
 // ---------------------------------------------------------------------------------------------
-struct StepScalars { float one_minus_sigma, dsigma, guidance; };
-
 __global__ void cfg_euler_kernel(__nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ pred,
                                  __nv_bfloat16* __restrict__ vel_out, int half_numel, int use_cfg,
                                  int x1_mode, const StepScalars* __restrict__ sc_dev, StepScalars sc_host) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half_numel) return;
   const StepScalars sc = sc_dev ? *sc_dev : sc_host;
-  // torch divides a CUDA tensor by a CPU scalar as a * (1 / b) in fp32 (BinaryDivTrueKernel.cu);
-  // the reference's `(pred - z) / (1.0 - sigma)` (scheduler.py:184) therefore rounds this way.
-  const float inv = 1.0f / sc.one_minus_sigma;
-  float zc = __bfloat162float(z[i]);
-  float c = __bfloat162float(pred[i]);
-  if (x1_mode) c = rbf(rbf(c - zc) * inv);
-  float zu = 0.f;
-  if (use_cfg) {
-    zu = __bfloat162float(z[half_numel + i]);
-    float u = __bfloat162float(pred[half_numel + i]);
-    if (x1_mode) u = rbf(rbf(u - zu) * inv);
-    c = rbf(u + rbf(sc.guidance * rbf(c - u)));
-  }
-  if (vel_out) vel_out[i] = __float2bfloat16_rn(c);
-  const float step = rbf(sc.dsigma * c);
-  z[i] = __float2bfloat16_rn(zc + step);
-  if (use_cfg) z[half_numel + i] = __float2bfloat16_rn(zu + step);
+  cfg_euler_element(z, __bfloat162float(pred[i]), use_cfg ? __bfloat162float(pred[half_numel + i]) : 0.f, vel_out, i,
+                    half_numel, use_cfg, x1_mode, sc);
 }
 
 int cfg_euler(void* z, const void* pred, void* vel_out, int half_numel, int use_cfg, int x1_mode,

@@ -143,7 +143,7 @@ __device__ __forceinline__ void store_chunk_swiglu(const uint32_t (&acc)[32], __
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                      const __grid_constant__ CUtensorMap tmap_w16, const __grid_constant__ CUtensorMap tmap_t,
+                      const __grid_constant__ CUtensorMap tmap_wsp, const __grid_constant__ CUtensorMap tmap_t,
                       __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ R, int M, int N, int K, int ldc,
                       int flags, const __grid_constant__ Sched sched) {
   using Cfg = GemmCfg<BN>;
@@ -172,7 +172,7 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (n_special) { tma_prefetch_desc(&tmap_w16); tma_prefetch_desc(&tmap_t); }
+    if (n_special) { tma_prefetch_desc(&tmap_wsp); tma_prefetch_desc(&tmap_t); }
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);          // leader producer's arrive.expect_tx covers both CTAs' bytes
       mbar_init(empty_bar(s), 1);         // leader's multicast commit
@@ -218,17 +218,18 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       for (int j = 0; j < n_special; ++j) {
         if ((int)sched.owner[j] != cluster_id) continue;
         const int c0 = j * sched.sp_width;
-        const int half = min(sched.sp_width, N - c0) >> 1;         // W rows per CTA (a multiple of 16)
+        const int half = min(sched.sp_width, N - c0) >> 1;         // this CTA's W rows of the piece
         const int n0 = c0 + (int)rank * half;
-        const uint32_t tx = 2u * (uint32_t)(Cfg::kABytes + (half + sched.T / 2) * kGBlockK * 2);
+        const uint32_t tx = 2u * (uint32_t)(Cfg::kABytes + (sched.sp_width / 2 + sched.T / 2) * kGBlockK * 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), tx);
           tma_load_2d_pair(sa, &tmap_a, full_bar(stage), kb * kGBlockK, sp_row0 + (int)rank * kGBlockM);
-          for (int r = 0; r < half; r += 16)
-            tma_load_2d_pair(sb + (uint32_t)r * kGBlockK * 2, &tmap_w16, full_bar(stage), kb * kGBlockK, n0 + r);
+          // ONE box of sp_width / 2 weight rows (a narrower last piece loads rows past its own half -- of the peer's
+          // half, or zero fill past N -- that no MMA column of this CTA maps to)
+          tma_load_2d_pair(sb, &tmap_wsp, full_bar(stage), kb * kGBlockK, n0);
           tma_load_2d_pair(sb + tail_off, &tmap_t, full_bar(stage), kb * kGBlockK, (int)rank * (sched.T / 2));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -448,7 +449,9 @@ static int launch_gemm(const void* A, const void* W, void* C, const void* R, int
     const int tail = M % 256;
     m_tiles_reg = M / 256 - 1;
     sched.tail_rows = tail;
-    sched.T = (tail + 15) & ~15;
+    // the tail MMA's N: always 32.  (N = 16 is legal but slow: with T = 16 a special piece measured ~920 cycles per
+    // k-block against 448 for its 224-wide main MMAs; tools/umma_rate.py mode 4 shows N = 32 at its 39-cycle floor.)
+    sched.T = kTailMax;
     // special width: main + tail accumulators in one TMEM stage, W + tail rows in the B slot; SwiGLU pairs
     // ([gate x 16 | up x 16] per 32 packed rows) must not straddle the two CTAs' halves: a multiple of 64
     int width = Cfg::kSpecialWidth;
@@ -459,7 +462,7 @@ static int launch_gemm(const void* A, const void* W, void* C, const void* R, int
       set_last_error("vgpt_gemm_bf16: N=%d needs %d special pieces (at most %d)", N, sched.n_special, kMaxSpecial);
       return -1;
     }
-    rc = make_tmap(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 16);
+    rc = make_tmap(&tw, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, width / 2);
     if (rc) return rc;
     const __nv_bfloat16* a_tail = static_cast<const __nv_bfloat16*>(A) + (size_t)(M - tail) * lda;
     rc = make_tmap(&tt, a_tail, (uint64_t)K, (uint64_t)tail, (uint64_t)lda * 2, sched.T / 2);   // rows >= tail: zero fill
@@ -494,6 +497,35 @@ static int launch_gemm(const void* A, const void* W, void* C, const void* R, int
   return 0;
 }
 
+// Modelled makespan (tensor-pipe cycles per k-block on the most loaded cluster) of a launch, plain or with the tail in
+// the k-loop -- the same list scheduling launch_gemm does.  Measured (profiles/r02d_gemm_sweep_tail_in_loop.txt): the
+// special pieces remove 10 % of the MMA work, but where a cluster only gets one or two work items their extra weight
+// lands on the most loaded cluster (o / down at M = 2064: 2 x 384 plain, 384 + 540 special), so the choice is made per
+// shape: at cfg2 qkv takes the special pieces (4 waves instead of 5), the other three projections stay plain.
+static double modelled_makespan(int M, int N, int bn, int epilogue, bool in_loop, int clusters) {
+  const int n_tiles = (N + bn - 1) / bn;
+  if (!in_loop) {
+    const int tiles = ((M + 255) / 256) * n_tiles;
+    return 2.0 * bn * ((tiles + clusters - 1) / clusters);
+  }
+  const int reg = (M / 256 - 1) * n_tiles;
+  int width = bn == 256 ? kTailCol : bn;
+  if (epilogue == kEpiSwiGLU) width = width / 64 * 64;
+  const int n_special = (N + width - 1) / width;
+  const int c_used = reg + n_special < clusters ? reg + n_special : clusters;
+  double load[256], worst = 0;
+  for (int c = 0; c < c_used; ++c) load[c] = 2.0 * bn * ((reg + c_used - 1 - c) / c_used);
+  for (int j = 0; j < n_special; ++j) {
+    int best = 0;
+    for (int c = 1; c < c_used; ++c)
+      if (load[c] < load[best] - 1e-9) best = c;
+    const int w = (N - j * width) < width ? (N - j * width) : width;
+    load[best] += 2.0 * w + 4.0 * 39.0;
+  }
+  for (int c = 0; c < c_used; ++c) worst = load[c] > worst ? load[c] : worst;
+  return worst;
+}
+
 // tail_mode: -1 = tuned default, 1 = plain 256-row tiles only, 3 = tail rows in the k-loop whenever the shape allows it.
 int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc, int epilogue,
               int block_n, int tail_mode, cudaStream_t stream) {
@@ -512,9 +544,23 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
   // VGPT_GEMM_TAIL_IN_LOOP=0 switches the default off for A/B timing
   static const bool in_loop_default = [] { const char* e = getenv("VGPT_GEMM_TAIL_IN_LOOP"); return !(e && e[0] == '0'); }();
   const int tail = M % 256;
-  const bool can = M >= 256 && tail > 0 && tail <= kTailMax;
-  const bool in_loop = can && (tail_mode == 3 || (tail_mode == -1 && in_loop_default));
-  if (block_n == 0) block_n = pick_pair_block_n(in_loop ? M - tail : M, N, sms);
+  const bool can = M >= 256 && tail > 0 && tail <= kTailMax && sms / 2 <= 255;
+  bool in_loop = can && tail_mode == 3;
+  if (block_n == 0) {
+    block_n = pick_pair_block_n(M, N, sms);
+    if (can && tail_mode == -1 && in_loop_default) {       // the cheaper of (plain, best width) and (special pieces, best width)
+      double best = modelled_makespan(M, N, block_n, epilogue, false, sms / 2) / (block_n == 256 ? 1.0 : 0.88);
+      const int cand[2] = {256, 192};
+      for (int i = 0; i < 2; ++i) {
+        const double t = modelled_makespan(M, N, cand[i], epilogue, true, sms / 2) / (cand[i] == 256 ? 1.0 : 0.88);
+        if (t < 0.97 * best) { best = t; block_n = cand[i]; in_loop = true; }
+      }
+    } else if (in_loop) {
+      block_n = pick_pair_block_n(M - tail, N, sms);
+    }
+  } else if (can && tail_mode == -1 && in_loop_default) {
+    in_loop = modelled_makespan(M, N, block_n, epilogue, true, sms / 2) < 0.97 * modelled_makespan(M, N, block_n, epilogue, false, sms / 2);
+  }
   VGPT_CHECK_ARG(block_n == 128 || block_n == 192 || block_n == 256, "vgpt_gemm_bf16: block_n must be 128, 192 or 256");
 #define VGPT_GEMM_CASE(BN_, EPI_) \
   if (block_n == BN_ && epilogue == EPI_) return launch_gemm<BN_, EPI_>(A, W, C, R, M, N, K, lda, ldc, sms, in_loop, stream);

@@ -50,11 +50,12 @@ int embed_assemble(void* hidden, int rows, int hs, const int32_t* kind, const in
 int timestep_sinusoid(const float* t, const float* freqs, void* out, int n, int dim, cudaStream_t s);
 int linear_small(const void* in, const void* W, const void* bias, void* out, int n, int N, int K,
                  int pre_silu, int post_silu, cudaStream_t s);
-int final_layer(const void* hidden, int hs, const int32_t* lat_row0, const void* mod, const void* w,
-                const void* bias, void* pred, int n_lat, int C, int lat_h, int lat_w, cudaStream_t s);
-int final_layer_rows(const void* hidden, int rows, int hs, const int32_t* kind, const int32_t* a,
-                     const int32_t* b, const void* mod, const void* w, const void* bias, void* const* preds,
-                     int n_preds, int C, int lat_h, int lat_w, cudaStream_t s);
+int final_layer(const void* hidden, int hs, const void* norm_w, float rms_eps, const int32_t* lat_row0, const void* mod,
+                const void* w, const void* bias, void* pred, int n_lat, int C, int lat_h, int lat_w, void* z_euler,
+                void* vel_out, const float* scalars_dev, int use_cfg, int x1_mode, cudaStream_t s);
+int final_layer_rows(const void* hidden, int rows, int hs, const void* norm_w, float rms_eps, const int32_t* kind,
+                     const int32_t* a, const int32_t* b, const void* mod, const void* w, const void* bias,
+                     void* const* preds, int n_preds, int C, int lat_h, int lat_w, cudaStream_t s);
 int peer_alloc(void** out, uint64_t bytes);
 int peer_free(void* p);
 int peer_export(void* p, void* handle64);

@@ -15,7 +15,8 @@ Design (B200-first, not the reference's control flow):
   kernel evaluates ``code_q >= code_k`` (see ``processor.token_codes``).
 * All rows of all sequences (cond / uncond / batch) are packed into one ``[M, hidden]``
   matrix, so every projection is one GEMM launch per layer.
-* One step = 9 + 8 x layers kernel launches, captured once in a CUDA graph and replayed.
+* One step = 8 + 8 x layers kernel launches (the final RMSNorm, the final layer, unpatchify and -- in the sampler's
+  fused loop -- the x1 -> v / CFG / Euler update are ONE kernel), captured once in a CUDA graph and replayed.
 """
 from __future__ import annotations
 
@@ -385,7 +386,11 @@ class NextClipEngine:
         # sampler loop: scheduler.py:171 builds `timesteps` from one sigma): the three small MLPs
         # then run on ONE row and the result is replicated -- identical numbers, 1/n of the work.
         self.uniform_t = False
-        self._graph_uniform = None
+        # Set by the sampler's fused loop (scheduler.run_prepared): (use_cfg, x1_mode) -> the final-layer kernel also
+        # applies the step's x1 -> v / CFG / Euler update to self.z, reading the step scalars from self.scalars; None:
+        # predict() only produces self.pred (the S2 callback seam, CFG-branch pairs, sequence-parallel groups)
+        self.euler_mode = None
+        self._graph_key = None
         self.plan: Optional[ClipPlan] = None
         # diagnostic tap (tools/parity_floor.py): a list that receives a copy of the hidden rows after every
         # decoder layer of eager (non-graph) passes; None in production
@@ -473,13 +478,17 @@ class NextClipEngine:
                               self._kv_shared.ptr_array((2 * li + 1) * pool_bytes)) for li in range(self.L)]
             self._pred_ptrs = self._pred_shared.ptr_array()
         self.ctx = torch.zeros(max(plan.n_ctx_latents, 1), 4, plan.lat_h, plan.lat_w, device=dev, dtype=bf)
-        self.t = torch.zeros(n, device=dev, dtype=torch.float32)
+        # per-step inputs in ONE buffer so that the sampler sets them with one copy per step:
+        # [timestep of every latent | 1 - sigma, d sigma, guidance]
+        self.step_inputs = torch.zeros(n + 3, device=dev, dtype=torch.float32)
+        self.t = self.step_inputs[:n]
+        self.scalars = self.step_inputs[n:n + 3]
+        self.vel = torch.zeros_like(self.z)
         self.t_sin = torch.empty(n, 256, device=dev, dtype=bf)
         self.t_h1 = torch.empty(n, self.hs, device=dev, dtype=bf)
         self.time_tokens = torch.empty(n, self.hs, device=dev, dtype=bf)
         self.t_emb = torch.empty(n, self.hs, device=dev, dtype=bf)
         self.mod = torch.empty(n, 2 * self.hs, device=dev, dtype=bf)
-        self.scalars = torch.zeros(3, device=dev, dtype=torch.float32)
         self.pos_rows = self._pos_rows(plan.lat_h, plan.lat_w)
         if self._rope_tab is None or self._rope_tab.shape[0] < plan.max_pos:
             self._rope_tab = ops.rope_table(self._inv_freq, max(plan.max_pos, self.rope_reserve, 1), self.D)
@@ -590,16 +599,22 @@ class NextClipEngine:
         if st.rows:
             self._assemble(st)
         yield from self._layers(st, kv_only_last=False)
-        if st.rows:
-            ops.rmsnorm(self.hidden[:st.rows], self.w.norm, self.eps, out=self.xn[:st.rows])
+        # llm.norm + FinalLayer + unpatchify (+ the scheduler update in the fused loop): one kernel on the raw residual stream
         if self.peers is None:
-            ops.final_layer(self.xn[:st.rows], plan.lat_row0, self.mod[:plan.n_latents], self.w.final_w,
-                            self.w.final_b, self.pred)
+            euler = None
+            if self.euler_mode is not None:
+                use_cfg, x1_mode = self.euler_mode
+                n_half = plan.n_latents // 2 if use_cfg else plan.n_latents
+                euler = (self.z, self.scalars, use_cfg, x1_mode, self.vel[:n_half])
+            ops.final_layer(self.hidden[:st.rows], plan.lat_row0, self.mod[:plan.n_latents], self.w.final_w,
+                            self.w.final_b, self.pred, norm_weight=self.w.norm, rms_eps=self.eps, euler=euler)
         else:                             # prediction stored into every rank's pred buffer
+            if self.euler_mode is not None:
+                raise RuntimeError("the fused scheduler update is single-GPU only: sequence-parallel ranks apply vgpt_cfg_euler")
             if st.rows:
-                ops.final_layer_rows(self.xn[:st.rows], st.kind, st.arg_a, st.arg_b, self.mod[:plan.n_latents],
+                ops.final_layer_rows(self.hidden[:st.rows], st.kind, st.arg_a, st.arg_b, self.mod[:plan.n_latents],
                                      self.w.final_w, self.w.final_b, self._pred_ptrs, self.peers.world,
-                                     plan.lat_h, plan.lat_w)
+                                     plan.lat_h, plan.lat_w, norm_weight=self.w.norm, rms_eps=self.eps)
             yield "pred"
 
     def predict_steps(self):
@@ -619,8 +634,11 @@ class NextClipEngine:
         if not self.use_cuda_graph:
             self._drive(self._predict_kernels())
             return self.pred
-        if self._graph is None or self._graph_uniform != self.uniform_t:
-            self._graph_uniform = self.uniform_t
+        key = (self.uniform_t, self.euler_mode)
+        if self._graph is None or self._graph_key != key:
+            self._graph_key = key
+            if self.euler_mode is not None:        # the warm-up and the capture pass must not advance the latents
+                z_keep = self.z.clone()
             self._drive(self._predict_kernels())   # warm-up (sets function attributes, fills caches)
             torch.cuda.synchronize()
             if self.peers is not None:
@@ -629,6 +647,8 @@ class NextClipEngine:
             with torch.cuda.graph(g):
                 self._drive(self._predict_kernels())
             self._graph = g
+            if self.euler_mode is not None:
+                self.z.copy_(z_keep)
             if self.peers is not None:
                 self.peers.host_barrier()
         self._graph.replay()
@@ -639,7 +659,7 @@ class NextClipEngine:
         """Kernels of this library per predict() (torch's two replicate copies under uniform_t are
         not counted)."""
         sync = (self.L + 1) if self.peers is not None and not self.peers.lockstep else 0
-        return 6 + 1 + 8 * self.L + 2 + sync
+        return 6 + 1 + 8 * self.L + 1 + sync
 
     @property
     def launches_per_prefill(self) -> int:

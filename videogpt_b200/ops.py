@@ -175,25 +175,44 @@ def linear_small(x, w, bias, pre_silu: bool = False, post_silu: bool = False, ou
     return out
 
 
-def final_layer(hidden, lat_row0, mod, w, bias, pred):
+def final_layer(hidden, lat_row0, mod, w, bias, pred, norm_weight=None, rms_eps: float = 0.0, euler=None):
+    """FinalLayer + unpatchify.  ``norm_weight``: ``hidden`` is the raw residual stream, apply the final RMSNorm first.
+    ``euler = (z, scalars_dev, use_cfg, x1_mode, vel_out or None)``: apply the step's scheduler update to ``z`` in the
+    same launch (``vgpt_cfg_euler`` arithmetic, device scalars ``[1 - sigma, d sigma, guidance]``)."""
     _req(hidden, BF16, "hidden"); _req(lat_row0, I32, "lat_row0"); _req(mod, BF16, "mod")
     _req(w, BF16, "w"); _req(bias, BF16, "bias"); _req(pred, BF16, "pred")
     n_lat, c, lat_h, lat_w = pred.shape
     assert mod.shape == (n_lat, 2 * hidden.shape[1]) and lat_row0.numel() >= n_lat
-    _lib.call("vgpt_final_layer", _p(hidden), hidden.shape[1], _p(lat_row0), _p(mod), _p(w), _p(bias),
-              _p(pred), n_lat, c, lat_h, lat_w, _stream())
+    if norm_weight is not None:
+        _req(norm_weight, BF16, "norm_weight")
+        assert norm_weight.numel() == hidden.shape[1]
+    z = sc = vel = None
+    use_cfg = x1 = 0
+    if euler is not None:
+        z, sc, use_cfg, x1, vel = euler
+        _req(z, BF16, "z"); _req(sc, F32, "scalars_dev")
+        assert z.shape == pred.shape and sc.numel() >= 3
+        if vel is not None:
+            _req(vel, BF16, "vel_out")
+            assert vel.numel() >= (z.numel() // 2 if use_cfg else z.numel())
+    _lib.call("vgpt_final_layer", _p(hidden), hidden.shape[1], _p(norm_weight), float(rms_eps), _p(lat_row0), _p(mod),
+              _p(w), _p(bias), _p(pred), n_lat, c, lat_h, lat_w, _p(z), _p(vel), _p(sc), int(bool(use_cfg)), int(bool(x1)),
+              _stream())
     return pred
 
 
-def final_layer_rows(hidden, row_kind, row_a, row_b, mod, w, bias, pred_ptrs, n_preds: int, lat_h: int, lat_w: int):
+def final_layer_rows(hidden, row_kind, row_a, row_b, mod, w, bias, pred_ptrs, n_preds: int, lat_h: int, lat_w: int,
+                     norm_weight=None, rms_eps: float = 0.0):
     """Row-driven final layer; ``pred_ptrs``: ctypes ``void*[n_preds]`` of ``[n_lat,4,lat_h,lat_w]`` buffers."""
     _req(hidden, BF16, "hidden"); _req(mod, BF16, "mod"); _req(w, BF16, "w"); _req(bias, BF16, "bias")
     rows = hidden.shape[0]
     for n, t in (("row_kind", row_kind), ("row_a", row_a), ("row_b", row_b)):
         _req(t, I32, n)
         assert t.numel() >= rows
-    _lib.call("vgpt_final_layer_rows", _p(hidden), rows, hidden.shape[1], _p(row_kind), _p(row_a), _p(row_b),
-              _p(mod), _p(w), _p(bias), pred_ptrs, n_preds, 4, lat_h, lat_w, _stream())
+    if norm_weight is not None:
+        _req(norm_weight, BF16, "norm_weight")
+    _lib.call("vgpt_final_layer_rows", _p(hidden), rows, hidden.shape[1], _p(norm_weight), float(rms_eps), _p(row_kind),
+              _p(row_a), _p(row_b), _p(mod), _p(w), _p(bias), pred_ptrs, n_preds, 4, lat_h, lat_w, _stream())
 
 
 def cfg_euler(z, pred, use_cfg: bool, x1_mode: bool, one_minus_sigma: float = 1.0, dsigma: float = 0.0,

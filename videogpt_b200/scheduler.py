@@ -67,18 +67,26 @@ class LVMScheduler:
         n = e.plan.n_latents
         assert len(z) == n
         e.z.copy_(torch.cat([t.reshape(1, 4, lat_h, lat_w) for t in z], 0) if is_list else z)
-        vel = torch.empty_like(e.z[: n // 2 if use_cfg else n]) if self.record_velocity is not None else None
-        e.uniform_t = True              # one sigma for every latent (scheduler.py:171)
+        x1 = prediction_type == "x1"
+        n_half = n // 2 if use_cfg else n
+        # per-step inputs of the whole clip in one table: [sigma_i x n | 1 - sigma_i, sigma_{i+1} - sigma_i, guidance]
+        # (the scalars exactly as the reference forms them); one device-to-device copy per step selects row i
+        rows = [[float(self.sigma[i])] * n + list(self._scalars(i)) + [guidance] for i in range(self.num_steps)]
+        table = torch.tensor(rows, dtype=torch.float32).to(e.step_inputs.device, non_blocking=True)
+        fused = e.peers is None          # single GPU: the update rides in the final-layer kernel of the step graph
+        e.uniform_t = True               # one sigma for every latent (scheduler.py:171)
+        e.euler_mode = (use_cfg, x1) if fused else None
         try:
             for i in range(self.num_steps):
-                e.t.fill_(float(self.sigma[i]))
+                e.step_inputs.copy_(table[i])
                 e.predict()
-                oms, ds = self._scalars(i)
-                ops.cfg_euler(e.z, e.pred, use_cfg, prediction_type == "x1", oms, ds, guidance, vel_out=vel)
-                if vel is not None:
-                    self.record_velocity.append(vel.clone())
+                if not fused:            # sequence-parallel ranks: every rank applies the update to its full copy of z
+                    ops.cfg_euler(e.z, e.pred, use_cfg, x1, scalars_dev=e.scalars, vel_out=e.vel[:n_half])
+                if self.record_velocity is not None:
+                    self.record_velocity.append(e.vel[:n_half].clone())
         finally:
             e.uniform_t = False
+            e.euler_mode = None
         if e.peers is not None:
             # sequence parallel: a barrier that timed out (a peer died or fell behind by ~10 s) lets this rank run
             # on K/V and prediction rows its peers never delivered -- never return such latents as a result
