@@ -6,6 +6,7 @@ run() { name=$1; shift; local t0=$SECONDS; timeout "$@" > gpurun_out/$name.log 2
 PT="python -m pytest -q -m gpu --no-header -p no:cacheprovider --tb=short"
 run kernel_tests 600 $PT tests/test_kernels_gpu.py tests/test_umma_layouts.py
 run umma_rate 100 python tools/umma_rate.py
+VGPT_ATTN_VARIANT=8 run attn_trace 100 python tools/attn_trace.py
 run gemmsweep 120 python tools/gemm_bench.py
 run gemmsweep_1040 120 python tools/gemm_bench.py 1040
 run model_tests 900 $PT tests/test_model_gpu.py tests/test_zz_batch_gpu.py tests/test_zz_rollout_gpu.py tests/test_sequence_parallel.py

@@ -51,8 +51,9 @@ struct PairCfg {
   static constexpr int kChunkBytes = 128 * kRowBytes;
   static constexpr int kTileBytes = kChunks * kChunkBytes;    // Q, K or V tile = 128 * D * 2
   static constexpr int kStages = (D == 128) ? 2 : (D == 96 ? 3 : 4);
-  static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + 1024;   // tiles + barriers + tile table + align
-  static constexpr int kSmemTrace = kSmem + 4 * 512 * 8;       // + the diagnostic instantiation's stamp rings
+  static constexpr int kCodeScratch = 8 * 128 * 4;            // one tile of key codes per softmax warp
+  static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + kCodeScratch + 1024;   // tiles + barriers + tile table + code scratch + align
+  static constexpr int kSmemTrace = kSmem + 10 * 192 * 8;      // + the diagnostic instantiation's stamp rings
   static constexpr int kTmemO = 256;                          // O_A at 256, O_B at 256 + D
   // 64 spare TMEM columns (head_dim <= 96): P gets its own buffer, shared by the two tiles, and
   // S_x(j+1) is issued as soon as the softmax warps have read S_x(j) -- it runs under softmax(j).
@@ -86,8 +87,8 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
       : "f"(a0), "f"(a1));
 }
 
-// Diagnostic instantiation (VGPT_ATTN_VARIANT=8, tools/attn_trace.py): lane 0 of four warps of CTA (0, 0, 0) -- softmax
-// A quad 0, softmax B quad 0, the TMA producer and the MMA issuer -- stamp the SM clock at every hand-over between the
+// Diagnostic instantiation (VGPT_ATTN_VARIANT=8, tools/attn_trace.py): lane 0 of ten warps of CTA (0, 0, 0) -- the eight
+// softmax warps, the TMA producer and the MMA issuer -- stamp the SM clock at every hand-over between the
 // roles into a per-warp ring in SHARED memory (a clock read and one st.shared: tens of cycles; a first version stamped
 // through a global atomic counter and cost ~900 cycles per event, which distorted the very timeline it recorded:
 // profiles/r02b_attn_trace_atomic_stamps.txt); the rings are copied to global memory when the CTA is done.  The default
@@ -95,7 +96,7 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
 // every fourth / every second exponential as a polynomial on the FMA pipe -- were validated and timed in round 2:
 // bit-exact / within 2^-7, and 0.3 - 2.8 us SLOWER than the default at cfg2 (profiles/r02b_attn_variants.txt): the MUFU
 // unit is 39 % busy, not the limit.  They were deleted.)
-constexpr int kTraceRoles = 4, kTracePerRole = 512;
+constexpr int kTraceRoles = 10, kTracePerRole = 192;     // warps 0..7 (softmax A / B, every quadrant), 8 (TMA), 9 (MMA)
 constexpr int kTraceMax = kTraceRoles * kTracePerRole;
 __device__ unsigned long long g_attn_trace[2 * kTraceMax];     // (clock, warp << 40 | tile << 32 | j << 8 | event)
 __device__ unsigned int g_attn_trace_n;
@@ -168,11 +169,11 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const bool has_b = rows_cta > kPairBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Tracer<TRACE> tr;
-  [[maybe_unused]] uint2* trace_rings = reinterpret_cast<uint2*>(t_kt + kPairMaxTiles);
+  int4* t_kcode = reinterpret_cast<int4*>(t_kt + kPairMaxTiles);                    // [softmax warp][32 lanes] key codes of a tile
+  [[maybe_unused]] uint2* trace_rings = reinterpret_cast<uint2*>(t_kcode + 8 * 32);
   __shared__ int s_trace_n[kTraceRoles];
   if constexpr (TRACE) {
-    const int role = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : warp == 9 ? 3 : -1;
-    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && role >= 0) tr.ring = trace_rings + role * kTracePerRole;
+    if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && warp < kTraceRoles) tr.ring = trace_rings + warp * kTracePerRole;
   }
 
   // ---- CTA-wide max of the valid query codes (tile classification) -----------------------------
@@ -264,16 +265,29 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
     constexpr uint32_t idesc_s = make_idesc_bf16(128, kPairBN);        // S = Q K^T (both K-major)
     constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O = P V   (V MN-major)
+    // Descriptors: everything but the 14-bit start address is constant, and the start addresses of one issue differ by
+    // compile-time offsets -- one add per descriptor on the low word.  (Rebuilding every descriptor from its byte
+    // address cost ~70 uniform-datapath instructions in front of each group of MMAs, four times per KV tile, on a warp
+    // that shares its scheduler with two softmax warps: the trace showed 300 - 700 idle cycles of the MMA warp between
+    // hand-overs it was not waiting for, profiles/r02d_attn_trace.txt.)
+    constexpr uint64_t kDescQK = make_smem_desc(0, 16, 8 * C::kRowBytes, C::kLayout);                // K-major Q / K
+    constexpr uint64_t kDescV = make_smem_desc(0, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);     // MN-major V
+    constexpr uint32_t kStageStep = (2 * C::kTileBytes) >> 4;
+    auto desc = [](uint64_t fixed, uint32_t lo) { return (fixed & 0xffffffff00000000ull) | (uint64_t)lo; };
+    const uint32_t q_lo0 = (uint32_t)kDescQK | ((s_q >> 4) & 0x3fffu);
+    const uint32_t q_lo1 = q_lo0 + (C::kTileBytes >> 4);
+    const uint32_t k_lo0 = (uint32_t)kDescQK | ((s_kv >> 4) & 0x3fffu);
+    const uint32_t v_lo0 = (uint32_t)kDescV | (((s_kv + C::kTileBytes) >> 4) & 0x3fffu);
     auto issue_s = [&](int x, int stage) {
       if (elect_one_sync()) {
-        const uint32_t sk = s_kv + 2 * stage * C::kTileBytes, sqx = s_q + x * C::kTileBytes;
+        const uint32_t ql = x ? q_lo1 : q_lo0, kl = k_lo0 + (uint32_t)stage * kStageStep;
+        const uint32_t td = tmem + x * 128;
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
 #pragma unroll
           for (int ks = 0; ks < C::kCW / 16; ++ks) {
-            const uint64_t da = make_smem_desc(sqx + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
-            const uint64_t db = make_smem_desc(sk + c * C::kChunkBytes + ks * 32, 16, 8 * C::kRowBytes, C::kLayout);
-            umma_f16_ss(tmem + x * 128, da, db, idesc_s, (c | ks) ? 1u : 0u);
+            const uint32_t off = (uint32_t)(c * C::kChunkBytes + ks * 32) >> 4;
+            umma_f16_ss(td, desc(kDescQK, ql + off), desc(kDescQK, kl + off), idesc_s, (c | ks) ? 1u : 0u);
           }
         }
         if (!(dbg & 32)) umma_commit(bar_s_full(x));          // (dbg & 32: timing probe, fewer commits)
@@ -282,13 +296,12 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     };
     auto issue_pv = [&](int x, int stage, int j, bool release_kv) {
       if (elect_one_sync()) {
-        const uint32_t sv = s_kv + 2 * stage * C::kTileBytes + C::kTileBytes;
+        const uint32_t vl = v_lo0 + (uint32_t)stage * kStageStep;
+        const uint32_t td = tmem + C::kTmemO + x * D, tp = tmem + (C::kEarlyS ? C::kTmemP : x * 128);
 #pragma unroll
-        for (int ks = 0; ks < kPairBN / 16; ++ks) {
-          const uint64_t db = make_smem_desc(sv + ks * 16 * C::kRowBytes, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);
-          umma_f16_ts(tmem + C::kTmemO + x * D, tmem + (C::kEarlyS ? C::kTmemP : x * 128) + ks * 8, db, idesc_o,
+        for (int ks = 0; ks < kPairBN / 16; ++ks)
+          umma_f16_ts(td, tp + ks * 8, desc(kDescV, vl + (uint32_t)((ks * 16 * C::kRowBytes) >> 4)), idesc_o,
                       (j > 0 || ks > 0) ? 1u : 0u);
-        }
         if (!(dbg & 32) || j == n_vis - 1) umma_commit(bar_o_full(x));
         if (release_kv) umma_commit(bar_kv_empty(stage));     // K(j), V(j) free once everything issued so far is done
       }
@@ -372,36 +385,22 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       for (int j = 0; j < n_vis; ++j) {
         if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
         const int tmax = t_tmax[j], kt = t_kt[j];                 // (shared memory, before the wait)
+        // Rare (the two tag rows at a frame start, the ragged last tile): some row of this warp cannot see the whole
+        // tile.  The tile's 128 key codes are fetched BEFORE the wait for S (one int4 per lane: the global-memory
+        // latency hides under the MMAs) and applied to S in registers below.  (A first version patched S in place in
+        // tensor memory, 32 columns at a time with the codes loaded inside the loop: 2200 cycles per tile for the
+        // whole CTA to protect two rows -- profiles/r02d_attn_trace.txt, tiles 8..16 of tile A.)
+        const bool pred = (kt + 1) * kPairBN > sq.kv_len || __any_sync(0xffffffffu, qc < tmax);
+        int4 kc4 = make_int4(0, 0, 0, 0);
+        if (pred) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN) + lane);
         mbar_wait(bar_s_full(x), j & 1);
-        if (quad == 0) tr(x, j, kEvSFull);
+        tr(x, j, kEvSFull);
         tc_fence_after();
         if (dbg & 1) {                                            // timing probe: tensor-pipe chain only
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (C::kEarlyS) mbar_arrive(bar_s_free(x)); mbar_arrive(bar_p_full(x)); }
           continue;
-        }
-        if ((kt + 1) * kPairBN > sq.kv_len || __any_sync(0xffffffffu, qc < tmax)) {
-          // Rare (the two tag rows at a frame start, the ragged last tile): apply the code predicate
-          // to S in place in tensor memory, 32 columns at a time, so the hot path below keeps its
-          // registers.
-          const int4* kcode = reinterpret_cast<const int4*>(kc + kt * kPairBN);
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t t[32];
-            tmem_ld_32x32b_x32(t_s + c * 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int4 c4 = __ldg(kcode + c * 8 + i);
-              if (qc < c4.x) t[4 * i + 0] = 0xff800000u;          // -inf
-              if (qc < c4.y) t[4 * i + 1] = 0xff800000u;
-              if (qc < c4.z) t[4 * i + 2] = 0xff800000u;
-              if (qc < c4.w) t[4 * i + 3] = 0xff800000u;
-            }
-            tmem_st_32x32b_x32(t_s + c * 32, t);
-          }
-          tmem_st_wait();
         }
         uint32_t s[128];
 #pragma unroll
@@ -413,7 +412,21 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_s_free(x));
         }
-        if (quad == 0) tr(x, j, kEvSRead);
+        tr(x, j, kEvSRead);
+        if (pred) {                                               // warp-uniform
+          int4* my = t_kcode + warp * 32;
+          my[lane] = kc4;
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int4 c4 = my[i];                                // broadcast read
+            if (qc < c4.x) s[4 * i + 0] = 0xff800000u;            // -inf
+            if (qc < c4.y) s[4 * i + 1] = 0xff800000u;
+            if (qc < c4.z) s[4 * i + 2] = 0xff800000u;
+            if (qc < c4.w) s[4 * i + 3] = 0xff800000u;
+          }
+          __syncwarp();                                           // scratch is rewritten for the next tile
+        }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -440,7 +453,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           fadd2(sum0, sum1, p0, p1);
           s[i] = pack_bf16x2(p0, p1);                             // P overwrites the dead half of s[]
         }
-        if (quad == 0) tr(x, j, kEvExpDone);
+        tr(x, j, kEvExpDone);
         if constexpr (C::kEarlyS) {
           // the P buffer is shared: its previous reader is P V of the other tile (B: tile j of A;
           // A: tile j-1 of B), or of this tile when it is alone
@@ -450,7 +463,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             mbar_wait(bar_o_full(y), need & 1);
             tc_fence_after();
           }
-          if (quad == 0) tr(x, j, kEvPBufFree);
+          tr(x, j, kEvPBufFree);
           tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
           tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
         } else {
@@ -477,14 +490,14 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 per tile)
-        if (quad == 0) tr(x, j, kEvPWritten);
+        tr(x, j, kEvPWritten);
       }
       // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------
       if (n_vis > 0) {
         mbar_wait(bar_o_full(x), (n_vis - 1) & 1);
         tc_fence_after();
       }
-      if (quad == 0) tr(x, n_vis, kEvEpilogue);
+      tr(x, n_vis, kEvEpilogue);
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __nv_bfloat16* orow = out + (size_t)grow * out_ld + head * D;
 #pragma unroll
@@ -519,14 +532,13 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   __syncthreads();
   if constexpr (TRACE) {
     if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0) {       // rings -> global memory, role after role
-      const int role_warp[kTraceRoles] = {0, 4, 8, 9};
       int base = 0;
       for (int r = 0; r < kTraceRoles; ++r) {
         const int n = s_trace_n[r];
         for (int i = threadIdx.x; i < n; i += kPairThreads) {
           const uint2 e = trace_rings[r * kTracePerRole + i];
           g_attn_trace[2 * (base + i)] = e.x;
-          g_attn_trace[2 * (base + i) + 1] = ((unsigned long long)role_warp[r] << 40) | ((unsigned long long)(e.y >> 28) << 32) |
+          g_attn_trace[2 * (base + i) + 1] = ((unsigned long long)r << 40) | ((unsigned long long)(e.y >> 28) << 32) |
                                              (unsigned long long)(e.y & 0x0fffffffu);
         }
         base += n;
