@@ -287,7 +287,7 @@ def run_ours(args, rank, world, local_rank):
     # (all rows of those videos and both CFG branches in one [M, hidden] matrix)
     vids_rank = 0
     if args.config in BATCH_VIDEOS:
-        total = BATCH_VIDEOS[args.config]
+        total = args.videos or BATCH_VIDEOS[args.config]
         if args.parallelism != "dp" or total % world or (total // world) % args.batch:
             raise SystemExit(f"{args.config}: {total} videos need --parallelism dp, a world size dividing {total} "
                              f"and --batch dividing {total}//world")
@@ -580,6 +580,8 @@ def main():
                          "sp = sequence parallel groups of --sp ranks per video")
     ap.add_argument("--sp", type=int, default=0, help="ranks per sequence-parallel group (default: all)")
     ap.add_argument("--batch", type=int, default=4, help="cfg4: videos per engine pass on a rank")
+    ap.add_argument("--videos", type=int, default=0, help="cfg4: total videos of the job (default 32 = BASELINE configs[3]; "
+                    "a smaller job is a SAMPLE of it, e.g. 8 videos on 1 GPU = the share of two of eight ranks)")
     ap.add_argument("--rollout", type=int, default=0, help="a step = this many clips generated autoregressively in "
                     "latent space (window = the workload's context + clip); 0 = one clip per step")
     ap.add_argument("--recompute", action="store_true", help="--rollout without the persistent K/V cache")

@@ -18,7 +18,7 @@ def _declared():
     text = open(os.path.join(ROOT, "include", "vgpt_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     out = {}
-    for m in re.finditer(r"(?:int|const char\*)\s+(vgpt_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"(?:int|size_t|const char\*)\s+(vgpt_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         args = m.group(2).strip()
         out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
     return out

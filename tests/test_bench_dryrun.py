@@ -50,7 +50,7 @@ def _run(monkeypatch, capsys, argv, workload):
         line["strong_scaling"] = bench.strong_scaling_single(argv["strong_single"])
     return json.loads(json.dumps(line))        # must be JSON-serialisable
 
-BASE = dict(gpus=1, steps=1, warmup=1, impl="ours", parallelism="dp", sp=0, batch=2, rollout=0, recompute=False,
+BASE = dict(gpus=1, steps=1, warmup=1, impl="ours", parallelism="dp", sp=0, batch=2, videos=0, rollout=0, recompute=False,
             no_baselines=False, strong="none", strong_timeout=10)
 
 def test_default(emu, monkeypatch, capsys):
