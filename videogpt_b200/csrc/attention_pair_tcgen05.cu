@@ -20,7 +20,8 @@
 //     whose maximum did not move use alpha == 1 exactly -- results do not depend on which rows
 //     share a tile (sequence parallelism relies on it).
 //   * The code predicate is evaluated only by warps that contain a row that cannot see the whole
-//     tile (the two tag rows at a frame start) and on the ragged last tile.
+//     tile (the two tag rows at a frame start) and on the ragged last tile -- in registers, from key codes
+//     prefetched before the wait for S; on a tile whose keys all carry one code such a row simply contributes P = 0.
 //
 // Warp roles (384 threads = 3 warpgroups): warps 0..3 = softmax / epilogue of tile A, warps 4..7 =
 // of tile B (TMEM lane quadrant = warp_idx % 4), warp 8 = TMA producer, warp 9 = TMEM allocator +
@@ -121,6 +122,7 @@ struct Tracer {
   }
 };
 
+constexpr int kTileUniform = 1 << 30;   // flag in the tile table's logical index: all 128 keys of the tile share one code
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
 template <int D, bool TRACE>
@@ -214,17 +216,18 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     for (int b0 = 0; b0 < n_kt; b0 += 32) {
       const int kt = b0 + lane;
       bool vis = false;
-      int tmax = 0, page = 0;
+      int tmax = 0, page = 0, uni = 0;
       if (kt < n_kt) {
         const int4 m4 = *reinterpret_cast<const int4*>(mm + 4 * kt);
         vis = min(m4.x, m4.z) <= q_max;               // else: fully masked for every query of this CTA
         tmax = max(m4.y, m4.w);
+        uni = min(m4.x, m4.z) == tmax ? kTileUniform : 0;     // every key of the tile carries the same code
         page = pt[kt];
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, vis);
       if (vis) {
         const int i = n + __popc(bal & ((1u << lane) - 1u));
-        t_page[i] = page; t_tmax[i] = tmax; t_kt[i] = kt;
+        t_page[i] = page; t_tmax[i] = tmax; t_kt[i] = kt | uni;
       }
       n += __popc(bal);
     }
@@ -244,7 +247,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     int stage = 0; uint32_t phase = 0;
     for (int i = 0; i < n_vis; ++i) {
       const int row = (t_page[i] * H + head) * kPairBN;         // pool viewed as [(page*H + head)*128 + tok][D]
-      mbar_wait(bar_kv_empty(stage), phase ^ 1);
+      mbar_wait_relaxed(bar_kv_empty(stage), phase ^ 1);
       tr(0, i, kEvKvEmpty);
       if ((dbg & 8) && i >= kStages) {                          // timing probe: operands not refreshed
         if (elect_one_sync()) mbar_arrive(bar_kv_full(stage));
@@ -384,15 +387,23 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_vis; ++j) {
         if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
-        const int tmax = t_tmax[j], kt = t_kt[j];                 // (shared memory, before the wait)
-        // Rare (the two tag rows at a frame start, the ragged last tile): some row of this warp cannot see the whole
-        // tile.  The tile's 128 key codes are fetched BEFORE the wait for S (one int4 per lane: the global-memory
-        // latency hides under the MMAs) and applied to S in registers below.  (A first version patched S in place in
-        // tensor memory, 32 columns at a time with the codes loaded inside the loop: 2200 cycles per tile for the
-        // whole CTA to protect two rows -- profiles/r02d_attn_trace.txt, tiles 8..16 of tile A.)
-        const bool pred = (kt + 1) * kPairBN > sq.kv_len || __any_sync(0xffffffffu, qc < tmax);
+        const int tmax = t_tmax[j], ktu = t_kt[j];                // (shared memory, before the wait)
+        const int kt = ktu & (kTileUniform - 1);
+        // Rows that cannot see the whole tile (the two tag rows at a frame start; everybody on the ragged last tile):
+        //   * tile with ONE key code (most: 256 patch tokens per frame): such a row sees none of it -- it runs the
+        //     same instructions with multiplier 0 / offset -inf (P = 0 exactly) and leaves the row maximum alone;
+        //   * mixed tile: the 128 key codes are fetched BEFORE the wait for S (one int4 per lane: the latency hides
+        //     under the MMAs), staged in shared memory and applied to S in registers, without predicates
+        //     (sign-mask + LOP3: seven predicate registers would serialise 128 compare / select pairs).
+        // (First version: S patched in place in tensor memory, 32 columns at a time, codes loaded inside the loop:
+        // 2200 cycles per tile for the whole CTA to protect two rows -- profiles/r02d_attn_trace.txt, tiles 8..16.)
+        const bool ragged = (kt + 1) * kPairBN > sq.kv_len;
+        const bool hidden = qc < tmax;
+        const bool some = ragged || __any_sync(0xffffffffu, hidden);
+        const bool elementwise = some && (ragged || !(ktu & kTileUniform));     // warp-uniform
+        const bool blind = some && !elementwise && hidden;                        // per row
         int4 kc4 = make_int4(0, 0, 0, 0);
-        if (pred) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN) + lane);
+        if (elementwise) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN) + lane);
         mbar_wait(bar_s_full(x), j & 1);
         tr(x, j, kEvSFull);
         tc_fence_after();
@@ -413,17 +424,19 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           if (lane == 0) mbar_arrive(bar_s_free(x));
         }
         tr(x, j, kEvSRead);
-        if (pred) {                                               // warp-uniform
+        if (elementwise) {
           int4* my = t_kcode + warp * 32;
           my[lane] = kc4;
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int4 c4 = my[i];                                // broadcast read
-            if (qc < c4.x) s[4 * i + 0] = 0xff800000u;            // -inf
-            if (qc < c4.y) s[4 * i + 1] = 0xff800000u;
-            if (qc < c4.z) s[4 * i + 2] = 0xff800000u;
-            if (qc < c4.w) s[4 * i + 3] = 0xff800000u;
+            const uint32_t m0 = (uint32_t)((qc - c4.x) >> 31), m1 = (uint32_t)((qc - c4.y) >> 31);   // all ones: hidden
+            const uint32_t m2 = (uint32_t)((qc - c4.z) >> 31), m3 = (uint32_t)((qc - c4.w) >> 31);
+            s[4 * i + 0] = (s[4 * i + 0] & ~m0) | (0xff800000u & m0);                                // -inf
+            s[4 * i + 1] = (s[4 * i + 1] & ~m1) | (0xff800000u & m1);
+            s[4 * i + 2] = (s[4 * i + 2] & ~m2) | (0xff800000u & m2);
+            s[4 * i + 3] = (s[4 * i + 3] & ~m3) | (0xff800000u & m3);
           }
           __syncwarp();                                           // scratch is rewritten for the next tile
         }
@@ -435,7 +448,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           mx2 = fmaxf(mx2, __uint_as_float(s[4 * i + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(s[4 * i + 3]));
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        const float mx = blind ? -INFINITY : fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         const bool grew = mx > m_run + thresh;                   // also true for the first finite maximum
         const float m_new = grew ? mx : m_run;
         const float sub = (m_new == -INFINITY) ? 0.f : __fmul_rn(m_new, scale_log2);
@@ -444,11 +457,11 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                             : (m_run == -INFINITY) ? 0.f
                                                    : ex2_ftz(__fsub_rn(__fmul_rn(m_run, scale_log2), sub));
         float sum0 = 0.f, sum1 = 0.f;
-        const float nsub = -sub;
+        const float nsub = blind ? -INFINITY : -sub, mul = blind ? 0.f : scale_log2;
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
           float p0, p1;
-          ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), scale_log2, nsub);
+          ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), mul, nsub);
           if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
           fadd2(sum0, sum1, p0, p1);
           s[i] = pack_bf16x2(p0, p1);                             // P overwrites the dead half of s[]

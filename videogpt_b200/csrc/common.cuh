@@ -124,6 +124,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// for waits that are long and not latency-critical (a producer waiting for a free stage): do not burn the issue
+// slots of the warps that share the scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA: 2-D / 4-D tiled tensor-map loads into shared memory, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------

@@ -377,7 +377,11 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (lane == 0) st_release_gpu(sm + 1, 1u);
           } else {
             if (lane == 0) {
+              // the other unit has claimed the slot: it is past its MMAs and parking its accumulator (microseconds).
+              // Bounded: a protocol error must abort the launch, not hang the device.
+              long long spins = 0;
               while (ld_acquire_gpu(sm + 1) == 0u) {
+                if (++spins > (1ll << 24)) __trap();
               }
             }
             __syncwarp();
@@ -388,11 +392,12 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             for (int c = 0; c < BN / 32; ++c) {
               uint32_t acc[32];
               tmem_ld_32x32b_x32(taddr + c * 32, acc);
-              if (row < M && n0 + c * 32 < N) {
-                float4 part[8];
+              const bool ok = row < M && n0 + c * 32 < N;
+              float4 part[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) part[q] = __ldcg(wsp + (c * 8 + q) * 32);
-                tmem_ld_wait();
+              for (int q = 0; q < 8; ++q) part[q] = ok ? __ldcg(wsp + (c * 8 + q) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+              tmem_ld_wait();                                      // (.sync.aligned: never under a lane-dependent branch)
+              if (ok) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                   acc[4 * q + 0] = __float_as_uint(__uint_as_float(acc[4 * q + 0]) + part[q].x);
@@ -401,8 +406,6 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                   acc[4 * q + 3] = __float_as_uint(__uint_as_float(acc[4 * q + 3]) + part[q].w);
                 }
                 store_chunk<EPI>(acc, crow + c * 32, rrow + c * 32);
-              } else {
-                tmem_ld_wait();
               }
             }
             __syncwarp();
