@@ -163,7 +163,7 @@ def test_gemm_splitk_residual(ops, M, N, K):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     tiles = ((M + 255) // 256) * ((N + 255) // 256)
     sem = ws[:ws.numel() - tiles * 256 * 1024].view(torch.int32)          # semaphores sit in front of the accumulators
-    assert int(sem.abs().sum()) == 0
+    assert sem.numel() * 4 == 256 * 1024 and int(sem.abs().sum()) == 0
     plain = ops.gemm(a, w, residual=r, out=r.clone(), epilogue=1)       # same function, one fp32 rounding fewer
     assert _rel(outs[0], plain) < 2e-3
 
@@ -179,6 +179,13 @@ def test_gemm_splitk_rows_do_not_depend_on_the_launch_shape(ops):
     for r0, r1 in [(0, 2064), (2064, 4128), (1032, 2064), (516, 1032), (100, 117)]:
         part = ops.gemm_splitk(a[r0:r1], w, ws)
         assert torch.equal(part, full[r0:r1]), (r0, r1)
+    # launches of different shapes share the workspace (prefill / step, o_proj / down_proj): small after large after small
+    for r1 in (1032, 4128, 300, 2064, 4128):
+        assert torch.equal(ops.gemm_splitk(a[:r1], w, ws), full[:r1]), r1
+    w2 = _rand((512, K), 8, 0.05)
+    ref2 = ops.gemm_splitk(a[:2064], w2, ops.gemm_splitk_workspace(2064, 512, DEV))
+    assert torch.equal(ops.gemm_splitk(a[:2064], w2, ws), ref2)
+    assert torch.equal(ops.gemm_splitk(a, w, ws), full)
 
 
 def test_gemm_rejects_bad_arguments(ops):

@@ -508,10 +508,15 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_
                            CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-// Split-K workspace: [semaphores: 2 words per (tile, CTA of the pair, epilogue warp)] [fp32 accumulators: 256 KB per tile]
+// Split-K workspace: [semaphores: 2 words per (tile, CTA of the pair, epilogue warp)] [fp32 accumulators: 256 KB per tile].
+// The semaphore region has ONE size for every launch: launches of different shapes share a workspace (prefill and
+// denoising step, o_proj and down_proj), and what one shape parks as accumulators must never be another shape's
+// semaphores (the first engine run did exactly that: a step launch read a prefill launch's partial sums as
+// "claimed", both units of a tile waited for each other, and the bounded spin trapped -- gpurun_out of call r02g).
+constexpr size_t kSplitKMaxTiles = 4096;
+constexpr size_t kSplitKSemBytes = kSplitKMaxTiles * 8 * 2 * sizeof(unsigned int);     // 256 KB
 static size_t splitk_tiles(int M, int N) { return (size_t)((M + 255) / 256) * ((N + 255) / 256); }
-static size_t splitk_sem_bytes(int M, int N) { return (splitk_tiles(M, N) * 8 * 2 * sizeof(unsigned int) + 1023) / 1024 * 1024; }
-size_t gemm_splitk_workspace_bytes(int M, int N) { return splitk_sem_bytes(M, N) + splitk_tiles(M, N) * 256 * 1024; }
+size_t gemm_splitk_workspace_bytes(int M, int N) { return kSplitKSemBytes + splitk_tiles(M, N) * 256 * 1024; }
 
 // `tail_in_loop`: M = 256 q + tail with q >= 1, 0 < tail <= kTailMax: tile rows 0 .. q-2 are regular tiles, row q-1 is cut
 // into special pieces that also compute the tail rows.
@@ -581,7 +586,7 @@ static int launch_gemm(const void* A, const void* W, void* C, const void* R, int
   kern<<<2 * clusters, kGThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tw, tt, static_cast<__nv_bfloat16*>(C),
                                                             static_cast<const __nv_bfloat16*>(R), M, N, K, ldc,
                                                             debug_gemm_flags(), sched,
-                                                            reinterpret_cast<float4*>(static_cast<char*>(workspace) + splitk_sem_bytes(M, N)),
+                                                            reinterpret_cast<float4*>(static_cast<char*>(workspace) + kSplitKSemBytes),
                                                             static_cast<unsigned int*>(workspace), split);
   VGPT_CHECK_LAUNCH();
   return 0;
@@ -682,6 +687,7 @@ int gemm_bf16_splitk(const void* A, const void* W, void* C, const void* R, int M
                  "vgpt_gemm_bf16_splitk: pointers must be 16-byte aligned");
   VGPT_CHECK_ARG(epilogue == kEpiStore || epilogue == kEpiResidual, "vgpt_gemm_bf16_splitk: epilogue %d (store or residual)", epilogue);
   VGPT_CHECK_ARG(epilogue != kEpiResidual || R, "vgpt_gemm_bf16_splitk: residual epilogue needs R");
+  VGPT_CHECK_ARG(splitk_tiles(M, N) <= kSplitKMaxTiles, "vgpt_gemm_bf16_splitk: %zu tiles (at most %zu)", splitk_tiles(M, N), kSplitKMaxTiles);
   VGPT_CHECK_ARG(workspace_bytes >= gemm_splitk_workspace_bytes(M, N), "vgpt_gemm_bf16_splitk: workspace of %zu bytes, need %zu",
                  workspace_bytes, gemm_splitk_workspace_bytes(M, N));
   const int sms = device_sm_count();
