@@ -52,17 +52,6 @@ const char* vgpt_last_error(void);
 int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
                    int ldc, int epilogue, int block_n, int tail_mode, void* stream);
 
-/* The same product with K split in two (256 x 256 tiles; epilogue VGPT_EPI_STORE or VGPT_EPI_RESIDUAL): every tile is
- * computed as two units, the unit that finishes second adds the other's fp32 accumulator (parked in `workspace`) to
- * its own and runs the epilogue.  For o_proj / down_proj (N = hidden): 1.46 waves of tiles become 2.92 waves of half
- * tiles.  The split does not depend on M, so a row gets the same bits whatever rows share its launch (it differs in
- * the last bit from vgpt_gemm_bf16: one more fp32 rounding).  K % 128 == 0.  `workspace`:
- * vgpt_gemm_splitk_workspace_bytes(M, N) bytes of device memory, ZEROED ONCE by the caller (the kernel leaves its
- * semaphores zero again); launches sharing a workspace must be ordered on one stream. */
-size_t vgpt_gemm_splitk_workspace_bytes(int M, int N);
-int vgpt_gemm_bf16_splitk(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                          int ldc, int epilogue, void* workspace, size_t workspace_bytes, void* stream);
-
 /* gate_up_proj.weight [2I,K] ([gate | up] rows, Phi3MLP chunk(2)) -> block-interleaved rows. */
 int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream);
 

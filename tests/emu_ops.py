@@ -57,14 +57,6 @@ def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int 
     return out
 
 
-def gemm_splitk_workspace(rows: int, n: int, device):
-    return torch.zeros(1, dtype=torch.uint8)
-
-
-def gemm_splitk(a, w, workspace, out=None, residual=None, epilogue: int = EPI_STORE):
-    return gemm(a, w, out=out, residual=residual, epilogue=epilogue)
-
-
 def rmsnorm(x, weight, eps: float, out=None):
     _log("rmsnorm")
     xf = x.float()

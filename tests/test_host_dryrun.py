@@ -48,12 +48,6 @@ class StubOps:
         assert (residual is not None) == (epilogue == 1)
         return out
 
-    def gemm_splitk_workspace(self, rows, n, device):
-        return torch.zeros(1, dtype=torch.uint8)
-
-    def gemm_splitk(self, a, w, workspace, out=None, residual=None, epilogue=0):
-        return self.gemm(a, w, out=out, residual=residual, epilogue=epilogue)
-
     def rope_kv_append(self, qkv, row_pos, row_slot, table, k_pool, v_pool, heads, head_dim):
         self._log("rope_kv_append")
         assert row_pos.numel() == row_slot.numel() == qkv.shape[0]

@@ -141,53 +141,6 @@ def test_gemm_tail_in_loop_full_size_projections(ops):
             assert torch.equal(o1, o2), (M, N, K, epi)
 
 
-@pytest.mark.timeout(300)
-@pytest.mark.parametrize("M,N,K", [(2064, 3072, 3072), (2064, 3072, 8192), (1032, 3072, 3072), (130, 512, 1024),
-                                   (16, 3072, 128), (8208, 3072, 3072), (300, 1536, 256)])
-def test_gemm_splitk_residual(ops, M, N, K):
-    """K split in two over 256 x 256 tiles (o_proj / down_proj): against fp32 math, in place on the residual stream,
-    repeated launches on one workspace (the kernel leaves its semaphores zero), and bit-identical from launch to
-    launch (the two partial sums commute: no dependence on which unit of a tile finishes first)."""
-    a, w, r = _rand((M, K), 3), _rand((N, K), 4, 0.05), _rand((M, N), 5)
-    ws = ops.gemm_splitk_workspace(M, N, DEV)
-    ref = ((a.float() @ w.float().t()).to(BF).float() + r.float())
-    outs = []
-    for _ in range(3):
-        c = r.clone()
-        ops.gemm_splitk(a, w, ws, out=c, residual=c, epilogue=1)
-        torch.cuda.synchronize()
-        outs.append(c)
-    assert _rel(outs[0], ref) < 4e-3
-    err = (outs[0].float() - ref).abs().max().item()
-    assert err <= 2 ** -6 * ref.abs().max().item(), err
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
-    tiles = ((M + 255) // 256) * ((N + 255) // 256)
-    sem = ws[:ws.numel() - tiles * 256 * 1024].view(torch.int32)          # semaphores sit in front of the accumulators
-    assert sem.numel() * 4 == 256 * 1024 and int(sem.abs().sum()) == 0
-    plain = ops.gemm(a, w, residual=r, out=r.clone(), epilogue=1)       # same function, one fp32 rounding fewer
-    assert _rel(outs[0], plain) < 2e-3
-
-
-@pytest.mark.timeout(300)
-def test_gemm_splitk_rows_do_not_depend_on_the_launch_shape(ops):
-    """Sequence parallelism and batching compare bit for bit against single runs: a row must get the same bits
-    whatever rows share its launch (the split points are the same for every M)."""
-    N, K = 3072, 8192
-    a, w = _rand((4128, K), 6), _rand((N, K), 7, 0.05)
-    ws = ops.gemm_splitk_workspace(4128, N, DEV)
-    full = ops.gemm_splitk(a, w, ws)
-    for r0, r1 in [(0, 2064), (2064, 4128), (1032, 2064), (516, 1032), (100, 117)]:
-        part = ops.gemm_splitk(a[r0:r1], w, ws)
-        assert torch.equal(part, full[r0:r1]), (r0, r1)
-    # launches of different shapes share the workspace (prefill / step, o_proj / down_proj): small after large after small
-    for r1 in (1032, 4128, 300, 2064, 4128):
-        assert torch.equal(ops.gemm_splitk(a[:r1], w, ws), full[:r1]), r1
-    w2 = _rand((512, K), 8, 0.05)
-    ref2 = ops.gemm_splitk(a[:2064], w2, ops.gemm_splitk_workspace(2064, 512, DEV))
-    assert torch.equal(ops.gemm_splitk(a[:2064], w2, ws), ref2)
-    assert torch.equal(ops.gemm_splitk(a, w, ws), full)
-
-
 def test_gemm_rejects_bad_arguments(ops):
     from videogpt_b200._lib import VgptError
     with pytest.raises(VgptError):

@@ -34,18 +34,4 @@ for name, (N, K, epi) in shapes.items():
         t.record(); torch.cuda.synchronize()
         us = s.elapsed_time(t) * 1e3 / (5 * L)
         print(f"{name:8s} M={M} N={N} K={K} block_n={bn} pair={pair}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:8.1f} TFLOP/s", flush=True)
-    if epi == ops.EPI_RESIDUAL:        # K split in two over 256 x 256 tiles (what the engine runs for o / down)
-        wk = ops.gemm_splitk_workspace(M, N, dev)
-
-        def run():
-            for w in ws:
-                ops.gemm_splitk(a, w, wk, out=out, residual=out, epilogue=epi)
-        run(); torch.cuda.synchronize()
-        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(5):
-            run()
-        t.record(); torch.cuda.synchronize()
-        us = s.elapsed_time(t) * 1e3 / (5 * L)
-        print(f"{name:8s} M={M} N={N} K={K} split-K 2, block_n=256: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:8.1f} TFLOP/s", flush=True)
     del ws

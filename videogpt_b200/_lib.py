@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint32, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvgpt_b200.so")
@@ -18,8 +18,6 @@ SIGNATURES = {
     "vgpt_abi_version": [],
     "vgpt_last_error": [],
     "vgpt_gemm_bf16": [P, P, P, P, I, I, I, I, I, I, I, I, P],
-    "vgpt_gemm_splitk_workspace_bytes": [I, I],
-    "vgpt_gemm_bf16_splitk": [P, P, P, P, I, I, I, I, I, I, P, c_size_t, P],
     "vgpt_pack_gate_up": [P, P, I, I, P],
     "vgpt_rmsnorm": [P, P, P, I, I, F, P],
     "vgpt_rope_table": [P, P, I, I, P],
@@ -75,8 +73,7 @@ def load(path: str = LIB_PATH) -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = (c_char_p if name == "vgpt_last_error" else
-                      c_size_t if name == "vgpt_gemm_splitk_workspace_bytes" else c_int)
+        fn.restype = c_char_p if name == "vgpt_last_error" else c_int
     _lib = lib
     return lib
 

@@ -16,11 +16,6 @@ int vgpt_gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, 
                    int ldc, int epilogue, int block_n, int tail_mode, void* stream) {
   return vgpt::gemm_bf16(A, W, C, R, M, N, K, lda, ldc, epilogue, block_n, tail_mode, S(stream));
 }
-size_t vgpt_gemm_splitk_workspace_bytes(int M, int N) { return vgpt::gemm_splitk_workspace_bytes(M, N); }
-int vgpt_gemm_bf16_splitk(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
-                          int ldc, int epilogue, void* workspace, size_t workspace_bytes, void* stream) {
-  return vgpt::gemm_bf16_splitk(A, W, C, R, M, N, K, lda, ldc, epilogue, workspace, workspace_bytes, S(stream));
-}
 int vgpt_pack_gate_up(const void* w, void* packed, int I, int K, void* stream) {
   return vgpt::pack_gate_up(w, packed, I, K, S(stream));
 }

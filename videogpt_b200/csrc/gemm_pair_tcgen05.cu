@@ -27,17 +27,10 @@
 //     (A first form -- tail tiles of their own after the main tiles -- was bit-exact too but ran latency-bound:
 //     156 cycles of MMA work per stage against a stage round trip of thousands; profiles/r02b_gemm_sweep_fused_tail.txt.)
 //
-//   * SPLIT K IN TWO for the N = hidden projections (o_proj, down_proj; `vgpt_gemm_bf16_splitk`).  With 256 x 256
-//     tiles these shapes have 108 tiles for 74 clusters at M = 2064 (1.46 waves, the second 46 % full), and the
-//     192-wide tiles that fill two waves pull 14 % more bytes per flop through L2 -> SMEM, which is what bounds every
-//     GEMM here (all four shapes run at 11 - 12 TB/s of operand fill = the measured L2 slice throughput).  Every tile
-//     becomes two units (first / second half of K), all first halves before all second halves so concurrently running
-//     clusters still share operand panels; the unit of a tile that finishes FIRST parks its fp32 accumulator in a
-//     workspace (coalesced, TMEM-lane-major), the one that finishes SECOND adds it to its own and runs the epilogue.
-//     Two addends commute, so the result does not depend on which unit arrives first, and the split is the same for
-//     every M: a row gets the same bits whatever rows it shares a launch with (sequence parallelism and batching
-//     compare bit for bit against single runs).  Per-warp semaphores (claim, ready) live in front of the workspace and
-//     are reset by the finishing warp.
+//   * (Tried and deleted, round 2: K split in two over 256 x 256 tiles for o_proj / down_proj with an fp32 hand-over
+//     through a workspace.  Bit-stable and M-independent, but 3 waves of half tiles cost exactly the MMA cycles of 2 waves
+//     of 192-wide tiles, and the hand-over traffic ate the better main-loop efficiency of the wider tile: o_proj 51.9 vs
+//     45.4 us, down_proj 92.3 vs 92.3 us at M = 2064; profiles/r02g_gemm_sweep_splitk.txt.)
 //
 // Pair protocol (cluster of 2 along M; rank 0 = leader): both CTAs' TMA loads are .cta_group::2 and complete_tx on
 // the LEADER's full barrier (its arrive.expect_tx accounts for both halves); the leader's elected thread issues the
@@ -157,8 +150,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGThreads, 1)
 gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_wsp, const __grid_constant__ CUtensorMap tmap_t,
                       __nv_bfloat16* __restrict__ C, const __nv_bfloat16* __restrict__ R, int M, int N, int K, int ldc,
-                      int flags, const __grid_constant__ Sched sched, float4* __restrict__ ws, unsigned int* __restrict__ sem,
-                      int split) {
+                      int flags, const __grid_constant__ Sched sched) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // swizzle-128B atoms: 1 KB aligned
@@ -178,8 +170,6 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = K / kGBlockK;
-  const int num_units = num_tiles * split;                        // split == 2: unit u = (tile u % num_tiles, K half u / num_tiles)
-  const int kb_unit = k_blocks / split;
   const int n_special = sched.tail_rows > 0 ? sched.n_special : 0;
   const int sp_row0 = m_tiles * 2 * kGBlockM;                     // first row of the special tile row
   const uint32_t tail_off = (uint32_t)(sched.sp_width / 2) * kGBlockK * 2;   // tail rows behind the W rows in the B slot
@@ -209,11 +199,10 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-        const int tile = unit % num_tiles, kb0 = (unit / num_tiles) * kb_unit;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile % m_tiles) * 2 * kGBlockM + rank * kGBlockM;
         const int n0 = (tile / m_tiles) * BN + rank * (BN / 2);
-        for (int kb = kb0; kb < kb0 + kb_unit; ++kb) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
@@ -258,13 +247,13 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
         mbar_wait(tmem_empty_bar(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kAccStride;
-        for (int kb = 0; kb < kb_unit; ++kb) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -340,79 +329,13 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
       }
     };
-    for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++local) {
-      const int tile = unit % num_tiles;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       const int row = (tile % m_tiles) * 2 * kGBlockM + rank * kGBlockM + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + lane_base + as * kAccStride;
       mbar_wait(tmem_full_bar(as), aphase);
       tc_fence_after();
-      if (split == 1) {
-        drain_main(taddr, row, (tile / m_tiles) * BN, BN);
-      } else if constexpr (EPI != kEpiSwiGLU && BN == 256) {
-        // Two units per tile; this warp's 32 rows x 256 columns are its own hand-over: claim, then park or finish.
-        if (row - lane < M) {                                      // (warp-uniform) some row of this warp exists
-          const int slot = (tile * 2 + (int)rank) * 4 + quad;
-          unsigned int* sm = sem + 2 * slot;
-          float4* wsp = ws + (size_t)slot * (BN / 4) * 32 + lane;  // [column / 4][lane] float4: 512 B per warp store
-          unsigned int first = 0;
-          if (lane == 0) first = atomicAdd(sm, 1u) == 0u;
-          first = __shfl_sync(0xffffffffu, first, 0);
-          if (first) {
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-              uint32_t acc[32];
-              tmem_ld_32x32b_x32(taddr + c * 32, acc);
-              tmem_ld_wait();
-              if (row < M) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  wsp[(c * 8 + q) * 32] = make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
-                                                      __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
-              }
-            }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_release_gpu(sm + 1, 1u);
-          } else {
-            if (lane == 0) {
-              // the other unit has claimed the slot: it is past its MMAs and parking its accumulator (microseconds).
-              // Bounded: a protocol error must abort the launch, not hang the device.
-              long long spins = 0;
-              while (ld_acquire_gpu(sm + 1) == 0u) {
-                if (++spins > (1ll << 24)) __trap();
-              }
-            }
-            __syncwarp();
-            const int n0 = (tile / m_tiles) * BN;
-            __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
-            const __nv_bfloat16* rrow = (EPI == kEpiResidual) ? R + (size_t)row * ldc + n0 : nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-              uint32_t acc[32];
-              tmem_ld_32x32b_x32(taddr + c * 32, acc);
-              const bool ok = row < M && n0 + c * 32 < N;
-              float4 part[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) part[q] = ok ? __ldcg(wsp + (c * 8 + q) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-              tmem_ld_wait();                                      // (.sync.aligned: never under a lane-dependent branch)
-              if (ok) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  acc[4 * q + 0] = __float_as_uint(__uint_as_float(acc[4 * q + 0]) + part[q].x);
-                  acc[4 * q + 1] = __float_as_uint(__uint_as_float(acc[4 * q + 1]) + part[q].y);
-                  acc[4 * q + 2] = __float_as_uint(__uint_as_float(acc[4 * q + 2]) + part[q].z);
-                  acc[4 * q + 3] = __float_as_uint(__uint_as_float(acc[4 * q + 3]) + part[q].w);
-                }
-                store_chunk<EPI>(acc, crow + c * 32, rrow + c * 32);
-              }
-            }
-            __syncwarp();
-            if (lane == 0) { sm[0] = 0u; sm[1] = 0u; }             // ready for the next launch on this stream
-          }
-        }
-      }
+      drain_main(tmem_base + lane_base + as * kAccStride, row, (tile / m_tiles) * BN, BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tmem_empty_bar(as), 0);
@@ -508,21 +431,11 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t inner, uint64_
                            CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-// Split-K workspace: [semaphores: 2 words per (tile, CTA of the pair, epilogue warp)] [fp32 accumulators: 256 KB per tile].
-// The semaphore region has ONE size for every launch: launches of different shapes share a workspace (prefill and
-// denoising step, o_proj and down_proj), and what one shape parks as accumulators must never be another shape's
-// semaphores (the first engine run did exactly that: a step launch read a prefill launch's partial sums as
-// "claimed", both units of a tile waited for each other, and the bounded spin trapped -- gpurun_out of call r02g).
-constexpr size_t kSplitKMaxTiles = 4096;
-constexpr size_t kSplitKSemBytes = kSplitKMaxTiles * 8 * 2 * sizeof(unsigned int);     // 256 KB
-static size_t splitk_tiles(int M, int N) { return (size_t)((M + 255) / 256) * ((N + 255) / 256); }
-size_t gemm_splitk_workspace_bytes(int M, int N) { return kSplitKSemBytes + splitk_tiles(M, N) * 256 * 1024; }
-
 // `tail_in_loop`: M = 256 q + tail with q >= 1, 0 < tail <= kTailMax: tile rows 0 .. q-2 are regular tiles, row q-1 is cut
 // into special pieces that also compute the tail rows.
 template <int BN, int EPI>
 static int launch_gemm(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
-                       int num_sms, bool tail_in_loop, cudaStream_t stream, void* workspace = nullptr) {
+                       int num_sms, bool tail_in_loop, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb, tw, tt;
   int rc = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kGBlockM);
@@ -536,8 +449,7 @@ static int launch_gemm(const void* A, const void* W, void* C, const void* R, int
   memset(&sched, 0, sizeof(sched));
   int m_tiles_reg = (M + 2 * kGBlockM - 1) / (2 * kGBlockM);
   const int n_tiles = (N + BN - 1) / BN;
-  const int split = workspace ? 2 : 1;
-  int work_items = m_tiles_reg * n_tiles * split;
+  int work_items = m_tiles_reg * n_tiles;
   if (tail_in_loop) {
     const int tail = M % 256;
     m_tiles_reg = M / 256 - 1;
@@ -585,9 +497,7 @@ static int launch_gemm(const void* A, const void* W, void* C, const void* R, int
   VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   kern<<<2 * clusters, kGThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tw, tt, static_cast<__nv_bfloat16*>(C),
                                                             static_cast<const __nv_bfloat16*>(R), M, N, K, ldc,
-                                                            debug_gemm_flags(), sched,
-                                                            reinterpret_cast<float4*>(static_cast<char*>(workspace) + kSplitKSemBytes),
-                                                            static_cast<unsigned int*>(workspace), split);
+                                                            debug_gemm_flags(), sched);
   VGPT_CHECK_LAUNCH();
   return 0;
 }
@@ -671,28 +581,6 @@ int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N
 #undef VGPT_GEMM_CASE
   set_last_error("vgpt_gemm_bf16: no kernel for block_n=%d epilogue=%d", block_n, epilogue);
   return -1;
-}
-
-// K split in two, 256 x 256 tiles, plain tile rows (see the header).  `workspace`: gemm_splitk_workspace_bytes(M, N)
-// bytes, zeroed once by the caller; launches that share it must be ordered on one stream.
-int gemm_bf16_splitk(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
-                     int epilogue, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  VGPT_CHECK_ARG(A && W && C && workspace, "vgpt_gemm_bf16_splitk: null pointer");
-  VGPT_CHECK_ARG(M > 0 && N > 0 && K > 0, "vgpt_gemm_bf16_splitk: empty problem M=%d N=%d K=%d", M, N, K);
-  VGPT_CHECK_ARG(K % (2 * kGBlockK) == 0, "vgpt_gemm_bf16_splitk: K=%d must be a multiple of %d", K, 2 * kGBlockK);
-  VGPT_CHECK_ARG(N % 64 == 0, "vgpt_gemm_bf16_splitk: N=%d must be a multiple of 64", N);
-  VGPT_CHECK_ARG(lda >= K && lda % 8 == 0, "vgpt_gemm_bf16_splitk: lda=%d invalid", lda);
-  VGPT_CHECK_ARG(ldc % 8 == 0, "vgpt_gemm_bf16_splitk: ldc=%d must be a multiple of 8", ldc);
-  VGPT_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
-                 "vgpt_gemm_bf16_splitk: pointers must be 16-byte aligned");
-  VGPT_CHECK_ARG(epilogue == kEpiStore || epilogue == kEpiResidual, "vgpt_gemm_bf16_splitk: epilogue %d (store or residual)", epilogue);
-  VGPT_CHECK_ARG(epilogue != kEpiResidual || R, "vgpt_gemm_bf16_splitk: residual epilogue needs R");
-  VGPT_CHECK_ARG(splitk_tiles(M, N) <= kSplitKMaxTiles, "vgpt_gemm_bf16_splitk: %zu tiles (at most %zu)", splitk_tiles(M, N), kSplitKMaxTiles);
-  VGPT_CHECK_ARG(workspace_bytes >= gemm_splitk_workspace_bytes(M, N), "vgpt_gemm_bf16_splitk: workspace of %zu bytes, need %zu",
-                 workspace_bytes, gemm_splitk_workspace_bytes(M, N));
-  const int sms = device_sm_count();
-  if (epilogue == kEpiStore) return launch_gemm<256, kEpiStore>(A, W, C, R, M, N, K, lda, ldc, sms, false, stream, workspace);
-  return launch_gemm<256, kEpiResidual>(A, W, C, R, M, N, K, lda, ldc, sms, false, stream, workspace);
 }
 
 }  // namespace vgpt

@@ -25,9 +25,6 @@ const char* last_error();
 
 int gemm_bf16(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda,
               int ldc, int epilogue, int block_n, int tail_mode, cudaStream_t stream);
-int gemm_bf16_splitk(const void* A, const void* W, void* C, const void* R, int M, int N, int K, int lda, int ldc,
-                     int epilogue, void* workspace, size_t workspace_bytes, cudaStream_t stream);
-size_t gemm_splitk_workspace_bytes(int M, int N);
 int debug_gemm_flags();
 int pick_pair_block_n(int M, int N, int num_sms);
 int pack_gate_up(const void* w, void* packed, int I, int K, cudaStream_t s);

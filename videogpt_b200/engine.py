@@ -21,7 +21,6 @@ Design (B200-first, not the reference's control flow):
 from __future__ import annotations
 
 import math
-import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -36,8 +35,6 @@ INT_MAX = 2 ** 31 - 1
 # rejects anything else); the name exists so the CPU emulation in tests/emu_ops.py can run this
 # module's host logic in fp32 against the fp32 oracle.
 ACT_DTYPE = torch.bfloat16
-# VGPT_GEMM_SPLITK=0: o_proj / down_proj through the unsplit GEMM (A/B timing; last-bit differences)
-SPLIT_K = os.environ.get("VGPT_GEMM_SPLITK", "1") != "0"
 
 
 # --------------------------------------------------------------------------------------------
@@ -445,9 +442,6 @@ class NextClipEngine:
         self.qkv = torch.empty(rows, 3 * self.hs, device=dev, dtype=bf)
         self.attn = torch.empty(rows, self.hs, device=dev, dtype=bf)
         self.mlp_h = torch.empty(rows, self.inter, device=dev, dtype=bf)
-        # o_proj / down_proj run with K split in two (gemm_pair_tcgen05.cu): fp32 hand-over workspace + semaphores
-        self.gemm_ws = (ops.gemm_splitk_workspace(rows, self.hs, dev)
-                        if SPLIT_K and self.hs % 128 == 0 and self.inter % 128 == 0 else None)
         # paged KV pools: [layer][k|v][page][H][128][D]
         n = max(plan.n_latents, 1)
         self.z = torch.zeros(n, 4, plan.lat_h, plan.lat_w, device=dev, dtype=bf)
@@ -566,19 +560,12 @@ class NextClipEngine:
                 continue
             ops.attention(qkv[:, :self.hs], attn, self.kv[li, 0], self.kv[li, 1], plan.page_table, ph.seqs,
                           ph.max_q_rows, ph.q_code, plan.k_code, plan.k_tile_minmax, self.H, self.D, scale)
-            self._gemm_residual(attn, lw["o"], hidden)
+            ops.gemm(attn, lw["o"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
             ops.rmsnorm(hidden, lw["ln2"], self.eps, out=xn)
             ops.gemm(xn, lw["gate_up"], out=mlp_h, epilogue=ops.EPI_SWIGLU)
-            self._gemm_residual(mlp_h, lw["down"], hidden)
+            ops.gemm(mlp_h, lw["down"], out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
             if self.layer_tap is not None:
                 self.layer_tap.append(hidden.clone())
-
-    def _gemm_residual(self, a, w, hidden):
-        """``hidden += bf16(a @ w^T)`` in place (o_proj / down_proj + the residual add of Phi3DecoderLayer)."""
-        if self.gemm_ws is not None:
-            ops.gemm_splitk(a, w, self.gemm_ws, out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
-        else:
-            ops.gemm(a, w, out=hidden, residual=hidden, epilogue=ops.EPI_RESIDUAL)
 
     def _drive(self, gen):
         """Run a kernel-sequence generator; at its sync points enqueue the cross-GPU barrier."""

@@ -62,36 +62,6 @@ def gemm(a, w, out=None, residual=None, epilogue: int = EPI_STORE, block_n: int 
     return out
 
 
-def gemm_splitk_workspace(rows: int, n: int, device) -> torch.Tensor:
-    """Zeroed workspace for ``gemm_splitk`` launches of up to ``rows`` x ``n`` outputs (semaphores + one fp32
-    accumulator per 256 x 256 tile).  Launches that share it must be ordered on one stream."""
-    nbytes = _lib.load().vgpt_gemm_splitk_workspace_bytes(int(rows), int(n))
-    return torch.zeros(nbytes, device=device, dtype=torch.uint8)
-
-
-def gemm_splitk(a, w, workspace, out=None, residual=None, epilogue: int = EPI_STORE):
-    """``gemm`` with K split in two over 256 x 256 tiles (o_proj / down_proj: 2.9 waves of half tiles instead of 1.5
-    waves of tiles); the split is the same for every M, so a row's bits do not depend on the rows it shares a
-    launch with.  ``workspace`` from ``gemm_splitk_workspace``."""
-    _req(a, BF16, "a", contiguous=False)
-    _req(w, BF16, "w")
-    _req(workspace, torch.uint8, "workspace")
-    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and a.shape[1] == w.shape[1]
-    assert epilogue in (EPI_STORE, EPI_RESIDUAL)
-    M, K = a.shape
-    N = w.shape[0]
-    if out is None:
-        out = torch.empty(M, N, device=a.device, dtype=BF16)
-    _req(out, BF16, "out", contiguous=False)
-    assert out.shape == (M, N) and out.stride(1) == 1
-    if residual is not None:
-        _req(residual, BF16, "residual", contiguous=False)
-        assert residual.shape == out.shape and residual.stride(0) == out.stride(0)
-    _lib.call("vgpt_gemm_bf16_splitk", _p(a), _p(w), _p(out), _p(residual), M, N, K, a.stride(0),
-              out.stride(0), epilogue, _p(workspace), workspace.numel(), _stream())
-    return out
-
-
 def pack_gate_up(w):
     _req(w, BF16, "gate_up_proj.weight")
     two_i, k = w.shape
