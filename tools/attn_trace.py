@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 from oracle import processor_oracle as po  # noqa: E402
 from videogpt_b200 import _lib, engine as eng, ops  # noqa: E402
 
-EV = {1: "mma: S may issue", 2: "mma: S issued", 3: "mma: P ready", 4: "mma: PV issued", 10: "sm: S full", 11: "sm: S read",
+EV = {1: "mma: S may issue", 2: "mma: S issued", 3: "mma: P ready", 4: "mma: PV issued", 5: "mma: loop top", 6: "mma: fenced", 10: "sm: S full", 11: "sm: S read",
       12: "sm: exp done", 13: "sm: P buffer free", 14: "sm: P written", 15: "sm: epilogue", 20: "tma: stage free",
       21: "tma: stage issued", 30: "start", 31: "table done", 32: "end"}
 

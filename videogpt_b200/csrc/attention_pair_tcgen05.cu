@@ -103,7 +103,7 @@ __device__ unsigned long long g_attn_trace[2 * kTraceMax];     // (clock, warp <
 __device__ unsigned int g_attn_trace_n;
 
 enum : int {   // trace events
-  kEvSFree = 1, kEvSIssued = 2, kEvPFull = 3, kEvPVIssued = 4,                    // MMA warp
+  kEvSFree = 1, kEvSIssued = 2, kEvPFull = 3, kEvPVIssued = 4, kEvMmaTop = 5, kEvMmaFenced = 6,   // MMA warp
   kEvSFull = 10, kEvSRead = 11, kEvExpDone = 12, kEvPBufFree = 13, kEvPWritten = 14, kEvEpilogue = 15,   // softmax warps
   kEvKvEmpty = 20, kEvKvIssued = 21,                                                // TMA warp
   kEvStart = 30, kEvTableDone = 31, kEvEnd = 32
@@ -122,6 +122,7 @@ struct Tracer {
   }
 };
 
+constexpr float kMasked = -1e30f;        // score of a hidden (query, key) pair on a mixed tile: exp2 gives 0 exactly
 constexpr int kTileUniform = 1 << 30;   // flag in the tile table's logical index: all 128 keys of the tile share one code
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
@@ -329,10 +330,12 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const bool has_next = j + 1 < n_vis;
         for (int x = 0; x < (has_b ? 2 : 1); ++x) {
           if (has_next) {
+            tr(x, j + 1, kEvMmaTop);
             if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
             if (x == 0) mbar_wait(bar_kv_full(stage_s), phase_s);
             tr(x, j + 1, kEvSFree);
             tc_fence_after();
+            tr(x, j + 1, kEvMmaFenced);
             issue_s(x, stage_s);
             tr(x, j + 1, kEvSIssued);
           }
@@ -393,8 +396,8 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         //   * tile with ONE key code (most: 256 patch tokens per frame): such a row sees none of it -- it runs the
         //     same instructions with multiplier 0 / offset -inf (P = 0 exactly) and leaves the row maximum alone;
         //   * mixed tile: the 128 key codes are fetched BEFORE the wait for S (one int4 per lane: the latency hides
-        //     under the MMAs), staged in shared memory and applied to S in registers, without predicates
-        //     (sign-mask + LOP3: seven predicate registers would serialise 128 compare / select pairs).
+        //     under the MMAs), staged in shared memory and applied to S in registers with two FMA-pipe instructions
+        //     per score.
         // (First version: S patched in place in tensor memory, 32 columns at a time, codes loaded inside the loop:
         // 2200 cycles per tile for the whole CTA to protect two rows -- profiles/r02d_attn_trace.txt, tiles 8..16.)
         const bool ragged = (kt + 1) * kPairBN > sq.kv_len;
@@ -425,18 +428,22 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
         tr(x, j, kEvSRead);
         if (elementwise) {
-          int4* my = t_kcode + warp * 32;
-          my[lane] = kc4;
+          // hidden(q, k) = code_k > code_q, as fp32 arithmetic on the FMA pipe: sat(code_k - code_q) is exactly 0 or 1
+          // (codes are integers < 2^24, or the INT_MAX sentinel of padding / evicted keys), and s - 1e30 * hidden
+          // leaves a visible score untouched bit for bit.  (Integer compare + select, or sign-mask + LOP3, run on
+          // the half-rate ALU pipe: 256 - 384 instructions x 2 cycles put +1300 cycles on the one warp the whole
+          // tile waits for -- profiles/r02g_attn_trace_all_warps.txt, tiles 8 / 10 / 12 / 14.)
+          float4* my = reinterpret_cast<float4*>(t_kcode + warp * 32);
+          my[lane] = make_float4((float)kc4.x, (float)kc4.y, (float)kc4.z, (float)kc4.w);
           __syncwarp();
+          const float nqc = -(float)qc;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int4 c4 = my[i];                                // broadcast read
-            const uint32_t m0 = (uint32_t)((qc - c4.x) >> 31), m1 = (uint32_t)((qc - c4.y) >> 31);   // all ones: hidden
-            const uint32_t m2 = (uint32_t)((qc - c4.z) >> 31), m3 = (uint32_t)((qc - c4.w) >> 31);
-            s[4 * i + 0] = (s[4 * i + 0] & ~m0) | (0xff800000u & m0);                                // -inf
-            s[4 * i + 1] = (s[4 * i + 1] & ~m1) | (0xff800000u & m1);
-            s[4 * i + 2] = (s[4 * i + 2] & ~m2) | (0xff800000u & m2);
-            s[4 * i + 3] = (s[4 * i + 3] & ~m3) | (0xff800000u & m3);
+            const float4 c4 = my[i];                              // broadcast read
+            s[4 * i + 0] = __float_as_uint(fmaf(__saturatef(c4.x + nqc), kMasked, __uint_as_float(s[4 * i + 0])));
+            s[4 * i + 1] = __float_as_uint(fmaf(__saturatef(c4.y + nqc), kMasked, __uint_as_float(s[4 * i + 1])));
+            s[4 * i + 2] = __float_as_uint(fmaf(__saturatef(c4.z + nqc), kMasked, __uint_as_float(s[4 * i + 2])));
+            s[4 * i + 3] = __float_as_uint(fmaf(__saturatef(c4.w + nqc), kMasked, __uint_as_float(s[4 * i + 3])));
           }
           __syncwarp();                                           // scratch is rewritten for the next tile
         }
@@ -448,7 +455,8 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           mx2 = fmaxf(mx2, __uint_as_float(s[4 * i + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(s[4 * i + 3]));
         }
-        const float mx = blind ? -INFINITY : fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (blind || mx < 0.1f * kMasked) mx = -INFINITY;         // the row sees no key of this tile
         const bool grew = mx > m_run + thresh;                   // also true for the first finite maximum
         const float m_new = grew ? mx : m_run;
         const float sub = (m_new == -INFINITY) ? 0.f : __fmul_rn(m_new, scale_log2);
