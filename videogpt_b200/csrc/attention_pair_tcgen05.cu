@@ -25,7 +25,7 @@
 //
 // Warp roles (384 threads = 3 warpgroups): warps 0..3 = softmax / epilogue of tile A, warps 4..7 =
 // of tile B (TMEM lane quadrant = warp_idx % 4), warp 8 = TMA producer, warp 9 = TMEM allocator +
-// MMA issuer of tile A, warp 10 = tile-table builder, then MMA issuer of tile B, warp 11 idle.  Registers are re-balanced per
+// MMA issuer, warp 10 = tile-table builder, warp 11 idle.  Registers are re-balanced per
 // warpgroup with setmaxnreg (softmax 224, the rest 56): a softmax thread holds a whole 128-key
 // row of S in registers.
 #include "common.cuh"
@@ -54,7 +54,7 @@ struct PairCfg {
   static constexpr int kStages = (D == 128) ? 2 : (D == 96 ? 3 : 4);
   static constexpr int kCodeScratch = 8 * 128 * 4;            // one tile of key codes per softmax warp
   static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + kCodeScratch + 1024;   // tiles + barriers + tile table + code scratch + align
-  static constexpr int kSmemTrace = kSmem + 11 * 192 * 8;      // + the diagnostic instantiation's stamp rings
+  static constexpr int kSmemTrace = kSmem + 10 * 192 * 8;      // + the diagnostic instantiation's stamp rings
   static constexpr int kTmemO = 256;                          // O_A at 256, O_B at 256 + D
   // 64 spare TMEM columns (head_dim <= 96): P gets its own buffer, shared by the two tiles, and
   // S_x(j+1) is issued as soon as the softmax warps have read S_x(j) -- it runs under softmax(j).
@@ -97,7 +97,7 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) 
 // every fourth / every second exponential as a polynomial on the FMA pipe -- were validated and timed in round 2:
 // bit-exact / within 2^-7, and 0.3 - 2.8 us SLOWER than the default at cfg2 (profiles/r02b_attn_variants.txt): the MUFU
 // unit is 39 % busy, not the limit.  They were deleted.)
-constexpr int kTraceRoles = 11, kTracePerRole = 192;     // warps 0..7 (softmax A / B, every quadrant), 8 (TMA), 9 / 10 (MMA A / B)
+constexpr int kTraceRoles = 10, kTracePerRole = 192;     // warps 0..7 (softmax A / B, every quadrant), 8 (TMA), 9 (MMA)
 constexpr int kTraceMax = kTraceRoles * kTracePerRole;
 __device__ unsigned long long g_attn_trace[2 * kTraceMax];     // (clock, warp << 40 | tile << 32 | j << 8 | event)
 __device__ unsigned int g_attn_trace_n;
@@ -186,7 +186,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
     mbar_init(bar_q, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), has_b ? 2 : 1); }   // one release per MMA issuer
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), 1); }
     for (int x = 0; x < 2; ++x) {
       mbar_init(bar_s_full(x), 1); mbar_init(bar_p_full(x), 4); mbar_init(bar_o_full(x), 1); mbar_init(bar_s_free(x), 4);
     }
@@ -264,98 +264,114 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       tr(0, i, kEvKvIssued);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 9 || (warp == 10 && has_b)) {
-    // =================================== MMA issuers ===================================
-    // ONE ISSUING WARP PER QUERY TILE: warp 9 issues S_A / P V_A, warp 10 (done with the tile table) S_B / P V_B.
-    // A single issuer walking A and B in turn was the bottleneck of the whole CTA: per tile it pays ~290 cycles of
-    // loop code, two barrier polls of ~150-200 cycles each even when the phase has long completed (the mbarrier
-    // unit sits behind the shared-memory pipe the tensor core is saturating) and ~800 cycles blocked in the MMA
-    // queue -- 1440 cycles, twice per KV tile = the measured 2880-cycle period, against 2212 of tensor-pipe work and
-    // ~2100 of a softmax pass (profiles/r02h_attn_trace_all_warps.txt).  Two issuers run those serial chains side by
-    // side; the tensor pipe interleaves their instructions (order only matters within a tile).
+  } else if (warp == 9) {
+    // =================================== MMA issuer ===================================
     // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
-    const int x = warp - 9;
+    // (One issuing warp per query tile -- warp 10 for tile B -- was tried once the trace showed this warp's serial chain
+    // of loop code, ~150-cycle barrier polls and MMA-queue blocking at 1440 cycles per tile: bit-identical, and no faster
+    // (cfg2 66.6 -> 68.7 us, cfg5 613 -> 600 us, profiles/r02i_attn_bench_two_issuers.txt): with the issuers side by side
+    // the period stayed at 2900 cycles because the softmax warps' own chain per tile -- S read 175, exponentials
+    // 1600-1900 with the other tile's warp on the same MUFU unit, shared P buffer 230-430, P write 160, next barrier 400 --
+    // is that long.  Deleted.)
     constexpr uint32_t idesc_s = make_idesc_bf16(128, kPairBN);        // S = Q K^T (both K-major)
     constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O = P V   (V MN-major)
     // Descriptors: everything but the 14-bit start address is constant, and the start addresses of one issue differ by
-    // compile-time offsets -- one add per descriptor on the low word.
+    // compile-time offsets -- one add per descriptor on the low word.  (Rebuilding every descriptor from its byte
+    // address cost ~70 uniform-datapath instructions in front of each group of MMAs, four times per KV tile, on a warp
+    // that shares its scheduler with two softmax warps: the trace showed 300 - 700 idle cycles of the MMA warp between
+    // hand-overs it was not waiting for, profiles/r02d_attn_trace.txt.)
     constexpr uint64_t kDescQK = make_smem_desc(0, 16, 8 * C::kRowBytes, C::kLayout);                // K-major Q / K
     constexpr uint64_t kDescV = make_smem_desc(0, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);     // MN-major V
     constexpr uint32_t kStageStep = (2 * C::kTileBytes) >> 4;
     auto desc = [](uint64_t fixed, uint32_t lo) { return (fixed & 0xffffffff00000000ull) | (uint64_t)lo; };
-    const uint32_t q_lo = ((uint32_t)kDescQK | ((s_q >> 4) & 0x3fffu)) + (uint32_t)x * (C::kTileBytes >> 4);
+    const uint32_t q_lo0 = (uint32_t)kDescQK | ((s_q >> 4) & 0x3fffu);
+    const uint32_t q_lo1 = q_lo0 + (C::kTileBytes >> 4);
     const uint32_t k_lo0 = (uint32_t)kDescQK | ((s_kv >> 4) & 0x3fffu);
     const uint32_t v_lo0 = (uint32_t)kDescV | (((s_kv + C::kTileBytes) >> 4) & 0x3fffu);
-    const uint32_t t_s = tmem + x * 128, t_o = tmem + C::kTmemO + x * D, t_p = tmem + (C::kEarlyS ? C::kTmemP : x * 128);
-    auto issue_s = [&](int stage) {
+    auto issue_s = [&](int x, int stage) {
       if (elect_one_sync()) {
-        const uint32_t kl = k_lo0 + (uint32_t)stage * kStageStep;
+        const uint32_t ql = x ? q_lo1 : q_lo0, kl = k_lo0 + (uint32_t)stage * kStageStep;
+        const uint32_t td = tmem + x * 128;
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
 #pragma unroll
           for (int ks = 0; ks < C::kCW / 16; ++ks) {
             const uint32_t off = (uint32_t)(c * C::kChunkBytes + ks * 32) >> 4;
-            umma_f16_ss(t_s, desc(kDescQK, q_lo + off), desc(kDescQK, kl + off), idesc_s, (c | ks) ? 1u : 0u);
+            umma_f16_ss(td, desc(kDescQK, ql + off), desc(kDescQK, kl + off), idesc_s, (c | ks) ? 1u : 0u);
           }
         }
         if (!(dbg & 32)) umma_commit(bar_s_full(x));          // (dbg & 32: timing probe, fewer commits)
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int stage, int j) {
+    auto issue_pv = [&](int x, int stage, int j, bool release_kv) {
       if (elect_one_sync()) {
         const uint32_t vl = v_lo0 + (uint32_t)stage * kStageStep;
+        const uint32_t td = tmem + C::kTmemO + x * D, tp = tmem + (C::kEarlyS ? C::kTmemP : x * 128);
 #pragma unroll
         for (int ks = 0; ks < kPairBN / 16; ++ks)
-          umma_f16_ts(t_o, t_p + ks * 8, desc(kDescV, vl + (uint32_t)((ks * 16 * C::kRowBytes) >> 4)), idesc_o,
+          umma_f16_ts(td, tp + ks * 8, desc(kDescV, vl + (uint32_t)((ks * 16 * C::kRowBytes) >> 4)), idesc_o,
                       (j > 0 || ks > 0) ? 1u : 0u);
         if (!(dbg & 32) || j == n_vis - 1) umma_commit(bar_o_full(x));
-        umma_commit(bar_kv_empty(stage));      // this tile is done with K(j), V(j) once everything issued so far has completed
+        if (release_kv) umma_commit(bar_kv_empty(stage));     // K(j), V(j) free once everything issued so far is done
       }
       __syncwarp();
     };
     mbar_wait(bar_q, 0);
     int stage_s = 0; uint32_t phase_s = 0;
     int stage_o = 0;
-    if (n_vis > 0) {                            // prologue: S_x(0)
+    if (n_vis > 0) {                            // prologue: S_A(0), S_B(0)
       mbar_wait(bar_kv_full(stage_s), phase_s);
       tc_fence_after();
-      issue_s(stage_s);
+      issue_s(0, stage_s);
+      if (has_b) issue_s(1, stage_s);
       if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
     }
     if constexpr (C::kEarlyS) {
-      // S_x(j+1) as soon as S_x(j) sits in the softmax warps' registers (s_free), P V_x(j) when P_x(j) is in the
-      // shared P buffer (p_full).
+      // S_x(j+1) as soon as S_x(j) sits in the softmax warps' registers (s_free), P V_x(j) when
+      // P_x(j) is in the shared P buffer (p_full); fixed order A, B -- the two tiles fall into a
+      // half-period stagger.  (An event loop polling all four barriers was measured slower:
+      // it competes with the softmax warps for issue slots.)
       for (int j = 0; j < n_vis; ++j) {
-        if (j + 1 < n_vis) {
-          tr(x, j + 1, kEvMmaTop);
-          if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
-          mbar_wait(bar_kv_full(stage_s), phase_s);
-          tr(x, j + 1, kEvSFree);
+        const bool has_next = j + 1 < n_vis;
+        for (int x = 0; x < (has_b ? 2 : 1); ++x) {
+          if (has_next) {
+            tr(x, j + 1, kEvMmaTop);
+            if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
+            if (x == 0) mbar_wait(bar_kv_full(stage_s), phase_s);
+            tr(x, j + 1, kEvSFree);
+            tc_fence_after();
+            tr(x, j + 1, kEvMmaFenced);
+            issue_s(x, stage_s);
+            tr(x, j + 1, kEvSIssued);
+          }
+          if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
+          tr(x, j, kEvPFull);
           tc_fence_after();
-          tr(x, j + 1, kEvMmaFenced);
-          issue_s(stage_s);
-          tr(x, j + 1, kEvSIssued);
-          if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+          issue_pv(x, stage_o, j, x == (has_b ? 1 : 0));
+          tr(x, j, kEvPVIssued);
         }
-        if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
-        tr(x, j, kEvPFull);
-        tc_fence_after();
-        issue_pv(stage_o, j);
-        tr(x, j, kEvPVIssued);
+        if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
         if (++stage_o == kStages) stage_o = 0;
       }
     } else {
       for (int j = 0; j < n_vis; ++j) {
-        mbar_wait(bar_p_full(x), j & 1);          // P_x(j) in TMEM (and O_x rescaled if it had to be)
+        const bool has_next = j + 1 < n_vis;
+        mbar_wait(bar_p_full(0), j & 1);          // P_A(j) in TMEM (and O_A rescaled if it had to be)
         tc_fence_after();
-        issue_pv(stage_o, j);
-        if (j + 1 < n_vis) {
+        issue_pv(0, stage_o, j, !has_b);
+        if (has_next) {
           mbar_wait(bar_kv_full(stage_s), phase_s);
           tc_fence_after();
-          issue_s(stage_s);     // S_x(j+1) overwrites P_x(j): behind P V_x(j) in pipe order (same issuer)
-          if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+          issue_s(0, stage_s);    // S_A(j+1) overwrites P_A(j): behind P V_A(j) in pipe order
         }
+        if (has_b) {
+          mbar_wait(bar_p_full(1), j & 1);
+          tc_fence_after();
+          issue_pv(1, stage_o, j, true);
+          if (has_next) issue_s(1, stage_s);
+        }
+        if (has_next && ++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
         if (++stage_o == kStages) stage_o = 0;
       }
     }
