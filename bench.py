@@ -545,11 +545,12 @@ def _run_child(cmd, env, timeout_s):
     return line, None
 
 
-def strong_scaling_child(world, config, timeout_s):
-    """One video of `config` sharded over all `world` GPUs (sequence parallel: rows split, K/V pushed to the peers over
-    NVLink) in a CHILD torchrun with a hard time-out, so that a stall there can never cost the parent's bench line."""
+def strong_scaling_child(world, config, timeout_s, parallelism="sp"):
+    """One video of `config` over all `world` GPUs -- sequence parallel (rows split, K/V pushed to the peers over NVLink)
+    or, with parallelism="cfg" on two GPUs, one CFG branch per rank -- in a CHILD torchrun with a hard time-out, so that
+    a stall there can never cost the parent's bench line."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.abspath(__file__), "--gpus", str(world), "--parallelism", "sp",
+           "--master-port", str(_free_port()), os.path.abspath(__file__), "--gpus", str(world), "--parallelism", parallelism,
            "--config", config, "--steps", "2", "--warmup", "3", "--no-baselines", "--strong", "none"]
     drop = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_NAME",
             "ROLE_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS")
@@ -666,6 +667,8 @@ def main():
             line["strong_scaling"] = {"n_gpus": world, "mode": f"sp{world}: one video over all GPUs, child torchrun, "
                                       f"hard time-out {args.strong_timeout} s",
                                       **{c: strong_scaling_child(world, c, args.strong_timeout) for c in cfgs}}
+            if world == 2:       # SURVEY 8(e) axis 1: the two CFG branches of ONE cfg2 video on a rank pair
+                line["strong_scaling"]["cfg2_cfg_branch_pair"] = strong_scaling_child(2, "cfg2", args.strong_timeout, "cfg")
     print(json.dumps(line), flush=True)
 
 
