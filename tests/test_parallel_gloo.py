@@ -137,9 +137,19 @@ def _peer_alloc(rank, world):
         mismatch = False
     except RuntimeError:
         mismatch = True
+    # free(): one buffer, collectively -- the peers' mappings go first, then this rank's memory; close() then has
+    # nothing left of it
+    big = grp.alloc(4096)
+    n_log = len(grp.log)
+    mapped, mine_big = [p for r, p in enumerate(big.ptrs) if r != rank], big.ptrs[rank]
+    grp.free(big)
+    freeing = grp.log[n_log:]
+    ok &= freeing == [("unmap", p) for p in mapped] + [("free", mine_big)] and big.ptrs == [] and big.local is None
+    ok &= mine_big not in grp._owned and not any(p in grp._imported for p in mapped)
     n_log = len(grp.log)
     grp.close()
     closing = [e[0] for e in grp.log[n_log:]]
+    ok &= ("free", mine_big) not in grp.log[n_log:]
     return ok, mismatch, closing == sorted(closing, key=lambda k: k != "unmap"), grp.world, grp.rank
 
 

@@ -468,8 +468,14 @@ class NextClipEngine:
             if self._kv_shared is None or self._kv_shared.local.numel() < kv_bytes:
                 if any(sp.n_cached for sp in plan.specs):
                     raise ValueError("the plan counts on cached K/V rows but the pool is being (re)allocated")
+                if self._kv_shared is not None:          # outgrown: release it on every rank before growing
+                    self.kv = None
+                    self.peers.free(self._kv_shared)
                 self._kv_shared = self.peers.alloc(kv_bytes)
             if self._pred_shared is None or self._pred_shared.local.numel() < pred_bytes:
+                if self._pred_shared is not None:
+                    self.pred = None
+                    self.peers.free(self._pred_shared)
                 self._pred_shared = self.peers.alloc(pred_bytes)
             self.kv = self._kv_shared.local[:kv_bytes].view(bf).view(kv_shape)
             self.pred = self._pred_shared.local[:pred_bytes].view(bf).view(self.z.shape)

@@ -129,6 +129,25 @@ class PeerGroup:
     def _sync(self):
         torch.cuda.synchronize(self.device)
 
+    def free(self, buf: SharedBuffer):
+        """*collective*: release ONE buffer of ``alloc`` -- every rank unmaps its peers' copies, then (after a
+        rendezvous: nobody frees while a peer still maps it) frees its own.  The engine calls it before it
+        re-allocates a pool that a later plan has outgrown; without it every growth step of a rollout leaked a
+        multi-GB pool on every rank until ``close``."""
+        import torch.distributed as dist
+        self._sync()
+        dist.barrier(group=self.group)
+        for r, p in enumerate(buf.ptrs):
+            if r != self.rank and p in self._imported:
+                self._unmap(p)
+                self._imported.remove(p)
+        dist.barrier(group=self.group)
+        mine = buf.ptrs[self.rank]
+        if mine in self._owned:
+            self._free(mine)
+            self._owned.remove(mine)
+        buf.local, buf.ptrs = None, []
+
     def close(self):
         """*collective*: unmap the peers' buffers, then free this rank's."""
         import torch.distributed as dist
@@ -202,6 +221,9 @@ class LocalPeerGroup:
         if bufs[0].numel() != nbytes:
             raise RuntimeError("LocalPeerGroup.alloc: members disagree on the allocation size")
         return SharedBuffer(bufs[self.rank], [b.data_ptr() for b in bufs], self.rank)
+
+    def free(self, buf: SharedBuffer):
+        buf.local, buf.ptrs = None, []        # torch owns the virtual ranks' buffers
 
     def barrier(self):
         pass
