@@ -34,6 +34,7 @@ def main():
     pipe.next_clip_latents(lat[:n_ctx], n_gen, num_inference_steps=2, img_guidance_scale=1.5,
                            prediction_type="x1", initial_noise=lat[n_ctx:])          # warm-up + plan
     e = model.engine()
+    e.uniform_t = True           # as the fused sampler loop sets it: one timestep for every latent -> the small MLPs run on one row
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     if not args.no_prefill:
