@@ -160,22 +160,16 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 
   // Grid (head, query pair, sequence), head fastest.  CTAs are dispatched in linear block order to
   // whichever SM frees up first, and a CTA's work is (query tiles) x (KV tiles it can see): about 2.2 CTAs of very
-  // different sizes per SM, so the order decides the makespan.  Heads innermost (all CTAs of one kind start
-  // together); then the FULL query pairs of every sequence, longest sequence first; the LAST pair of every sequence
-  // -- the half-empty one: 8 rows at cfg2 -- goes to the end, where it fills the gaps.  List scheduling of the
-  // measured CTA durations at cfg2 (55 / 32 thousand cycles for a full pair of the conditional / unconditional
-  // sequence, 45 / 27 for their tails): makespan 114 with the tails in sequence order, 109 with the tails last, 91
-  // evenly spread.
-  const int head = blockIdx.x;
-  int seq_id, pair;
-  {
-    const int P = gridDim.y, S = gridDim.z, L = blockIdx.z * P + blockIdx.y, n_full = S * (P - 1);
-    if (P == 1) { seq_id = L; pair = 0; }
-    else if (L < n_full) { seq_id = L / (P - 1); pair = L % (P - 1); }
-    else { seq_id = L - n_full; pair = P - 1; }
-  }
+  // different sizes per SM at cfg2, so the order decides the makespan.  With the heads innermost all full pairs of
+  // the longest (first: conditional) sequence start before its half-empty last pair and before the short
+  // unconditional sequence -- longest first.  (With the pair index innermost the first wave mixed 4 full pairs :
+  // 1 tail per head and left 12 full-size CTAs for a second round.  Sending the half-empty last pair of every
+  // sequence to the very end instead -- list scheduling of the measured CTA durations at cfg2 predicts makespan 109
+  // against 114 thousand cycles -- measured no gain at cfg2 (66.9 vs 66.6 us) and a loss at cfg3, where the tail of
+  // the long sequence walks 73 KV tiles and must not start last: 208 vs 183 us; profiles/r02m_attn_bench_tails_last.txt.)
+  const int seq_id = blockIdx.z, head = blockIdx.x;
   const AttnSeqP sq = seqs[seq_id];
-  const int q0 = pair * 2 * kPairBM;
+  const int q0 = blockIdx.y * 2 * kPairBM;
   if (q0 >= sq.n_q) return;
   const int rows_cta = min(2 * kPairBM, sq.n_q - q0);          // valid rows of A and B together
   const bool has_b = rows_cta > kPairBM;
