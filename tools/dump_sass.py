@@ -8,15 +8,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "videogpt_b200", "build")
 OUT = os.path.join(ROOT, "profiles", "sass")
 WANT = [  # (object, substring of the demangled name, short file name)
-    ("gemm2_tcgen05.o", "gemm_bf16_tcgen05_pair_kernel<256, 0>", "gemm_pair_bn256_store"),
-    ("gemm2_tcgen05.o", "gemm_bf16_tcgen05_pair_kernel<256, 2>", "gemm_pair_bn256_swiglu"),
-    ("gemm2_tcgen05.o", "gemm_bf16_tcgen05_pair_kernel<192, 1>", "gemm_pair_bn192_residual"),
-    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<96, 0>", "attn_pair_d96"),
-    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<128, 0>", "attn_pair_d128"),
+    ("gemm_pair_tcgen05.o", "gemm_bf16_pair_kernel<256, 0>", "gemm_pair_bn256_store"),
+    ("gemm_pair_tcgen05.o", "gemm_bf16_pair_kernel<256, 2>", "gemm_pair_bn256_swiglu"),
+    ("gemm_pair_tcgen05.o", "gemm_bf16_pair_kernel<192, 1>", "gemm_pair_bn192_residual"),
+    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<96, false>", "attn_pair_d96"),
+    ("attention_pair_tcgen05.o", "attn_pair_tcgen05_kernel<128, false>", "attn_pair_d128"),
     ("elementwise.o", "rmsnorm_kernel", "rmsnorm"),
     ("elementwise.o", "rope_kv_append_kernel", "rope_kv_append"),
     ("elementwise.o", "embed_assemble_kernel", "embed_assemble"),
-    ("elementwise.o", "linear_small_kernel", "linear_small"),
+    ("elementwise.o", "linear_small_kernel<1>", "linear_small"),
     ("elementwise.o", "final_layer_kernel", "final_layer"),
     ("elementwise.o", "cfg_euler_kernel", "cfg_euler"),
     ("elementwise.o", "timestep_sinusoid_kernel", "timestep_sinusoid"),
