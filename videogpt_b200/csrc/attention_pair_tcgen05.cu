@@ -334,34 +334,26 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       // S_x(j+1) as soon as S_x(j) sits in the softmax warps' registers (s_free), P V_x(j) when
       // P_x(j) is in the shared P buffer (p_full); fixed order A, B -- the two tiles fall into a
       // half-period stagger.  (An event loop polling all four barriers was measured slower:
-      // it competes with the softmax warps for issue slots.)
-      // A barrier poll costs 150 - 200 cycles here even when the phase completed long ago (the mbarrier unit sits
-      // behind the shared-memory pipe the tensor core is saturating), and this warp polls twice per tile: each poll is
-      // therefore ISSUED before the group of MMAs in front of it (non-blocking test; its answer arrives while that
-      // group is being queued) and only repeated as a blocking wait if the early answer was "not yet".
-      bool pre_sfree = false;                   // early answer for the next s_free wait
+      // it competes with the softmax warps for issue slots.  Issuing every barrier poll early -- a non-blocking test
+      // in front of the MMA group / P hand-over that precedes the wait, in this warp and in the softmax warps -- was
+      // measured too: 67.8 / 187.9 / 622.4 us at cfg2 / cfg3 / cfg5 against 66.6 / 183.3 / 613.4,
+      // profiles/r02n_attn_bench_early_polls.txt.  Deleted.)
       for (int j = 0; j < n_vis; ++j) {
         const bool has_next = j + 1 < n_vis;
         for (int x = 0; x < (has_b ? 2 : 1); ++x) {
-          bool pre_p = false;
           if (has_next) {
             tr(x, j + 1, kEvMmaTop);
-            if (!pre_sfree && !(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
+            if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
             if (x == 0) mbar_wait(bar_kv_full(stage_s), phase_s);
             tr(x, j + 1, kEvSFree);
             tc_fence_after();
             tr(x, j + 1, kEvMmaFenced);
-            pre_p = __all_sync(0xffffffffu, mbar_test(bar_p_full(x), j & 1));
             issue_s(x, stage_s);
             tr(x, j + 1, kEvSIssued);
           }
-          if (!pre_p && !(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
+          if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
           tr(x, j, kEvPFull);
           tc_fence_after();
-          {                                     // the next group's first wait: s_free of (tile xn, KV tile jn)
-            const int xn = has_b ? (x ^ 1) : 0, jn = (has_b && x == 0) ? j : j + 1;
-            pre_sfree = (jn + 1 < n_vis) && __all_sync(0xffffffffu, mbar_test(bar_s_free(xn), jn & 1));
-          }
           issue_pv(x, stage_o, j, x == (has_b ? 1 : 0));
           tr(x, j, kEvPVIssued);
         }
@@ -408,7 +400,6 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const int32_t* kc = k_code + (size_t)seq_id * max_pages * kPairBN;
       const float thresh = 8.0f / scale_log2;                   // lazy rescale: 2^8 head-room
       float m_run = -INFINITY, l_run = 0.f;
-      bool s_ready = false;                                       // early answer of the poll for S_x(j), see below
       for (int j = 0; j < n_vis; ++j) {
         if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
         const int tmax = t_tmax[j], ktu = t_kt[j];                // (shared memory, before the wait)
@@ -428,7 +419,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const bool blind = some && !elementwise && hidden;                        // per row
         int4 kc4 = make_int4(0, 0, 0, 0);
         if (elementwise) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN) + lane);
-        if (!s_ready) mbar_wait(bar_s_full(x), j & 1);
+        mbar_wait(bar_s_full(x), j & 1);
         tr(x, j, kEvSFull);
         tc_fence_after();
         if (dbg & 1) {                                            // timing probe: tensor-pipe chain only
@@ -496,10 +487,6 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           s[i] = pack_bf16x2(p0, p1);                             // P overwrites the dead half of s[]
         }
         tr(x, j, kEvExpDone);
-        // S_x(j+1) was issued while this tile's exponentials ran: ask for it now, the answer arrives under the
-        // P hand-over below (a poll that has to travel behind the tensor core's shared-memory traffic costs a few
-        // hundred cycles at the top of the loop even when the phase completed long ago)
-        s_ready = C::kEarlyS && j + 1 < n_vis && __all_sync(0xffffffffu, mbar_test(bar_s_full(x), (j + 1) & 1));
         if constexpr (C::kEarlyS) {
           // the P buffer is shared: its previous reader is P V of the other tile (B: tile j of A;
           // A: tile j-1 of B), or of this tile when it is alone
