@@ -39,7 +39,9 @@ namespace vgpt {
 
 constexpr int kPairBM = 128;         // queries per tile (two tiles per CTA)
 constexpr int kPairBN = 128;         // keys per tile = one KV page
-constexpr int kPairThreads = 384;   // 3 warpgroups: softmax A, softmax B, {TMA, MMA, table, idle}
+// KH softmax warps per TMEM lane quadrant and tile (each takes 128 / KH key columns of its 32 rows): 8 * KH softmax
+// warps + {TMA, MMA, table, idle}
+constexpr int pair_threads(int kh) { return (8 * kh + 4) * 32; }
 
 struct AttnSeqP { int32_t q_row0, n_q, kv_len, reserved; };
 
@@ -52,8 +54,9 @@ struct PairCfg {
   static constexpr int kChunkBytes = 128 * kRowBytes;
   static constexpr int kTileBytes = kChunks * kChunkBytes;    // Q, K or V tile = 128 * D * 2
   static constexpr int kStages = (D == 128) ? 2 : (D == 96 ? 3 : 4);
-  static constexpr int kCodeScratch = 8 * 128 * 4;            // one tile of key codes per softmax warp
-  static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + kCodeScratch + 1024;   // tiles + barriers + tile table + code scratch + align
+  static constexpr int kCodeScratch = 16 * 128 * 4;           // one tile of key codes per softmax warp (up to 16 warps)
+  static constexpr int kXchg = (2 * 2 * 2 + 2 * 2) * 128 * 4;  // row maxima [tile parity][tile][half][row] + row sums [tile][half][row] (KH = 2)
+  static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + kCodeScratch + kXchg + 1024;   // tiles + barriers + tile table + code scratch + exchange + align
   static constexpr int kSmemTrace = kSmem + 10 * 192 * 8;      // + the diagnostic instantiation's stamp rings
   static constexpr int kTmemO = 256;                          // O_A at 256, O_B at 256 + D
   // 64 spare TMEM columns (head_dim <= 96): P gets its own buffer, shared by the two tiles, and
@@ -126,8 +129,8 @@ constexpr float kMasked = -1e30f;        // score of a hidden (query, key) pair 
 constexpr int kTileUniform = 1 << 30;   // flag in the tile table's logical index: all 128 keys of the tile share one code
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
-template <int D, bool TRACE>
-__global__ void __launch_bounds__(kPairThreads, 1)
+template <int D, bool TRACE, int KH>
+__global__ void __launch_bounds__(pair_threads(KH), 1)
 attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int out_ld,
                          const int32_t* __restrict__ page_table, int max_pages,
@@ -174,9 +177,13 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int rows_cta = min(2 * kPairBM, sq.n_q - q0);          // valid rows of A and B together
   const bool has_b = rows_cta > kPairBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWTma = 8 * KH, kWMma = kWTma + 1, kWTable = kWTma + 2;             // role warps behind the softmax warps
+  static_assert(!TRACE || KH == 1, "the diagnostic instantiation traces the 4-warps-per-tile layout");
   Tracer<TRACE> tr;
   int4* t_kcode = reinterpret_cast<int4*>(t_kt + kPairMaxTiles);                    // [softmax warp][32 lanes] key codes of a tile
-  [[maybe_unused]] uint2* trace_rings = reinterpret_cast<uint2*>(t_kcode + 8 * 32);
+  [[maybe_unused]] float* x_max = reinterpret_cast<float*>(t_kcode + 16 * 32);      // KH = 2: [tile parity][tile][half][row]
+  [[maybe_unused]] float* x_sum = x_max + 2 * 2 * 2 * 128;                          //          [tile][half][row]
+  [[maybe_unused]] uint2* trace_rings = reinterpret_cast<uint2*>(x_sum + 2 * 2 * 128);
   __shared__ int s_trace_n[kTraceRoles];
   if constexpr (TRACE) {
     if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && warp < kTraceRoles) tr.ring = trace_rings + warp * kTracePerRole;
@@ -186,23 +193,23 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   if (threadIdx.x == 0) { s_qmin = 0x7fffffff; s_qmax = (int)0x80000000; s_nvis = 0; }
   __syncthreads();
   if ((int)threadIdx.x < rows_cta && threadIdx.x < 2 * kPairBM) atomicMax(&s_qmax, q_code[sq.q_row0 + q0 + threadIdx.x]);
-  if (warp == 8 && lane == 0) {
+  if (warp == kWTma && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
     mbar_init(bar_q, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(bar_s_full(x), 1); mbar_init(bar_p_full(x), 4); mbar_init(bar_o_full(x), 1); mbar_init(bar_s_free(x), 4);
+      mbar_init(bar_s_full(x), 1); mbar_init(bar_p_full(x), 4 * KH); mbar_init(bar_o_full(x), 1); mbar_init(bar_s_free(x), 4 * KH);
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  if (warp == kWMma) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const int n_kt = (sq.kv_len + kPairBN - 1) / kPairBN;
   tr(0, 0, kEvStart);
-  if (warp == 8) {                        // Q does not need the table: start its load now
+  if (warp == kWTma) {                    // Q does not need the table: start its load now
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_q, (has_b ? 2 : 1) * C::kTileBytes);
       for (int x = 0; x < (has_b ? 2 : 1); ++x)
@@ -212,7 +219,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                       sq.q_row0 + q0 + x * kPairBM);
     }
     __syncwarp();
-  } else if (warp == 10) {                // ordered compaction of the visible tiles, 32 per step
+  } else if (warp == kWTable) {           // ordered compaction of the visible tiles, 32 per step
     const int q_max = s_qmax;
     const int32_t* mm = k_tile_minmax + (size_t)seq_id * max_k_tiles64 * 2;   // (min, max) per 64 keys
     const int32_t* pt = page_table + (size_t)seq_id * max_pages;
@@ -241,11 +248,12 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int n_vis = s_nvis;
   tr(0, n_vis, kEvTableDone);
 
-  if (warp >= 8) {
-    // 256 x 224 + 128 x 56 = 64512 = the 384 x 168 registers the CTA was launched with.  (A first version gave the
-    // variants 64 here: 65536 > 64512, and setmaxnreg.inc of the softmax warps waited forever.)
+  if (warp >= kWTma) {
+    // KH = 1: 256 x 224 + 128 x 56 = 64512 = the 384 x 168 registers the CTA was launched with.  (A first version gave
+    // the variants 64 here: 65536 > 64512, and setmaxnreg.inc of the softmax warps waited forever.)
+    // KH = 2: 640 threads are launched with 96 registers (61440); 512 x 104 + 128 x 56 = 60416.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 8) {
+  if (warp == kWTma) {
     // =================================== TMA producer ===================================
     // (whole warp runs the loop; one elected lane issues)
     int stage = 0; uint32_t phase = 0;
@@ -267,7 +275,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       tr(0, i, kEvKvIssued);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 9) {
+  } else if (warp == kWMma) {
     // =================================== MMA issuer ===================================
     // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
     // (One issuing warp per query tile -- warp 10 for tile B -- was tried once the trace showed this warp's serial chain
@@ -383,11 +391,21 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if constexpr (KH == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ============================ softmax / rescale / epilogue ============================
-    const int x = warp >> 2;                                    // 0 = tile A, 1 = tile B
+    // Warp (x, h, quad): tile x, key columns [h * NC, (h + 1) * NC) of the tile, query rows quad * 32 + lane.
+    // KH = 2: two warps share a row.  They exchange the row maximum of every tile through shared memory (a named
+    // barrier of their 64 threads), keep their own partial row sum (the rescale factor is the same for both) and add
+    // the two at the end in a fixed order.  Why: ONE warp's softmax pass is bound by its own issue occupancy -- a MUFU
+    // instruction holds the warp's issue slot for 8 cycles, the packed FMA / pack / max instructions for 2: 128 x 8 +
+    // ~235 x 2 = 1500 cycles for 128 columns, which is what the trace shows (1540), and the pass of the other tile's warp
+    // on the same scheduler is staggered by half a period, so nothing overlaps it.  Two warps with 64 columns each run
+    // side by side on the scheduler: one's MUFU cycles hide the other's FMA-pipe cycles.
+    constexpr int NC = kPairBN / KH;                              // key columns per warp
+    const int x = warp / (4 * KH);                                // 0 = tile A, 1 = tile B
     if (x == 0 || has_b) {
-      const int quad = warp & 3;
+      const int quad = warp & 3, h = (warp / 4) % KH;
       const int row = quad * 32 + lane;                         // row of the tile == TMEM lane
       const int rows_here = min(kPairBM, rows_cta - x * kPairBM);
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -399,6 +417,8 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const int qc = valid ? q_code[grow] : 0x7fffffff;         // padding rows: see everything, never stored
       const int32_t* kc = k_code + (size_t)seq_id * max_pages * kPairBN;
       const float thresh = 8.0f / scale_log2;                   // lazy rescale: 2^8 head-room
+      [[maybe_unused]] const int pair_bar = 1 + x * 4 + quad;     // named barrier of the two warps of a row block (KH = 2)
+      auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_vis; ++j) {
         if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
@@ -407,7 +427,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         // Rows that cannot see the whole tile (the two tag rows at a frame start; everybody on the ragged last tile):
         //   * tile with ONE key code (most: 256 patch tokens per frame): such a row sees none of it -- it runs the
         //     same instructions with multiplier 0 / offset -inf (P = 0 exactly) and leaves the row maximum alone;
-        //   * mixed tile: the 128 key codes are fetched BEFORE the wait for S (one int4 per lane: the latency hides
+        //   * mixed tile: the key codes are fetched BEFORE the wait for S (one int4 per lane: the latency hides
         //     under the MMAs), staged in shared memory and applied to S in registers with two FMA-pipe instructions
         //     per score.
         // (First version: S patched in place in tensor memory, 32 columns at a time, codes loaded inside the loop:
@@ -418,7 +438,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const bool elementwise = some && (ragged || !(ktu & kTileUniform));     // warp-uniform
         const bool blind = some && !elementwise && hidden;                        // per row
         int4 kc4 = make_int4(0, 0, 0, 0);
-        if (elementwise) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN) + lane);
+        if (elementwise && lane < NC / 4) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN + h * NC) + lane);
         mbar_wait(bar_s_full(x), j & 1);
         tr(x, j, kEvSFull);
         tc_fence_after();
@@ -428,10 +448,10 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           if (lane == 0) { if (C::kEarlyS) mbar_arrive(bar_s_free(x)); mbar_arrive(bar_p_full(x)); }
           continue;
         }
-        uint32_t s[128];
+        uint32_t s[NC];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tmem_ld_32x32b_x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        for (int c = 0; c < NC / 32; ++c)
+          tmem_ld_32x32b_x32(t_s + h * NC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
         tmem_ld_wait();
         if constexpr (C::kEarlyS) {                                // S_x is free: S_x(j+1) may be issued now
           tc_fence_before();
@@ -450,7 +470,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           __syncwarp();
           const float nqc = -(float)qc;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < NC / 4; ++i) {
             const float4 c4 = my[i];                              // broadcast read
             s[4 * i + 0] = __float_as_uint(fmaf(__saturatef(c4.x + nqc), kMasked, __uint_as_float(s[4 * i + 0])));
             s[4 * i + 1] = __float_as_uint(fmaf(__saturatef(c4.y + nqc), kMasked, __uint_as_float(s[4 * i + 1])));
@@ -461,14 +481,24 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < NC / 4; ++i) {
           mx0 = fmaxf(mx0, __uint_as_float(s[4 * i + 0]));
           mx1 = fmaxf(mx1, __uint_as_float(s[4 * i + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(s[4 * i + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(s[4 * i + 3]));
         }
         float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (blind || mx < 0.1f * kMasked) mx = -INFINITY;         // the row sees no key of this tile
+        if (blind || mx < 0.1f * kMasked) mx = -INFINITY;         // the row sees no key of these columns
+        if constexpr (KH == 2) {
+          // the row maximum of the whole tile: slot [tile parity][tile][half][row]; the parity keeps tile j + 1's
+          // writes away from a partner still reading tile j (it cannot be two tiles behind: it passed barrier j)
+          float* xm = x_max + (((j & 1) * 2 + x) * 2) * 128;
+          xm[h * 128 + row] = mx;
+          tc_fence_before();                                      // (head_dim 128: the partner's P goes where this warp read S)
+          pair_sync();
+          tc_fence_after();
+          mx = fmaxf(mx, xm[(h ^ 1) * 128 + row]);
+        }
         const bool grew = mx > m_run + thresh;                   // also true for the first finite maximum
         const float m_new = grew ? mx : m_run;
         const float sub = (m_new == -INFINITY) ? 0.f : __fmul_rn(m_new, scale_log2);
@@ -479,7 +509,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         float sum0 = 0.f, sum1 = 0.f;
         const float nsub = blind ? -INFINITY : -sub, mul = blind ? 0.f : scale_log2;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < NC / 2; ++i) {
           float p0, p1;
           ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), mul, nsub);
           if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
@@ -497,20 +527,23 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tc_fence_after();
           }
           tr(x, j, kEvPBufFree);
-          tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-          tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+#pragma unroll
+          for (int c = 0; c < NC / 64; ++c)
+            tmem_st_32x32b_x32(t_p + h * (NC / 2) + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
         } else {
-          tmem_st_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
-          tmem_st_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+#pragma unroll
+          for (int c = 0; c < NC / 64; ++c)
+            tmem_st_32x32b_x32(t_s + h * (NC / 2) + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
         }
-        l_run = l_run * alpha + (sum0 + sum1);
+        l_run = l_run * alpha + (sum0 + sum1);                    // (KH = 2: this warp's columns only)
         m_run = m_new;
         if (j > 0 && __any_sync(0xffffffffu, grew)) {
-          // rare after the first tiles: O_x(j-1) must be complete, then scale this row
+          // rare after the first tiles: O_x(j-1) must be complete, then scale this row (KH = 2: the two warps of a row
+          // take turns over the 32-column chunks; both see the same `grew`)
           mbar_wait(bar_o_full(x), (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int u = 0; u < D / 32; ++u) {
+          for (int u = h; u < D / 32; u += KH) {
             uint32_t o[32];
             tmem_ld_32x32b_x32(t_o + u * 32, o);
             tmem_ld_wait();
@@ -522,10 +555,16 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 per tile)
+        if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 * KH per tile)
         tr(x, j, kEvPWritten);
       }
       // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------
+      if constexpr (KH == 2) {                                    // row sum = columns of half 0 + columns of half 1, in that order
+        float* xs = x_sum + (x * 2) * 128;
+        xs[h * 128 + row] = l_run;
+        pair_sync();
+        l_run = xs[row] + xs[128 + row];
+      }
       if (n_vis > 0) {
         mbar_wait(bar_o_full(x), (n_vis - 1) & 1);
         tc_fence_after();
@@ -534,7 +573,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __nv_bfloat16* orow = out + (size_t)grow * out_ld + head * D;
 #pragma unroll
-      for (int u = 0; u < D / 32; ++u) {
+      for (int u = h; u < D / 32; u += KH) {
         uint32_t o[32];
         if (n_vis > 0) {
           tmem_ld_32x32b_x32(t_o + u * 32, o);
@@ -568,7 +607,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       int base = 0;
       for (int r = 0; r < kTraceRoles; ++r) {
         const int n = s_trace_n[r];
-        for (int i = threadIdx.x; i < n; i += kPairThreads) {
+        for (int i = threadIdx.x; i < n; i += pair_threads(KH)) {
           const uint2 e = trace_rings[r * kTracePerRole + i];
           g_attn_trace[2 * (base + i)] = e.x;
           g_attn_trace[2 * (base + i) + 1] = ((unsigned long long)r << 40) | ((unsigned long long)(e.y >> 28) << 32) |
@@ -579,7 +618,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       if (threadIdx.x == 0) g_attn_trace_n = (unsigned)base;
     }
   }
-  if (warp == 9) {
+  if (warp == kWMma) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -598,7 +637,13 @@ static bool attn_trace_on() {      // VGPT_ATTN_VARIANT=8: the diagnostic instan
   return e && atoi(e) == 8;
 }
 
-template <int D, bool TRACE>
+// VGPT_ATTN_HALVES=2: two softmax warps per row block (64 key columns each, 640 threads); default 1
+static int attn_halves() {
+  static const int v = [] { const char* e = getenv("VGPT_ATTN_HALVES"); return e && atoi(e) == 2 ? 2 : 1; }();
+  return v;
+}
+
+template <int D, bool TRACE, int KH>
 static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                             const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                             const void* seqs, int num_seqs, int q_pairs, const int32_t* q_code,
@@ -623,12 +668,12 @@ static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int 
     rc = encode_tensor_map(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(v_pool), dims, strides, box, estr, swz);
     if (rc) return rc;
   }
-  auto kern = attn_pair_tcgen05_kernel<D, TRACE>;
+  auto kern = attn_pair_tcgen05_kernel<D, TRACE, KH>;
   constexpr int smem = TRACE ? C::kSmemTrace : C::kSmem;
   // per launch: the attribute is per device, and a process may drive several devices (cheap, capture-safe)
   VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(H, q_pairs, num_seqs);
-  kern<<<grid, kPairThreads, smem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
+  kern<<<grid, pair_threads(KH), smem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
                                             (const AttnSeqP*)seqs, q_code, k_code, k_tile_minmax,
                                             max_k_tiles64, H, scale * 1.4426950408889634f, debug_attn_flags());
   VGPT_CHECK_LAUNCH();
@@ -672,15 +717,19 @@ int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int ou
   if (num_seqs <= 0 || max_q_rows <= 0) return 0;
   const int q_pairs = (max_q_rows + 2 * kPairBM - 1) / (2 * kPairBM);
   const bool trace = D == 96 && attn_trace_on();
-#define VGPT_ATTN_CASE(D_, T_)                                                                              \
-  if (D == D_ && trace == T_)                                                                                \
-    return launch_attn_pair<D_, T_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,  \
-                                    max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,      \
-                                    max_k_tiles, H, scale, s);
-  VGPT_ATTN_CASE(64, false)
-  VGPT_ATTN_CASE(96, false)
-  VGPT_ATTN_CASE(96, true)
-  VGPT_ATTN_CASE(128, false)
+#define VGPT_ATTN_CASE(D_, T_, KH_)                                                                          \
+  if (D == D_ && trace == T_ && halves == KH_)                                                               \
+    return launch_attn_pair<D_, T_, KH_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table, \
+                                         max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,   \
+                                         max_k_tiles, H, scale, s);
+  const int halves = trace ? 1 : attn_halves();
+  VGPT_ATTN_CASE(64, false, 1)
+  VGPT_ATTN_CASE(96, false, 1)
+  VGPT_ATTN_CASE(96, true, 1)
+  VGPT_ATTN_CASE(128, false, 1)
+  VGPT_ATTN_CASE(64, false, 2)
+  VGPT_ATTN_CASE(96, false, 2)
+  VGPT_ATTN_CASE(128, false, 2)
 #undef VGPT_ATTN_CASE
   return -1;
 }
