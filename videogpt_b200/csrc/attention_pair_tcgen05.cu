@@ -129,7 +129,7 @@ constexpr float kMasked = -1e30f;        // score of a hidden (query, key) pair 
 constexpr int kTileUniform = 1 << 30;   // flag in the tile table's logical index: all 128 keys of the tile share one code
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
-template <int D, bool TRACE, int KH>
+template <int D, bool TRACE, int KH, int NI>
 __global__ void __launch_bounds__(pair_threads(KH), 1)
 attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int out_ld,
@@ -196,7 +196,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   if (warp == kWTma && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
     mbar_init(bar_q, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), (NI == 2 && has_b) ? 2 : 1); }   // one release per MMA issuer
     for (int x = 0; x < 2; ++x) {
       mbar_init(bar_s_full(x), 1); mbar_init(bar_p_full(x), 4 * KH); mbar_init(bar_o_full(x), 1); mbar_init(bar_s_free(x), 4 * KH);
     }
@@ -275,7 +275,102 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       tr(0, i, kEvKvIssued);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == kWMma) {
+  } else if (NI == 2 && (warp == kWMma || (warp == kWTable && has_b))) {
+    // =================================== MMA issuers ===================================
+    // ONE ISSUING WARP PER QUERY TILE: warp 9 issues S_A / P V_A, warp 10 (done with the tile table) S_B / P V_B.
+    // A single issuer walking A and B in turn was the bottleneck of the whole CTA: per tile it pays ~290 cycles of
+    // loop code, two barrier polls of ~150-200 cycles each even when the phase has long completed (the mbarrier
+    // unit sits behind the shared-memory pipe the tensor core is saturating) and ~800 cycles blocked in the MMA
+    // queue -- 1440 cycles, twice per KV tile = the measured 2880-cycle period, against 2212 of tensor-pipe work and
+    // ~2100 of a softmax pass (profiles/r02h_attn_trace_all_warps.txt).  Two issuers run those serial chains side by
+    // side; the tensor pipe interleaves their instructions (order only matters within a tile).
+    // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
+    const int x = warp - kWMma;
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, kPairBN);        // S = Q K^T (both K-major)
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O = P V   (V MN-major)
+    // Descriptors: everything but the 14-bit start address is constant, and the start addresses of one issue differ by
+    // compile-time offsets -- one add per descriptor on the low word.
+    constexpr uint64_t kDescQK = make_smem_desc(0, 16, 8 * C::kRowBytes, C::kLayout);                // K-major Q / K
+    constexpr uint64_t kDescV = make_smem_desc(0, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);     // MN-major V
+    constexpr uint32_t kStageStep = (2 * C::kTileBytes) >> 4;
+    auto desc = [](uint64_t fixed, uint32_t lo) { return (fixed & 0xffffffff00000000ull) | (uint64_t)lo; };
+    const uint32_t q_lo = ((uint32_t)kDescQK | ((s_q >> 4) & 0x3fffu)) + (uint32_t)x * (C::kTileBytes >> 4);
+    const uint32_t k_lo0 = (uint32_t)kDescQK | ((s_kv >> 4) & 0x3fffu);
+    const uint32_t v_lo0 = (uint32_t)kDescV | (((s_kv + C::kTileBytes) >> 4) & 0x3fffu);
+    const uint32_t t_s = tmem + x * 128, t_o = tmem + C::kTmemO + x * D, t_p = tmem + (C::kEarlyS ? C::kTmemP : x * 128);
+    auto issue_s = [&](int stage) {
+      if (elect_one_sync()) {
+        const uint32_t kl = k_lo0 + (uint32_t)stage * kStageStep;
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+#pragma unroll
+          for (int ks = 0; ks < C::kCW / 16; ++ks) {
+            const uint32_t off = (uint32_t)(c * C::kChunkBytes + ks * 32) >> 4;
+            umma_f16_ss(t_s, desc(kDescQK, q_lo + off), desc(kDescQK, kl + off), idesc_s, (c | ks) ? 1u : 0u);
+          }
+        }
+        if (!(dbg & 32)) umma_commit(bar_s_full(x));          // (dbg & 32: timing probe, fewer commits)
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int stage, int j) {
+      if (elect_one_sync()) {
+        const uint32_t vl = v_lo0 + (uint32_t)stage * kStageStep;
+#pragma unroll
+        for (int ks = 0; ks < kPairBN / 16; ++ks)
+          umma_f16_ts(t_o, t_p + ks * 8, desc(kDescV, vl + (uint32_t)((ks * 16 * C::kRowBytes) >> 4)), idesc_o,
+                      (j > 0 || ks > 0) ? 1u : 0u);
+        if (!(dbg & 32) || j == n_vis - 1) umma_commit(bar_o_full(x));
+        umma_commit(bar_kv_empty(stage));      // this tile is done with K(j), V(j) once everything issued so far has completed
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar_q, 0);
+    int stage_s = 0; uint32_t phase_s = 0;
+    int stage_o = 0;
+    if (n_vis > 0) {                            // prologue: S_x(0)
+      mbar_wait(bar_kv_full(stage_s), phase_s);
+      tc_fence_after();
+      issue_s(stage_s);
+      if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+    }
+    if constexpr (C::kEarlyS) {
+      // S_x(j+1) as soon as S_x(j) sits in the softmax warps' registers (s_free), P V_x(j) when P_x(j) is in the
+      // shared P buffer (p_full).
+      for (int j = 0; j < n_vis; ++j) {
+        if (j + 1 < n_vis) {
+          tr(x, j + 1, kEvMmaTop);
+          if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
+          mbar_wait(bar_kv_full(stage_s), phase_s);
+          tr(x, j + 1, kEvSFree);
+          tc_fence_after();
+          tr(x, j + 1, kEvMmaFenced);
+          issue_s(stage_s);
+          tr(x, j + 1, kEvSIssued);
+          if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+        }
+        if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
+        tr(x, j, kEvPFull);
+        tc_fence_after();
+        issue_pv(stage_o, j);
+        tr(x, j, kEvPVIssued);
+        if (++stage_o == kStages) stage_o = 0;
+      }
+    } else {
+      for (int j = 0; j < n_vis; ++j) {
+        mbar_wait(bar_p_full(x), j & 1);          // P_x(j) in TMEM (and O_x rescaled if it had to be)
+        tc_fence_after();
+        issue_pv(stage_o, j);
+        if (j + 1 < n_vis) {
+          mbar_wait(bar_kv_full(stage_s), phase_s);
+          tc_fence_after();
+          issue_s(stage_s);     // S_x(j+1) overwrites P_x(j): behind P V_x(j) in pipe order (same issuer)
+          if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
+        }
+        if (++stage_o == kStages) stage_o = 0;
+      }
+    }
+  } else if (NI == 1 && warp == kWMma) {
     // =================================== MMA issuer ===================================
     // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
     // (One issuing warp per query tile -- warp 10 for tile B -- was tried once the trace showed this warp's serial chain
@@ -643,7 +738,7 @@ static int attn_halves() {
   return v;
 }
 
-template <int D, bool TRACE, int KH>
+template <int D, bool TRACE, int KH, int NI>
 static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                             const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                             const void* seqs, int num_seqs, int q_pairs, const int32_t* q_code,
@@ -668,7 +763,7 @@ static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int 
     rc = encode_tensor_map(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(v_pool), dims, strides, box, estr, swz);
     if (rc) return rc;
   }
-  auto kern = attn_pair_tcgen05_kernel<D, TRACE, KH>;
+  auto kern = attn_pair_tcgen05_kernel<D, TRACE, KH, NI>;
   constexpr int smem = TRACE ? C::kSmemTrace : C::kSmem;
   // per launch: the attribute is per device, and a process may drive several devices (cheap, capture-safe)
   VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -719,7 +814,7 @@ int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int ou
   const bool trace = D == 96 && attn_trace_on();
 #define VGPT_ATTN_CASE(D_, T_, KH_)                                                                          \
   if (D == D_ && trace == T_ && halves == KH_)                                                               \
-    return launch_attn_pair<D_, T_, KH_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table, \
+    return launch_attn_pair<D_, T_, KH_, KH_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table, \
                                          max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,   \
                                          max_k_tiles, H, scale, s);
   const int halves = trace ? 1 : attn_halves();
