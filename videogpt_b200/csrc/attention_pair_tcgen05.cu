@@ -39,9 +39,7 @@ namespace vgpt {
 
 constexpr int kPairBM = 128;         // queries per tile (two tiles per CTA)
 constexpr int kPairBN = 128;         // keys per tile = one KV page
-// KH softmax warps per TMEM lane quadrant and tile (each takes 128 / KH key columns of its 32 rows): 8 * KH softmax
-// warps + {TMA, MMA, table, idle}
-constexpr int pair_threads(int kh) { return (8 * kh + 4) * 32; }
+constexpr int kPairThreads = 384;   // 3 warpgroups: softmax A, softmax B, {TMA, MMA, table, idle}
 
 struct AttnSeqP { int32_t q_row0, n_q, kv_len, reserved; };
 
@@ -54,9 +52,8 @@ struct PairCfg {
   static constexpr int kChunkBytes = 128 * kRowBytes;
   static constexpr int kTileBytes = kChunks * kChunkBytes;    // Q, K or V tile = 128 * D * 2
   static constexpr int kStages = (D == 128) ? 2 : (D == 96 ? 3 : 4);
-  static constexpr int kCodeScratch = 16 * 128 * 4;           // one tile of key codes per softmax warp (up to 16 warps)
-  static constexpr int kXchg = (2 * 2 * 2 + 2 * 2) * 128 * 4;  // row maxima [tile parity][tile][half][row] + row sums [tile][half][row] (KH = 2)
-  static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + kCodeScratch + kXchg + 1024;   // tiles + barriers + tile table + code scratch + exchange + align
+  static constexpr int kCodeScratch = 8 * 128 * 4;            // one tile of key codes per softmax warp
+  static constexpr int kSmem = kTileBytes * (2 + 2 * kStages) + 256 + 3 * 1024 * 4 + kCodeScratch + 1024;   // tiles + barriers + tile table + code scratch + align
   static constexpr int kSmemTrace = kSmem + 10 * 192 * 8;      // + the diagnostic instantiation's stamp rings
   static constexpr int kTmemO = 256;                          // O_A at 256, O_B at 256 + D
   // 64 spare TMEM columns (head_dim <= 96): P gets its own buffer, shared by the two tiles, and
@@ -129,8 +126,8 @@ constexpr float kMasked = -1e30f;        // score of a hidden (query, key) pair 
 constexpr int kTileUniform = 1 << 30;   // flag in the tile table's logical index: all 128 keys of the tile share one code
 constexpr int kPairMaxTiles = 1024;      // KV tiles per sequence the per-CTA tile table can hold (128 K tokens)
 
-template <int D, bool TRACE, int KH, int NI>
-__global__ void __launch_bounds__(pair_threads(KH), 1)
+template <int D, bool TRACE>
+__global__ void __launch_bounds__(kPairThreads, 1)
 attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                          const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int out_ld,
                          const int32_t* __restrict__ page_table, int max_pages,
@@ -177,13 +174,9 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int rows_cta = min(2 * kPairBM, sq.n_q - q0);          // valid rows of A and B together
   const bool has_b = rows_cta > kPairBM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWTma = 8 * KH, kWMma = kWTma + 1, kWTable = kWTma + 2;             // role warps behind the softmax warps
-  static_assert(!TRACE || KH == 1, "the diagnostic instantiation traces the 4-warps-per-tile layout");
   Tracer<TRACE> tr;
   int4* t_kcode = reinterpret_cast<int4*>(t_kt + kPairMaxTiles);                    // [softmax warp][32 lanes] key codes of a tile
-  [[maybe_unused]] float* x_max = reinterpret_cast<float*>(t_kcode + 16 * 32);      // KH = 2: [tile parity][tile][half][row]
-  [[maybe_unused]] float* x_sum = x_max + 2 * 2 * 2 * 128;                          //          [tile][half][row]
-  [[maybe_unused]] uint2* trace_rings = reinterpret_cast<uint2*>(x_sum + 2 * 2 * 128);
+  [[maybe_unused]] uint2* trace_rings = reinterpret_cast<uint2*>(t_kcode + 8 * 32);
   __shared__ int s_trace_n[kTraceRoles];
   if constexpr (TRACE) {
     if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0 && warp < kTraceRoles) tr.ring = trace_rings + warp * kTracePerRole;
@@ -193,23 +186,23 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   if (threadIdx.x == 0) { s_qmin = 0x7fffffff; s_qmax = (int)0x80000000; s_nvis = 0; }
   __syncthreads();
   if ((int)threadIdx.x < rows_cta && threadIdx.x < 2 * kPairBM) atomicMax(&s_qmax, q_code[sq.q_row0 + q0 + threadIdx.x]);
-  if (warp == kWTma && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
     mbar_init(bar_q, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), (NI == 2 && has_b) ? 2 : 1); }   // one release per MMA issuer
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_kv_full(s), 1); mbar_init(bar_kv_empty(s), 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(bar_s_full(x), 1); mbar_init(bar_p_full(x), 4 * KH); mbar_init(bar_o_full(x), 1); mbar_init(bar_s_free(x), 4 * KH);
+      mbar_init(bar_s_full(x), 1); mbar_init(bar_p_full(x), 4); mbar_init(bar_o_full(x), 1); mbar_init(bar_s_free(x), 4);
     }
     fence_barrier_init();
   }
-  if (warp == kWMma) tmem_alloc<512>(tmem_slot);
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const int n_kt = (sq.kv_len + kPairBN - 1) / kPairBN;
   tr(0, 0, kEvStart);
-  if (warp == kWTma) {                    // Q does not need the table: start its load now
+  if (warp == 8) {                        // Q does not need the table: start its load now
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_q, (has_b ? 2 : 1) * C::kTileBytes);
       for (int x = 0; x < (has_b ? 2 : 1); ++x)
@@ -219,7 +212,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
                       sq.q_row0 + q0 + x * kPairBM);
     }
     __syncwarp();
-  } else if (warp == kWTable) {           // ordered compaction of the visible tiles, 32 per step
+  } else if (warp == 10) {                // ordered compaction of the visible tiles, 32 per step
     const int q_max = s_qmax;
     const int32_t* mm = k_tile_minmax + (size_t)seq_id * max_k_tiles64 * 2;   // (min, max) per 64 keys
     const int32_t* pt = page_table + (size_t)seq_id * max_pages;
@@ -248,12 +241,11 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
   const int n_vis = s_nvis;
   tr(0, n_vis, kEvTableDone);
 
-  if (warp >= kWTma) {
-    // KH = 1: 256 x 224 + 128 x 56 = 64512 = the 384 x 168 registers the CTA was launched with.  (A first version gave
-    // the variants 64 here: 65536 > 64512, and setmaxnreg.inc of the softmax warps waited forever.)
-    // KH = 2: 640 threads are launched with 96 registers (61440); 512 x 104 + 128 x 56 = 60416.
+  if (warp >= 8) {
+    // 256 x 224 + 128 x 56 = 64512 = the 384 x 168 registers the CTA was launched with.  (A first version gave the
+    // variants 64 here: 65536 > 64512, and setmaxnreg.inc of the softmax warps waited forever.)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == kWTma) {
+  if (warp == 8) {
     // =================================== TMA producer ===================================
     // (whole warp runs the loop; one elected lane issues)
     int stage = 0; uint32_t phase = 0;
@@ -275,102 +267,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       tr(0, i, kEvKvIssued);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
-  } else if (NI == 2 && (warp == kWMma || (warp == kWTable && has_b))) {
-    // =================================== MMA issuers ===================================
-    // ONE ISSUING WARP PER QUERY TILE: warp 9 issues S_A / P V_A, warp 10 (done with the tile table) S_B / P V_B.
-    // A single issuer walking A and B in turn was the bottleneck of the whole CTA: per tile it pays ~290 cycles of
-    // loop code, two barrier polls of ~150-200 cycles each even when the phase has long completed (the mbarrier
-    // unit sits behind the shared-memory pipe the tensor core is saturating) and ~800 cycles blocked in the MMA
-    // queue -- 1440 cycles, twice per KV tile = the measured 2880-cycle period, against 2212 of tensor-pipe work and
-    // ~2100 of a softmax pass (profiles/r02h_attn_trace_all_warps.txt).  Two issuers run those serial chains side by
-    // side; the tensor pipe interleaves their instructions (order only matters within a tile).
-    // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
-    const int x = warp - kWMma;
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, kPairBN);        // S = Q K^T (both K-major)
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, D, 0, 1);        // O = P V   (V MN-major)
-    // Descriptors: everything but the 14-bit start address is constant, and the start addresses of one issue differ by
-    // compile-time offsets -- one add per descriptor on the low word.
-    constexpr uint64_t kDescQK = make_smem_desc(0, 16, 8 * C::kRowBytes, C::kLayout);                // K-major Q / K
-    constexpr uint64_t kDescV = make_smem_desc(0, C::kChunkBytes, 8 * C::kRowBytes, C::kLayout);     // MN-major V
-    constexpr uint32_t kStageStep = (2 * C::kTileBytes) >> 4;
-    auto desc = [](uint64_t fixed, uint32_t lo) { return (fixed & 0xffffffff00000000ull) | (uint64_t)lo; };
-    const uint32_t q_lo = ((uint32_t)kDescQK | ((s_q >> 4) & 0x3fffu)) + (uint32_t)x * (C::kTileBytes >> 4);
-    const uint32_t k_lo0 = (uint32_t)kDescQK | ((s_kv >> 4) & 0x3fffu);
-    const uint32_t v_lo0 = (uint32_t)kDescV | (((s_kv + C::kTileBytes) >> 4) & 0x3fffu);
-    const uint32_t t_s = tmem + x * 128, t_o = tmem + C::kTmemO + x * D, t_p = tmem + (C::kEarlyS ? C::kTmemP : x * 128);
-    auto issue_s = [&](int stage) {
-      if (elect_one_sync()) {
-        const uint32_t kl = k_lo0 + (uint32_t)stage * kStageStep;
-#pragma unroll
-        for (int c = 0; c < C::kChunks; ++c) {
-#pragma unroll
-          for (int ks = 0; ks < C::kCW / 16; ++ks) {
-            const uint32_t off = (uint32_t)(c * C::kChunkBytes + ks * 32) >> 4;
-            umma_f16_ss(t_s, desc(kDescQK, q_lo + off), desc(kDescQK, kl + off), idesc_s, (c | ks) ? 1u : 0u);
-          }
-        }
-        if (!(dbg & 32)) umma_commit(bar_s_full(x));          // (dbg & 32: timing probe, fewer commits)
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int stage, int j) {
-      if (elect_one_sync()) {
-        const uint32_t vl = v_lo0 + (uint32_t)stage * kStageStep;
-#pragma unroll
-        for (int ks = 0; ks < kPairBN / 16; ++ks)
-          umma_f16_ts(t_o, t_p + ks * 8, desc(kDescV, vl + (uint32_t)((ks * 16 * C::kRowBytes) >> 4)), idesc_o,
-                      (j > 0 || ks > 0) ? 1u : 0u);
-        if (!(dbg & 32) || j == n_vis - 1) umma_commit(bar_o_full(x));
-        umma_commit(bar_kv_empty(stage));      // this tile is done with K(j), V(j) once everything issued so far has completed
-      }
-      __syncwarp();
-    };
-    mbar_wait(bar_q, 0);
-    int stage_s = 0; uint32_t phase_s = 0;
-    int stage_o = 0;
-    if (n_vis > 0) {                            // prologue: S_x(0)
-      mbar_wait(bar_kv_full(stage_s), phase_s);
-      tc_fence_after();
-      issue_s(stage_s);
-      if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
-    }
-    if constexpr (C::kEarlyS) {
-      // S_x(j+1) as soon as S_x(j) sits in the softmax warps' registers (s_free), P V_x(j) when P_x(j) is in the
-      // shared P buffer (p_full).
-      for (int j = 0; j < n_vis; ++j) {
-        if (j + 1 < n_vis) {
-          tr(x, j + 1, kEvMmaTop);
-          if (!(dbg & 4)) mbar_wait(bar_s_free(x), j & 1);
-          mbar_wait(bar_kv_full(stage_s), phase_s);
-          tr(x, j + 1, kEvSFree);
-          tc_fence_after();
-          tr(x, j + 1, kEvMmaFenced);
-          issue_s(stage_s);
-          tr(x, j + 1, kEvSIssued);
-          if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
-        }
-        if (!(dbg & 4)) mbar_wait(bar_p_full(x), j & 1);
-        tr(x, j, kEvPFull);
-        tc_fence_after();
-        issue_pv(stage_o, j);
-        tr(x, j, kEvPVIssued);
-        if (++stage_o == kStages) stage_o = 0;
-      }
-    } else {
-      for (int j = 0; j < n_vis; ++j) {
-        mbar_wait(bar_p_full(x), j & 1);          // P_x(j) in TMEM (and O_x rescaled if it had to be)
-        tc_fence_after();
-        issue_pv(stage_o, j);
-        if (j + 1 < n_vis) {
-          mbar_wait(bar_kv_full(stage_s), phase_s);
-          tc_fence_after();
-          issue_s(stage_s);     // S_x(j+1) overwrites P_x(j): behind P V_x(j) in pipe order (same issuer)
-          if (++stage_s == kStages) { stage_s = 0; phase_s ^= 1; }
-        }
-        if (++stage_o == kStages) stage_o = 0;
-      }
-    }
-  } else if (NI == 1 && warp == kWMma) {
+  } else if (warp == 9) {
     // =================================== MMA issuer ===================================
     // Warp-uniform control flow; the MMAs / commits are issued by one elected lane.
     // (One issuing warp per query tile -- warp 10 for tile B -- was tried once the trace showed this warp's serial chain
@@ -486,21 +383,18 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
   }
   } else {
-    if constexpr (KH == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ============================ softmax / rescale / epilogue ============================
-    // Warp (x, h, quad): tile x, key columns [h * NC, (h + 1) * NC) of the tile, query rows quad * 32 + lane.
-    // KH = 2: two warps share a row.  They exchange the row maximum of every tile through shared memory (a named
-    // barrier of their 64 threads), keep their own partial row sum (the rescale factor is the same for both) and add
-    // the two at the end in a fixed order.  Why: ONE warp's softmax pass is bound by its own issue occupancy -- a MUFU
-    // instruction holds the warp's issue slot for 8 cycles, the packed FMA / pack / max instructions for 2: 128 x 8 +
-    // ~235 x 2 = 1500 cycles for 128 columns, which is what the trace shows (1540), and the pass of the other tile's warp
-    // on the same scheduler is staggered by half a period, so nothing overlaps it.  Two warps with 64 columns each run
-    // side by side on the scheduler: one's MUFU cycles hide the other's FMA-pipe cycles.
-    constexpr int NC = kPairBN / KH;                              // key columns per warp
-    const int x = warp / (4 * KH);                                // 0 = tile A, 1 = tile B
+    // (Two warps per row block -- 64 key columns each, the row maximum exchanged through shared memory and a named
+    // barrier of their 64 threads, partial row sums added in a fixed order, 640 threads -- were built on the theory that
+    // one warp's pass is bound by its own issue occupancy (128 MUFU x 8 cycles + ~235 packed FMA / pack / max x 2 = 1500
+    // cycles, what the trace shows) and that a second warp on the same scheduler would hide one's MUFU cycles under the
+    // other's FMA-pipe cycles.  Bit-identical in every test; 79.3 us at cfg2 with the single MMA issuer, 68.4 us with one
+    // issuer per query tile, against 66.4 us for this layout (cfg5: 765 / 632 / 606 us) -- 104 registers per thread spill
+    // inside the loop and the exchange adds a barrier to every tile.  profiles/r02p_attn_bench_8_softmax_warps.txt.  Deleted.)
+    const int x = warp >> 2;                                    // 0 = tile A, 1 = tile B
     if (x == 0 || has_b) {
-      const int quad = warp & 3, h = (warp / 4) % KH;
+      const int quad = warp & 3;
       const int row = quad * 32 + lane;                         // row of the tile == TMEM lane
       const int rows_here = min(kPairBM, rows_cta - x * kPairBM);
       const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -512,8 +406,6 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const int qc = valid ? q_code[grow] : 0x7fffffff;         // padding rows: see everything, never stored
       const int32_t* kc = k_code + (size_t)seq_id * max_pages * kPairBN;
       const float thresh = 8.0f / scale_log2;                   // lazy rescale: 2^8 head-room
-      [[maybe_unused]] const int pair_bar = 1 + x * 4 + quad;     // named barrier of the two warps of a row block (KH = 2)
-      auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_vis; ++j) {
         if (dbg & 4) continue;                                    // timing probe: free-running tensor pipe
@@ -522,7 +414,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         // Rows that cannot see the whole tile (the two tag rows at a frame start; everybody on the ragged last tile):
         //   * tile with ONE key code (most: 256 patch tokens per frame): such a row sees none of it -- it runs the
         //     same instructions with multiplier 0 / offset -inf (P = 0 exactly) and leaves the row maximum alone;
-        //   * mixed tile: the key codes are fetched BEFORE the wait for S (one int4 per lane: the latency hides
+        //   * mixed tile: the 128 key codes are fetched BEFORE the wait for S (one int4 per lane: the latency hides
         //     under the MMAs), staged in shared memory and applied to S in registers with two FMA-pipe instructions
         //     per score.
         // (First version: S patched in place in tensor memory, 32 columns at a time, codes loaded inside the loop:
@@ -533,7 +425,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         const bool elementwise = some && (ragged || !(ktu & kTileUniform));     // warp-uniform
         const bool blind = some && !elementwise && hidden;                        // per row
         int4 kc4 = make_int4(0, 0, 0, 0);
-        if (elementwise && lane < NC / 4) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN + h * NC) + lane);
+        if (elementwise) kc4 = __ldg(reinterpret_cast<const int4*>(kc + kt * kPairBN) + lane);
         mbar_wait(bar_s_full(x), j & 1);
         tr(x, j, kEvSFull);
         tc_fence_after();
@@ -543,10 +435,10 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           if (lane == 0) { if (C::kEarlyS) mbar_arrive(bar_s_free(x)); mbar_arrive(bar_p_full(x)); }
           continue;
         }
-        uint32_t s[NC];
+        uint32_t s[128];
 #pragma unroll
-        for (int c = 0; c < NC / 32; ++c)
-          tmem_ld_32x32b_x32(t_s + h * NC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        for (int c = 0; c < 4; ++c)
+          tmem_ld_32x32b_x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
         tmem_ld_wait();
         if constexpr (C::kEarlyS) {                                // S_x is free: S_x(j+1) may be issued now
           tc_fence_before();
@@ -565,7 +457,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
           __syncwarp();
           const float nqc = -(float)qc;
 #pragma unroll
-          for (int i = 0; i < NC / 4; ++i) {
+          for (int i = 0; i < 32; ++i) {
             const float4 c4 = my[i];                              // broadcast read
             s[4 * i + 0] = __float_as_uint(fmaf(__saturatef(c4.x + nqc), kMasked, __uint_as_float(s[4 * i + 0])));
             s[4 * i + 1] = __float_as_uint(fmaf(__saturatef(c4.y + nqc), kMasked, __uint_as_float(s[4 * i + 1])));
@@ -576,24 +468,14 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < NC / 4; ++i) {
+        for (int i = 0; i < 32; ++i) {
           mx0 = fmaxf(mx0, __uint_as_float(s[4 * i + 0]));
           mx1 = fmaxf(mx1, __uint_as_float(s[4 * i + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(s[4 * i + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(s[4 * i + 3]));
         }
         float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        if (blind || mx < 0.1f * kMasked) mx = -INFINITY;         // the row sees no key of these columns
-        if constexpr (KH == 2) {
-          // the row maximum of the whole tile: slot [tile parity][tile][half][row]; the parity keeps tile j + 1's
-          // writes away from a partner still reading tile j (it cannot be two tiles behind: it passed barrier j)
-          float* xm = x_max + (((j & 1) * 2 + x) * 2) * 128;
-          xm[h * 128 + row] = mx;
-          tc_fence_before();                                      // (head_dim 128: the partner's P goes where this warp read S)
-          pair_sync();
-          tc_fence_after();
-          mx = fmaxf(mx, xm[(h ^ 1) * 128 + row]);
-        }
+        if (blind || mx < 0.1f * kMasked) mx = -INFINITY;         // the row sees no key of this tile
         const bool grew = mx > m_run + thresh;                   // also true for the first finite maximum
         const float m_new = grew ? mx : m_run;
         const float sub = (m_new == -INFINITY) ? 0.f : __fmul_rn(m_new, scale_log2);
@@ -604,7 +486,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         float sum0 = 0.f, sum1 = 0.f;
         const float nsub = blind ? -INFINITY : -sub, mul = blind ? 0.f : scale_log2;
 #pragma unroll
-        for (int i = 0; i < NC / 2; ++i) {
+        for (int i = 0; i < 64; ++i) {
           float p0, p1;
           ffma2(p0, p1, __uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), mul, nsub);
           if (!(dbg & 2)) { p0 = ex2_ftz(p0); p1 = ex2_ftz(p1); }  // (dbg & 2: timing probe without MUFU)
@@ -622,23 +504,20 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
             tc_fence_after();
           }
           tr(x, j, kEvPBufFree);
-#pragma unroll
-          for (int c = 0; c < NC / 64; ++c)
-            tmem_st_32x32b_x32(t_p + h * (NC / 2) + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+          tmem_st_32x32b_x32(t_p, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_st_32x32b_x32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
         } else {
-#pragma unroll
-          for (int c = 0; c < NC / 64; ++c)
-            tmem_st_32x32b_x32(t_s + h * (NC / 2) + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+          tmem_st_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_st_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
         }
-        l_run = l_run * alpha + (sum0 + sum1);                    // (KH = 2: this warp's columns only)
+        l_run = l_run * alpha + (sum0 + sum1);
         m_run = m_new;
         if (j > 0 && __any_sync(0xffffffffu, grew)) {
-          // rare after the first tiles: O_x(j-1) must be complete, then scale this row (KH = 2: the two warps of a row
-          // take turns over the 32-column chunks; both see the same `grew`)
+          // rare after the first tiles: O_x(j-1) must be complete, then scale this row
           mbar_wait(bar_o_full(x), (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int u = h; u < D / 32; u += KH) {
+          for (int u = 0; u < D / 32; ++u) {
             uint32_t o[32];
             tmem_ld_32x32b_x32(t_o + u * 32, o);
             tmem_ld_wait();
@@ -650,16 +529,10 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 * KH per tile)
+        if (lane == 0) mbar_arrive(bar_p_full(x));               // one arrival per warp (4 per tile)
         tr(x, j, kEvPWritten);
       }
       // ---- epilogue: O / l -> bf16 -> global ------------------------------------------------
-      if constexpr (KH == 2) {                                    // row sum = columns of half 0 + columns of half 1, in that order
-        float* xs = x_sum + (x * 2) * 128;
-        xs[h * 128 + row] = l_run;
-        pair_sync();
-        l_run = xs[row] + xs[128 + row];
-      }
       if (n_vis > 0) {
         mbar_wait(bar_o_full(x), (n_vis - 1) & 1);
         tc_fence_after();
@@ -668,7 +541,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __nv_bfloat16* orow = out + (size_t)grow * out_ld + head * D;
 #pragma unroll
-      for (int u = h; u < D / 32; u += KH) {
+      for (int u = 0; u < D / 32; ++u) {
         uint32_t o[32];
         if (n_vis > 0) {
           tmem_ld_32x32b_x32(t_o + u * 32, o);
@@ -702,7 +575,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       int base = 0;
       for (int r = 0; r < kTraceRoles; ++r) {
         const int n = s_trace_n[r];
-        for (int i = threadIdx.x; i < n; i += pair_threads(KH)) {
+        for (int i = threadIdx.x; i < n; i += kPairThreads) {
           const uint2 e = trace_rings[r * kTracePerRole + i];
           g_attn_trace[2 * (base + i)] = e.x;
           g_attn_trace[2 * (base + i) + 1] = ((unsigned long long)r << 40) | ((unsigned long long)(e.y >> 28) << 32) |
@@ -713,7 +586,7 @@ attn_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
       if (threadIdx.x == 0) g_attn_trace_n = (unsigned)base;
     }
   }
-  if (warp == kWMma) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -732,13 +605,7 @@ static bool attn_trace_on() {      // VGPT_ATTN_VARIANT=8: the diagnostic instan
   return e && atoi(e) == 8;
 }
 
-// VGPT_ATTN_HALVES=2: two softmax warps per row block (64 key columns each, 640 threads); default 1
-static int attn_halves() {
-  static const int v = [] { const char* e = getenv("VGPT_ATTN_HALVES"); return e && atoi(e) == 2 ? 2 : 1; }();
-  return v;
-}
-
-template <int D, bool TRACE, int KH, int NI>
+template <int D, bool TRACE>
 static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int out_ld, const void* k_pool,
                             const void* v_pool, int total_pages, const int32_t* page_table, int max_pages,
                             const void* seqs, int num_seqs, int q_pairs, const int32_t* q_code,
@@ -763,12 +630,12 @@ static int launch_attn_pair(const void* q, int q_ld, int q_rows, void* out, int 
     rc = encode_tensor_map(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(v_pool), dims, strides, box, estr, swz);
     if (rc) return rc;
   }
-  auto kern = attn_pair_tcgen05_kernel<D, TRACE, KH, NI>;
+  auto kern = attn_pair_tcgen05_kernel<D, TRACE>;
   constexpr int smem = TRACE ? C::kSmemTrace : C::kSmem;
   // per launch: the attribute is per device, and a process may drive several devices (cheap, capture-safe)
   VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(H, q_pairs, num_seqs);
-  kern<<<grid, pair_threads(KH), smem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
+  kern<<<grid, kPairThreads, smem, s>>>(tq, tk, tv, (__nv_bfloat16*)out, out_ld, page_table, max_pages,
                                             (const AttnSeqP*)seqs, q_code, k_code, k_tile_minmax,
                                             max_k_tiles64, H, scale * 1.4426950408889634f, debug_attn_flags());
   VGPT_CHECK_LAUNCH();
@@ -812,19 +679,15 @@ int attn_clip_causal_pair(const void* q, int q_ld, int q_rows, void* out, int ou
   if (num_seqs <= 0 || max_q_rows <= 0) return 0;
   const int q_pairs = (max_q_rows + 2 * kPairBM - 1) / (2 * kPairBM);
   const bool trace = D == 96 && attn_trace_on();
-#define VGPT_ATTN_CASE(D_, T_, KH_)                                                                          \
-  if (D == D_ && trace == T_ && halves == KH_)                                                               \
-    return launch_attn_pair<D_, T_, KH_, KH_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table, \
-                                         max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,   \
-                                         max_k_tiles, H, scale, s);
-  const int halves = trace ? 1 : attn_halves();
-  VGPT_ATTN_CASE(64, false, 1)
-  VGPT_ATTN_CASE(96, false, 1)
-  VGPT_ATTN_CASE(96, true, 1)
-  VGPT_ATTN_CASE(128, false, 1)
-  VGPT_ATTN_CASE(64, false, 2)
-  VGPT_ATTN_CASE(96, false, 2)
-  VGPT_ATTN_CASE(128, false, 2)
+#define VGPT_ATTN_CASE(D_, T_)                                                                              \
+  if (D == D_ && trace == T_)                                                                                \
+    return launch_attn_pair<D_, T_>(q, q_ld, q_rows, out, out_ld, k_pool, v_pool, total_pages, page_table,  \
+                                    max_pages, seqs, num_seqs, q_pairs, q_code, k_code, k_tile_minmax,      \
+                                    max_k_tiles, H, scale, s);
+  VGPT_ATTN_CASE(64, false)
+  VGPT_ATTN_CASE(96, false)
+  VGPT_ATTN_CASE(96, true)
+  VGPT_ATTN_CASE(128, false)
 #undef VGPT_ATTN_CASE
   return -1;
 }
