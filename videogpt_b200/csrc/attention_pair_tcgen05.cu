@@ -1,8 +1,8 @@
 // Clip-block-causal flash attention, production kernel: TWO 128-row query tiles per CTA that
 // ping-pong on the tensor pipe (tcgen05 + TMEM + TMA).
 //
-// Same contract as attention.cu / attention_tcgen05.cu (codes instead of a mask, paged KV pools,
-// tile classification from per-tile code min/max).  What changed against attention_tcgen05.cu
+// Same contract as attention.cu, the mma.sync cross-check kernel (codes instead of a mask, paged KV pools,
+// tile classification from per-tile code min/max).  What changed against the first tcgen05 version
 // (one query tile, 8 softmax warps, 101 us per launch at cfg2) and why:
 //
 //   * One CTA owns query tiles A and B of the same (sequence, head): every K/V tile is loaded once

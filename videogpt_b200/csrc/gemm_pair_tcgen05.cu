@@ -32,6 +32,10 @@
 //     of 192-wide tiles, and the hand-over traffic ate the better main-loop efficiency of the wider tile: o_proj 51.9 vs
 //     45.4 us, down_proj 92.3 vs 92.3 us at M = 2064; profiles/r02g_gemm_sweep_splitk.txt.)
 //
+//   * (Also tried: the residual of chunk c + 1 requested before the wait for chunk c's accumulator, so that the epilogue
+//     of a cluster's last tile does not pay a global-load latency per chunk: o_proj 45.3 vs 45.1 us, down_proj inside
+//     the run-to-run band -- no measurable gain, reverted.)
+//
 // Pair protocol (cluster of 2 along M; rank 0 = leader): both CTAs' TMA loads are .cta_group::2 and complete_tx on
 // the LEADER's full barrier (its arrive.expect_tx accounts for both halves); the leader's elected thread issues the
 // MMAs and commits with .multicast::cluster to the empty / tmem-full barriers of BOTH CTAs; each CTA's epilogue warps
@@ -124,24 +128,6 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&acc)[32], __nv_bflo
         a = rbf(a) + bf16lo(rv);
         b = rbf(b) + bf16hi(rv);
       }
-      w[j] = pack_bf16x2(a, b);
-    }
-    op[i] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
-// The same with the residual already in registers (loaded one chunk ahead by the caller).
-__device__ __forceinline__ void store_chunk_residual(const uint32_t (&acc)[32], __nv_bfloat16* __restrict__ out,
-                                                     const uint4 (&r)[4]) {
-  uint4* op = reinterpret_cast<uint4*>(out);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t rv = (&r[i].x)[j];
-      const float a = rbf(__uint_as_float(acc[i * 8 + j * 2])) + bf16lo(rv);
-      const float b = rbf(__uint_as_float(acc[i * 8 + j * 2 + 1])) + bf16hi(rv);
       w[j] = pack_bf16x2(a, b);
     }
     op[i] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -335,40 +321,15 @@ gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           tmem_ld_wait();
           if (row < M && n0 + c * 32 < N) store_chunk_swiglu(acc, crow + c * 16);
         }
-      } else if constexpr (EPI == kEpiResidual) {
-        // The residual of chunk c + 1 is requested BEFORE the wait for chunk c's accumulator: a global load issued
-        // inside store_chunk cost its full latency on every one of the 6 - 8 chunks, and the epilogue of a cluster's
-        // LAST tile is not hidden behind any main loop (o_proj / down_proj: two tiles per cluster).  In place on the
-        // residual stream: a chunk's residual is only ever overwritten by this same thread, later.
-        __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
-        const uint4* rrow = reinterpret_cast<const uint4*>(R + (size_t)row * ldc + n0);
-        const int chunks = width / 32;
-        uint4 r_cur[4], r_next[4];
-        auto load_r = [&](int c, uint4 (&r)[4]) {
-          if (row < M && n0 + c * 32 < N) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) r[i] = rrow[c * 4 + i];
-          }
-        };
-        load_r(0, r_cur);
-#pragma unroll 1
-        for (int c = 0; c < chunks; ++c) {
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, acc);
-          if (c + 1 < chunks) load_r(c + 1, r_next);
-          tmem_ld_wait();
-          if (row < M && n0 + c * 32 < N) store_chunk_residual(acc, crow + c * 32, r_cur);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) r_cur[i] = r_next[i];
-        }
       } else {
         __nv_bfloat16* crow = C + (size_t)row * ldc + n0;
+        const __nv_bfloat16* rrow = (EPI == kEpiResidual) ? R + (size_t)row * ldc + n0 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < width / 32; ++c) {
           uint32_t acc[32];
           tmem_ld_32x32b_x32(taddr + c * 32, acc);
           tmem_ld_wait();
-          if (row < M && n0 + c * 32 < N) store_chunk<EPI>(acc, crow + c * 32, nullptr);
+          if (row < M && n0 + c * 32 < N) store_chunk<EPI>(acc, crow + c * 32, rrow + c * 32);
         }
       }
     };

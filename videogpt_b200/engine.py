@@ -247,7 +247,7 @@ def shard_rows(lo: int, hi: int, rank: int, world: int):
     boundaries are rounded down to multiples of 128 rows (the last rank takes the remainder): a shard
     then starts on a tile boundary of the attention kernel (a 129-row shard would cost a second, almost
     empty query tile on EVERY rank instead of on one) and the remainder rows meet the GEMM as one tail
-    (``gemm2_tcgen05.cu`` tail tiles).  Otherwise sizes differ by at most one."""
+    (``gemm_pair_tcgen05.cu``: tail rows in the k-loop).  Otherwise sizes differ by at most one."""
     n = hi - lo
     if n >= SHARD_ALIGN * world:
         cut = lambda r: n if r >= world else (n * r // world) // SHARD_ALIGN * SHARD_ALIGN
