@@ -274,10 +274,15 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     sp_size = 1
+    cfg_split = args.parallelism == "cfg" and world > 1
     if args.parallelism == "sp" and world > 1:
         from videogpt_b200 import parallel_states
         sp_size = args.sp or world
         parallel_states.initialize_sequence_parallel_state(sp_size)   # the reference's SP switch
+    elif cfg_split:
+        from videogpt_b200 import parallel_states
+        sp_size = 2                                                   # pairs of ranks, one CFG branch each
+        parallel_states.initialize_cfg_branch_parallel_state()
     model = build_model(dims, dev)
     pipe = LVMPipeline(None, model, LVMProcessor(FakeTokenizer()), device=dev)
     block = H * W // 256 + 2
@@ -292,23 +297,6 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    cfg_split = args.parallelism == "cfg" and world > 1
-    if cfg_split:
-        from videogpt_b200 import parallel
-        grp = parallel.CfgBranchGroup()
-        lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42 + grp.video_group)
-        ctx_dev = [x.to(dev, torch.bfloat16) for x in lat[:n_ctx]]
-        noise_dev = [x.to(dev, torch.bfloat16) for x in lat[n_ctx:]]
-        proc = LVMProcessor(FakeTokenizer())
-        from videogpt_b200.pipeline import frame_block_prompts
-        p, p_ = frame_block_prompts(n_ctx, n_gen)
-        d = proc.prompt_condition_frame_block_inference(
-            [p, p_], [[torch.empty(3, H, W, device="meta")] * n_ctx, []], height=H, width=W, use_img_cfg=True,
-            use_input_image_size_as_output=True, frame_blocks=[n_ctx, n_gen], build_dense_mask=False)
-        mk = dict(input_ids=d["input_ids"], input_img_latents=ctx_dev, input_image_sizes=d["input_image_sizes"],
-                  attention_mask=None, position_ids=d["position_ids"], denoise_image_sizes=d["denoise_image_sizes"],
-                  time_emb_inx=d["time_emb_inx"], img_cfg_scale=GUIDANCE, use_img_cfg=True)
 
     # configs[3]: this rank's share of the job's videos, `--batch` videos per pass through the engine
     # (all rows of those videos and both CFG branches in one [M, hidden] matrix)
@@ -340,8 +328,6 @@ def run_ours(args, rank, world, local_rank):
             return pipe.rollout_latents([x.clone() for x in ctx_dev], [n_gen] * rounds, **roll_kw)
         if vids_rank:
             return batch_pass([[x.clone() for x in c] for c in vctx_dev], vnoise_dev)
-        if cfg_split:
-            return parallel.sample_cfg_split(model, LVMScheduler(euler), [x.clone() for x in noise_dev] * 2, mk, grp, "x1")
         # a fresh context tensor list every clip => the engine re-runs the prefill (as a new clip would)
         return pipe.next_clip_latents([x.clone() for x in ctx_dev], n_gen, initial_noise=noise_dev, **kw)
 
@@ -350,12 +336,7 @@ def run_ours(args, rank, world, local_rank):
             return [x.to("cpu") for x in pipe.rollout_latents(ctx_host, [n_gen] * rounds, **roll_kw)]
         if vids_rank:
             return [[x.to("cpu") for x in v] for v in batch_pass(vctx_host, vnoise_host)]
-        if cfg_split:
-            mk["input_img_latents"] = [x.to(dev, non_blocking=True) for x in ctx_host]
-            out = parallel.sample_cfg_split(model, LVMScheduler(euler), [x.to(dev, non_blocking=True) for x in noise_host] * 2,
-                                            mk, grp, "x1")
-        else:
-            out = pipe.next_clip_latents(ctx_host, n_gen, initial_noise=noise_host, **kw)
+        out = pipe.next_clip_latents(ctx_host, n_gen, initial_noise=noise_host, **kw)
         return [x.to("cpu", non_blocking=False) for x in out]
 
     if sp_size > 1 and os.environ.get("VGPT_SP_WATCHDOG"):
@@ -412,16 +393,16 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return None
     tokens_per_clip = 2 * n_gen * block * euler * rounds
-    videos = world // 2 if cfg_split else world // sp_size
+    videos = world // sp_size
     if vids_rank:
         videos = world * vids_rank
     value = videos * tokens_per_clip * args.steps / dt
     e2e = videos * tokens_per_clip * args.steps / dt_e2e
     step_fl, prefill_fl, clip_fl = algorithmic_flops(dims, n_ctx, n_gen, block, euler)
     e = model.engine()
-    # per Euler step: the engine's kernels (the scheduler update rides in the final-layer kernel on one GPU; a separate
-    # vgpt_cfg_euler launch per step in sequence-parallel groups and CFG-branch pairs)
-    launches = args.steps * rounds * (e.launches_per_prefill + euler * (e.launches_per_predict + (1 if (sp_size > 1 or cfg_split) else 0)))
+    # per Euler step: the engine's kernels (the scheduler update rides in the final-layer kernel on one GPU; it is a
+    # vgpt_cfg_euler launch of its own, inside the step graph, in sequence-parallel groups and CFG-branch pairs)
+    launches = args.steps * rounds * (e.launches_per_prefill + euler * (e.launches_per_predict + (1 if sp_size > 1 else 0)))
     if vids_rank:
         launches *= vids_rank // args.batch
 
@@ -477,7 +458,8 @@ def run_ours(args, rank, world, local_rank):
                        "euler_steps": euler, "cfg": True, "guidance": GUIDANCE, "prediction_type": "x1",
                        "parallelism": (f"dp{world}: {vids_rank} of {world * vids_rank} videos per rank, {args.batch} videos x 2 CFG "
                                        f"branches per engine pass" if vids_rank else
-                                       f"cfg-branch pairs x dp{world // 2}" if cfg_split else
+                                       f"cfg-branch pairs (rank 0 of a pair: conditional sequence, rank 1: unconditional; the "
+                                       f"prediction pushed to the peer over NVLink, K/V local) x dp{world // 2}" if cfg_split else
                                        f"sp{sp_size} (rows of one video sharded, K/V pushed to peers over NVLink) x dp{world // sp_size}"
                                        if sp_size > 1 else f"dp{world} (independent videos)"),
                        "rollout": ({"rounds": rounds, "window_frames": n_ctx + n_gen,
@@ -499,12 +481,14 @@ def run_ours(args, rank, world, local_rank):
         rows_step, rows_prefill = 2 * n_gen * block, n_ctx * block
         kv_row = 2 * dims.hidden_size * 2 * dims.num_hidden_layers
         n_steps_timed = args.steps * rounds * euler
+        if cfg_split:          # whole sequences per rank: K/V stay local, two barriers per step
+            kv_row = 0
         line["sequence_parallel"] = {
             "sp": sp_size, "per_gpu_tflops": clip_fl * args.steps / dt / 1e12 / sp_size,
             "barrier_ms_per_euler_step": {"slowest_rank": 1e3 * barrier_max / n_steps_timed,
                                           "fastest_rank": 1e3 * barrier_min / n_steps_timed,
                                           "note": "device time inside vgpt_peer_barrier kernels (%d per step): waiting for the "
-                                                  "slowest peer + NVLink flag round trip; prefill barriers included" % (dims.num_hidden_layers + 1)},
+                                                  "slowest peer + NVLink flag round trip; prefill barriers included" % (2 if cfg_split else dims.num_hidden_layers + 1)},
             "nvlink_bytes_per_euler_step": (sp_size - 1) * (rows_step * kv_row + 2 * n_gen * lat_bytes),
             "nvlink_bytes_prefill": (sp_size - 1) * rows_prefill * kv_row}
         roofline["whole_clip_frac_of_sustained"] = roofline["whole_clip_tflops"] / sp_size / peaks.get("bf16_tflops_sustained", 1400.0)

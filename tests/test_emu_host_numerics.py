@@ -347,13 +347,18 @@ def test_rollout_refuses_to_continue_after_the_engine_was_used_for_another_clip(
 
 
 # ---- sequence parallelism: row-sharded plans on virtual ranks --------------------------------------
-@pytest.mark.parametrize("world,geom", [(2, (3, 2, 64, 96)), (3, (2, 2, 64, 64)), (4, (8, 2, 64, 64)), (8, (4, 4, 128, 128)), (8, (1, 1, 32, 32))])
-def test_row_sharded_virtual_ranks_reproduce_the_unsharded_engine_and_the_oracle(emu, world, geom):
+@pytest.mark.parametrize("world,geom,partition", [(2, (3, 2, 64, 96), "rows"), (3, (2, 2, 64, 64), "rows"), (4, (8, 2, 64, 64), "rows"),
+                                                  (8, (4, 4, 128, 128), "rows"), (8, (1, 1, 32, 32), "rows"),
+                                                  (2, (2, 2, 256, 256), "rows"), (3, (3, 3, 256, 256), "rows"),   # two ranges per rank
+                                                  (2, (3, 2, 64, 96), "sequences"), (2, (1, 1, 32, 32), "sequences")])
+def test_row_sharded_virtual_ranks_reproduce_the_unsharded_engine_and_the_oracle(emu, world, geom, partition):
     """CPU twin of tests/test_sequence_parallel.py::test_virtual_ranks_match_unsharded_engine_bit_exact:
     every virtual rank runs its chunk of the rows of every sequence, the K/V-append and final-layer
     emulations store into every rank's buffers through the raw pointers the engine hands out, and
     all ranks end up with the complete K/V pool and the complete prediction -- equal to the
-    unsharded engine's (fp32 rounding) and, over 3 Euler steps, to the oracle's sampler."""
+    unsharded engine's (fp32 rounding) and, over 3 Euler steps, to the oracle's sampler.
+    ``partition="sequences"``: one CFG branch per rank -- K/V stay on the rank that owns the sequence,
+    only the prediction is stored into the peer."""
     from videogpt_b200 import engine as eng, peer
     n_ctx, n_gen, H, W = geom
     dims = synth.REDUCED
@@ -376,12 +381,17 @@ def test_row_sharded_virtual_ranks_reproduce_the_unsharded_engine_and_the_oracle
     ref.prefill(ctx)
     ranks = [engine(m) for m in peer.LocalPeerGroup.create(world, dev)]
     for r, e in enumerate(ranks):
-        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev, shard=(r, world)))
+        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev, shard=(r, world), partition=partition))
         emu.register_peer_buffers(e._kv_shared)
         emu.register_peer_buffers(e._pred_shared)
     eng.run_lockstep([e.prefill_steps(ctx) for e in ranks])
-    for e in ranks:
-        assert (e.kv - ref.kv).abs().max() < 1e-4
+    for r, e in enumerate(ranks):
+        if partition == "rows":
+            assert (e.kv - ref.kv).abs().max() < 1e-4
+        else:           # only its own sequence's pages; nobody wrote the other sequence's
+            mine = ref.plan.page_table[r, :(specs[r].n_prefix + specs[r].n_active + 127) // 128].long()
+            other = ref.plan.page_table[1 - r, :(specs[1 - r].n_prefix + specs[1 - r].n_active + 127) // 128].long()
+            assert (e.kv[:, :, mine] - ref.kv[:, :, mine]).abs().max() < 1e-4 and e.kv[:, :, other].abs().max() == 0
     sigma = torch.linspace(0, 1, 4)
     for e in [ref] + ranks:
         e.z.copy_(z0)
@@ -401,6 +411,85 @@ def test_row_sharded_virtual_ranks_reproduce_the_unsharded_engine_and_the_oracle
                                mk, num_steps=3, prediction_type="x1")
     for e in ranks:
         assert _maxerr([e.z], [torch.cat(want, 0)]) < 5 * TOL
+
+
+def test_cfg_branch_pair_through_model_and_scheduler_reproduces_the_oracle(emu):
+    """The user-facing flow of a CFG-branch pair: ``initialize_sequence_parallel_state(2, partition="sequences")``
+    (here: its state set by hand, two ranks as threads), then ``LVMScheduler`` on ``frame_block_forward_with_cfg``
+    as on one GPU.  Barriers per clip: none in the prefill, two per Euler step; both ranks end on the oracle's
+    latents, x1 and v, and a second clip with fresh context tensors reuses the plan."""
+    import threading
+    from videogpt_b200 import LVMScheduler, engine as eng, parallel_states as ps, peer
+    world, n_ctx, n_gen, H, W, steps = 2, 3, 2, 64, 96, 3
+    bar, lock = threading.Barrier(world), threading.Lock()
+    counts = [0] * world
+
+    class ThreadPeers(peer.LocalPeerGroup):
+        lockstep = False
+
+        def alloc(self, nbytes):
+            with lock:
+                buf = super().alloc(nbytes)
+                emu.register_peer_buffers(buf)
+            bar.wait()
+            return buf
+
+        def barrier(self):
+            counts[self.rank] += 1
+            bar.wait()
+
+        def host_barrier(self):
+            bar.wait()
+
+    registry = []
+    members = [ThreadPeers(r, world, torch.device("cpu"), registry) for r in range(world)]
+    models = [_model()[0] for _ in range(world)]
+    sd = _model()[1]
+    got, errors, rows = [dict() for _ in range(world)], [], [None] * world
+
+    def rank_main(r):
+        try:
+            m, d = models[r], models[r].dims()
+            m._engine = eng.NextClipEngine(eng.EngineWeights(m.state_dict(), d.num_hidden_layers, "cpu"), d.hidden_size,
+                                           d.intermediate_size, d.num_hidden_layers, d.num_attention_heads,
+                                           d.rms_norm_eps, d.rope_theta, "cpu", use_cuda_graph=False, peers=members[r])
+            m._engine_key = tuple(p._version for p in m.parameters())
+            m.engine = lambda: m._engine
+            for pt in ("x1", "v"):
+                for clip in range(2):
+                    mk, z_list = _mk(n_ctx, n_gen, H, W)
+                    before = counts[r]
+                    out = LVMScheduler(steps)([x.clone() for x in z_list] * 2, m.frame_block_forward_with_cfg, mk,
+                                              prediction_type=pt)
+                    got[r][(pt, clip)] = (out, counts[r] - before)
+            rows[r] = (m._engine.plan.partition, m._engine.plan.prefix.rows, m._engine.plan.step.rows)
+        except BaseException as exc:          # a dead rank must not leave the other waiting forever
+            errors.append(exc)
+            bar.abort()
+
+    ps.hccl_info.partition = "sequences"
+    try:
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(300)
+    finally:
+        ps.hccl_info.partition = "rows"
+    assert not errors, errors
+    block = H * W // 256 + 2
+    assert rows == [("sequences", n_ctx * block, n_gen * block), ("sequences", 0, n_gen * block)]
+    for pt in ("x1", "v"):
+        mk, z_list = _mk(n_ctx, n_gen, H, W)
+        with torch.no_grad():
+            want = so.euler_sample([x.clone() for x in z_list] * 2,
+                                   lambda z, t, **kw: mo.frame_block_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                                   mk, num_steps=steps, prediction_type=pt)
+        for r in range(world):
+            for clip in range(2):
+                out, n_barriers = got[r][(pt, clip)]
+                assert n_barriers == 2 * steps, (r, pt, clip, n_barriers)
+                assert _maxerr(out, want) < 5 * TOL, (r, pt, clip)
 
 
 def test_rollout_under_sequence_parallelism_matches_the_single_rank_rollout(emu):

@@ -236,6 +236,42 @@ def test_sequence_parallel_ranks_agree_on_sync_points(monkeypatch, geom, world):
     assert sum(t[3] for t in traces) == sum(sp.n_active for sp in specs)
 
 
+@pytest.mark.parametrize("geom", [(4, 4, 256, 256), (32, 4, 256, 256), (1, 1, 64, 64)])
+def test_cfg_branch_pair_ranks_agree_on_sync_points(monkeypatch, geom):
+    """partition="sequences" on two ranks: no barrier in the prefill (K/V never travel: the local append kernel, not
+    the peer one), two per step -- one in front (a peer's next prediction must not overwrite one this rank has not
+    consumed) and one behind the prediction stores -- on BOTH ranks although rank 1 has no prefix rows at all; the
+    scheduler update is enqueued behind the second barrier when the sampler's fused loop asks for it."""
+    from videogpt_b200 import engine as eng, peer
+    stub = StubOpsSP()
+    monkeypatch.setattr(eng, "ops", stub)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    n_ctx, n_gen, H, W = geom
+    dims = synth.REDUCED
+    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
+    specs, n_lat, n_ctx_lat = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
+                                                   d["denoise_image_sizes"], d["time_emb_inx"])
+    sd = {k: v.to(BF) for k, v in synth.init_state_dict(dims, seed=0, with_pos_embed=False).items()}
+    w = eng.EngineWeights(sd, dims.num_hidden_layers, "cpu")
+    L = dims.num_hidden_layers
+    for r, m in enumerate(peer.LocalPeerGroup.create(2, "cpu")):
+        e = eng.NextClipEngine(w, dims.hidden_size, dims.intermediate_size, dims.num_hidden_layers,
+                               dims.num_attention_heads, dims.rms_norm_eps, dims.rope_theta, "cpu",
+                               dims.pos_embed_max_size, 2, use_cuda_graph=False, peers=m)
+        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu", shard=(r, 2), partition="sequences"))
+        stub.calls.clear()
+        assert list(e.prefill_steps(None)) == []
+        assert (e.plan.prefix.rows, e.plan.step.rows) == ((specs[0].n_prefix, specs[0].n_active) if r == 0 else (0, specs[1].n_active))
+        assert stub.calls.count("rope_kv_append") == (L if r == 0 else 0) and "rope_kv_append_peers" not in stub.calls
+        stub.calls.clear()
+        e.euler_mode = (True, True)
+        assert list(e.predict_steps()) == ["start", "pred"]
+        assert stub.calls.count("rope_kv_append") == L and "rope_kv_append_peers" not in stub.calls
+        assert stub.calls.count("final_layer_rows") == 1 and stub.calls[-1] == "cfg_euler"
+        m.lockstep = False
+        assert e.launches_per_predict == 6 + 1 + 8 * L + 1 + 2
+
+
 def test_plan_cache_keeps_its_key_objects_alive(dry):
     """The per-clip cache key identifies the conditioning tensors by object; the model must hold
     them, otherwise the allocator hands the freed address to the NEXT clip's context and a stale

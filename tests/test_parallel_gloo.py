@@ -185,7 +185,7 @@ def test_peer_groups_of_two_in_world4():
 # many collectives a rank enters (plan cache hits, prefill, re-planning) are the real code.
 # A rank-inconsistent decision dead-locks here (caught by the timeout) exactly as it would on GPUs.
 # ------------------------------------------------------------------------------------------------
-def _sp_host_flow(rank, world):
+def _sp_host_flow(rank, world, partition="rows"):
     from unittest import mock
     from transformers import Phi3Config
     from oracle import processor_oracle as po
@@ -212,7 +212,7 @@ def _sp_host_flow(rank, world):
                                                  peers=self.sequence_parallel_peers())
         return self._engine
 
-    ps.initialize_sequence_parallel_state(2)
+    ps.initialize_sequence_parallel_state(2, partition=partition)
     try:
         with mock.patch.object(engine, "ops", stub), mock.patch.object(model, "ops", stub), \
                 mock.patch.object(scheduler, "ops", stub), mock.patch.object(torch.cuda, "is_available", lambda: True), \
@@ -237,7 +237,7 @@ def _sp_host_flow(rank, world):
                 per_clip.append(len(barriers) - before)
                 del junk, mk
             e = m._engine
-            return per_clip, e.plan.shard, (e.plan.prefix.rows, e.plan.step.rows), L
+            return per_clip, e.plan.shard, (e.plan.prefix.rows, e.plan.step.rows), L, e.plan.partition
     finally:
         ps.destroy_sequence_parallel_group()
 
@@ -250,6 +250,20 @@ def test_sequence_parallel_host_flow_world2():
     assert out[0][0] == out[1][0] == [L + 2 * (L + 1)] * 3
     assert out[0][1] == (0, 2) and out[1][1] == (1, 2)
     assert out[0][2][0] + out[1][2][0] == 3 * 26 and out[0][2][1] + out[1][2][1] == 2 * 2 * 26
+
+
+def _cfg_pair_host_flow(rank, world):
+    return _sp_host_flow(rank, world, partition="sequences")
+
+
+@pytest.mark.timeout(240)
+def test_cfg_branch_pair_host_flow_world2():
+    """Same flow with one CFG branch per rank (``partition="sequences"``): rank 1 has no context rows, yet both ranks
+    enter the same host rendezvous and the same two barriers per Euler step, every clip."""
+    out = _spawn(2, _cfg_pair_host_flow)
+    assert out[0][0] == out[1][0] == [2 * 2] * 3
+    assert out[0][1] == (0, 2) and out[1][1] == (1, 2) and out[0][4] == out[1][4] == "sequences"
+    assert out[0][2] == (3 * 26, 2 * 26) and out[1][2] == (0, 2 * 26)
 
 
 # ---- CFG-branch pairs, numerically: two gloo ranks, kernel wrappers emulated on CPU (fp32) --------

@@ -43,21 +43,84 @@ def test_sharded_plans_partition_the_unsharded_plan(world, geom):
         f = getattr(full, which)
         ph = [getattr(p, which) for p in parts]
         assert sum(x.rows for x in ph) == f.rows
-        for name in ("row_pos", "row_slot", "q_code", "kind", "arg_a", "arg_b"):
-            # rows of sequence s on rank r, re-assembled sequence-major, must equal the full plan
-            pieces = []
-            for s in range(len(specs)):
-                for x in ph:
-                    q0, n = int(x.seqs[s, 0]), int(x.seqs[s, 1])
-                    pieces.append(getattr(x, name)[q0:q0 + n])
-            assert torch.equal(torch.cat(pieces), getattr(f, name)), (which, name)
         for s in range(len(specs)):
+            # the rows of sequence s on all ranks, put back in sequence order (a row's K/V slot is unique and
+            # ascending in the fresh plan), are exactly the unsharded plan's rows of that sequence
+            fq0, fn = int(f.seqs[s, 0]), int(f.seqs[s, 1])
+            pieces = {name: torch.cat([getattr(x, name)[int(x.seqs[s, 0]):int(x.seqs[s, 0]) + int(x.seqs[s, 1])] for x in ph])
+                      for name in ("row_pos", "row_slot", "q_code", "kind", "arg_a", "arg_b")}
+            order = torch.argsort(pieces["row_slot"])
+            assert len(torch.unique(pieces["row_slot"])) == fn                # nobody's rows overlap
+            for name, got in pieces.items():
+                assert torch.equal(got[order], getattr(f, name)[fq0:fq0 + fn]), (which, name, s)
+            for x in ph:       # inside a rank the rows of a sequence stay in ascending order (cheap chunk, then dear chunk)
+                slots = x.row_slot[int(x.seqs[s, 0]):int(x.seqs[s, 0]) + int(x.seqs[s, 1])]
+                assert bool((slots[1:] > slots[:-1]).all())
             sizes = [int(x.seqs[s, 1]) for x in ph]
-            # balanced: within one row, or -- when every rank gets whole 128-row tiles -- within one tile + remainder
-            assert max(sizes) - min(sizes) <= (1 if sum(sizes) < eng.SHARD_ALIGN * world else 2 * eng.SHARD_ALIGN - 1)
-            if sum(sizes) >= eng.SHARD_ALIGN * world:
-                assert all(n % eng.SHARD_ALIGN == 0 for n in sizes[:-1])   # every shard starts on an attention tile
             assert all(int(x.seqs[s, 2]) == int(f.seqs[s, 2]) for x in ph)   # every rank sees all keys
+            if sum(sizes) >= 2 * eng.SHARD_ALIGN * world:
+                # whole 128-row tiles everywhere; only the owner of the sequence's last rows carries the remainder
+                assert sorted(n % eng.SHARD_ALIGN for n in sizes)[:-1] == [0] * (world - 1)
+            else:
+                assert max(sizes) - min(sizes) <= (1 if sum(sizes) < eng.SHARD_ALIGN * world else 2 * eng.SHARD_ALIGN - 1)
+
+
+def _attention_tiles(ranges, block, n_ctx_blocks):
+    """KV tiles a rank's attention CTAs walk for the given generated rows (frame-block causal)."""
+    rows = np.concatenate([np.arange(a, b) for a, b in ranges]) if ranges else np.zeros(0, int)
+    total = 0
+    for c0 in range(0, len(rows), 256):
+        last = rows[min(c0 + 256, len(rows)) - 1]
+        total += -(-((n_ctx_blocks + last // block + 1) * block) // 128)
+    return total
+
+
+@pytest.mark.parametrize("world,n", [(2, 4104), (4, 4104), (8, 4104), (2, 1032), (2, 8256), (8, 8256)])
+def test_shard_ranges_balance_the_causal_attention_cost(world, n):
+    """BASELINE configs[4] / [1] geometries: with one contiguous chunk per rank the last rank walks far more KV tiles
+    than the first (its queries are the last frames); cheapest-with-dearest chunk pairs even that out, and the two
+    sequences' remainder rows (an attention CTA of their own each) land on different ranks."""
+    block, ctx = n // 4, 4
+    contiguous = [_attention_tiles([eng.shard_rows(0, n, r, world)], block, ctx) for r in range(world)]
+    paired = [_attention_tiles(eng.shard_ranges(0, n, r, world), block, ctx) for r in range(world)]
+    assert sum(paired) <= sum(contiguous) + world and max(paired) < max(contiguous)
+    # slowest rank over the mean: 1.21 -> 1.07 (cfg5, 2 ranks), 1.71 -> 1.50 (8 ranks: what is left is the CTA of the 8
+    # remainder rows, which walks every KV tile like a full one), 1.18 -> 1.04 (cfg3's prefill, 2 ranks)
+    assert max(paired) / (sum(paired) / world) < max(contiguous) / (sum(contiguous) / world) - 0.1
+    tail_owner = [r for r in range(world) if any(b == n for _, b in eng.shard_ranges(0, n, r, world))]
+    tail_owner_flipped = [r for r in range(world) if any(b == n for _, b in eng.shard_ranges(0, n, r, world, flip=True))]
+    assert tail_owner == [0] and tail_owner_flipped == [world - 1]
+
+
+@pytest.mark.parametrize("geom", [(4, 4, 256, 256), (3, 2, 64, 96), (1, 1, 64, 64)])
+def test_sequence_partition_gives_every_rank_whole_sequences(geom):
+    """partition="sequences" with two ranks = one CFG branch per rank (CFG axis): rank 0 owns every
+    row of the conditional sequence (context + clip), rank 1 every row of the unconditional one; the global
+    structures (page table, key codes, latent numbering) stay those of the unsharded plan."""
+    n_ctx, n_gen, H, W = geom
+    _, specs, n_lat, n_ctx_lat = _specs(n_ctx, n_gen, H, W)
+    full = eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu")
+    parts = [eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu", shard=(r, 2), partition="sequences")
+             for r in range(2)]
+    for r, p in enumerate(parts):
+        assert p.partition == "sequences" and p.shard == (r, 2)
+        assert torch.equal(p.page_table, full.page_table) and torch.equal(p.k_code, full.k_code)
+        assert torch.equal(p.lat_row0, full.lat_row0) and p.n_latents == full.n_latents
+        for which in ("prefix", "step"):
+            f, x = getattr(full, which), getattr(p, which)
+            for s_ in range(2):
+                q0, n = int(f.seqs[s_, 0]), int(f.seqs[s_, 1])
+                assert int(x.seqs[s_, 1]) == (n if s_ == r else 0) and int(x.seqs[s_, 2]) == int(f.seqs[s_, 2])
+            q0, n = int(f.seqs[r, 0]), int(f.seqs[r, 1])
+            assert x.rows == n
+            for name in ("row_pos", "row_slot", "q_code", "kind", "arg_a", "arg_b"):
+                assert torch.equal(getattr(x, name), getattr(f, name)[q0:q0 + n]), (which, name)
+    assert full.partition == "rows"
+    with pytest.raises(ValueError, match="whole sequences"):
+        eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu", shard=(0, 4), partition="sequences")
+    with pytest.raises(ValueError, match="unknown partition"):
+        eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, "cpu", shard=(0, 2), partition="heads")
+    assert [eng.sequence_owner(s_, 8, 2) for s_ in range(8)] == [0] * 4 + [1] * 4      # batch: cond rows, then uncond rows
 
 
 def test_shard_rows_covers_range():
@@ -65,6 +128,15 @@ def test_shard_rows_covers_range():
         chunks = [eng.shard_rows(lo, hi, r, w) for r in range(w)]
         assert chunks[0][0] == lo and chunks[-1][1] == hi
         assert all(chunks[i][1] == chunks[i + 1][0] for i in range(w - 1))
+    for lo, hi, w in ((0, 4104, 2), (0, 4104, 8), (1032, 2064, 2), (258, 8514, 8), (0, 1032, 8), (5, 7, 4), (0, 0, 2), (0, 520, 2)):
+        for flip in (False, True):
+            per_rank = [eng.shard_ranges(lo, hi, r, w, flip) for r in range(w)]
+            cover = sorted(x for rs in per_rank for x in rs)
+            assert all(b > a for a, b in cover) and all(rs == sorted(rs) and len(rs) <= 2 for rs in per_rank)
+            if hi > lo:
+                assert cover[0][0] == lo and cover[-1][1] == hi
+                assert all(cover[i][1] == cover[i + 1][0] for i in range(len(cover) - 1))     # disjoint, complete
+            assert per_rank == [eng.shard_ranges(lo, hi, w - 1 - r, w, not flip) for r in range(w)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -80,10 +152,12 @@ WIDE = synth.BackboneDims(num_hidden_layers=2)       # full width (32 heads x 96
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,geom,dims", [(2, (3, 2, 64, 96), synth.REDUCED), (3, (2, 2, 64, 64), synth.REDUCED),
-                                             (4, (4, 4, 128, 128), synth.REDUCED), (2, (4, 4, 256, 256), WIDE),
-                                             (3, (4, 4, 256, 256), WIDE), (8, (2, 2, 128, 256), WIDE)])
-def test_virtual_ranks_match_unsharded_engine_bit_exact(world, geom, dims):
+@pytest.mark.parametrize("world,geom,dims,partition", [
+    (2, (3, 2, 64, 96), synth.REDUCED, "rows"), (3, (2, 2, 64, 64), synth.REDUCED, "rows"),
+    (4, (4, 4, 128, 128), synth.REDUCED, "rows"), (2, (4, 4, 256, 256), WIDE, "rows"),
+    (3, (4, 4, 256, 256), WIDE, "rows"), (8, (2, 2, 128, 256), WIDE, "rows"),
+    (2, (3, 2, 64, 96), synth.REDUCED, "sequences"), (2, (4, 4, 256, 256), WIDE, "sequences")])
+def test_virtual_ranks_match_unsharded_engine_bit_exact(world, geom, dims, partition):
     from videogpt_b200 import ops, peer
     dev, bf = torch.device("cuda", 0), torch.bfloat16
     n_ctx, n_gen, H, W = geom
@@ -100,11 +174,17 @@ def test_virtual_ranks_match_unsharded_engine_bit_exact(world, geom, dims):
     members = peer.LocalPeerGroup.create(world, dev)
     ranks = [_engine(w, dims, dev, peers=m) for m in members]
     for r, e in enumerate(ranks):
-        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev, shard=(r, world)))
+        e.set_plan(eng.build_plan(specs, n_lat, n_ctx_lat, H // 8, W // 8, dev, shard=(r, world), partition=partition))
     eng.run_lockstep([e.prefill_steps(ctx) for e in ranks])
     torch.cuda.synchronize()
-    for e in ranks:                                   # every rank ends up with ALL context K/V
-        assert torch.equal(e.kv, ref.kv)
+
+    def kv_as_expected(e, r):
+        if partition == "rows":                       # every rank ends up with ALL K/V
+            return torch.equal(e.kv, ref.kv)
+        mine = ref.plan.page_table[r, :(specs[r].n_prefix + specs[r].n_active + 127) // 128].long()
+        return torch.equal(e.kv[:, :, mine], ref.kv[:, :, mine])    # whole sequences: its own sequence's pages
+
+    assert all(kv_as_expected(e, r) for r, e in enumerate(ranks))
     ref.z.copy_(z0)
     for e in ranks:
         e.z.copy_(z0)
@@ -114,9 +194,9 @@ def test_virtual_ranks_match_unsharded_engine_bit_exact(world, geom, dims):
         ref.predict()
         eng.run_lockstep([e.predict_steps() for e in ranks])
         torch.cuda.synchronize()
-        for e in ranks:
+        for r, e in enumerate(ranks):
             assert torch.equal(e.pred, ref.pred), f"step {step}: prediction differs"
-            assert torch.equal(e.kv, ref.kv)
+            assert kv_as_expected(e, r)
         for e in [ref] + ranks:
             ops.cfg_euler(e.z, e.pred, True, True, 1.0 - t, 0.3, 1.5)
     assert all(torch.equal(e.z, ref.z) for e in ranks)
@@ -131,7 +211,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ret, geom=(3, 2, 64, 96), fresh_context=False):
+def _worker(rank, world, port, ret, geom=(3, 2, 64, 96), fresh_context=False, partition="rows"):
     import torch.distributed as dist
     from transformers import Phi3Config
     from videogpt_b200 import LVM, LVMScheduler, parallel_states as ps
@@ -159,7 +239,7 @@ def _worker(rank, world, port, ret, geom=(3, 2, 64, 96), fresh_context=False):
         single_model = model()
         single = {pt: LVMScheduler(steps)([x.clone() for x in lat[n_ctx:]] * 2, single_model.frame_block_forward_with_cfg,
                                           mk, prediction_type=pt) for pt in ("x1", "v")}
-        ps.initialize_sequence_parallel_state(world)          # the reference's SP switch
+        ps.initialize_sequence_parallel_state(world, partition=partition)     # the reference's SP switch
         sp_model = model()
         out = {}
         for pt in ("x1", "v"):
@@ -171,13 +251,22 @@ def _worker(rank, world, port, ret, geom=(3, 2, 64, 96), fresh_context=False):
                 torch.cuda.synchronize()
                 out[f"{pt}{rep}"] = all(torch.equal(a, b) for a, b in zip(got, single[pt]))
         sp_model.engine().peers.check()
-        out["sharded"] = sp_model.engine().plan.shard == (rank, world)
+        plan = sp_model.engine().plan
+        out["sharded"] = plan.shard == (rank, world) and plan.partition == partition
+        if partition == "sequences":      # one CFG branch per rank: all rows of its own sequence, none of the other
+            out["sharded"] &= plan.step.rows == specs_rows(d)[rank]
         ret[rank] = out
         dist.barrier()
         sp_model.engine().peers.close()
     finally:
         ps.destroy_sequence_parallel_group()
         dist.destroy_process_group()
+
+
+def specs_rows(d):
+    specs, _, _ = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
+                                        d["denoise_image_sizes"], d["time_emb_inx"])
+    return [sp.n_active for sp in specs]
 
 
 def _spawn_with_deadline(args, nprocs, seconds):
@@ -206,5 +295,21 @@ def test_sequence_parallel_two_gpus_matches_single_gpu(geom, fresh):
     mgr = mp.Manager()
     ret = mgr.dict()
     _spawn_with_deadline((2, _free_port(), ret, geom, fresh), 2, 240)
+    want = {"x10": True, "x11": True, "v0": True, "v1": True, "sharded": True}
+    assert dict(ret) == {0: want, 1: want}
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("geom,fresh", [((3, 2, 64, 96), False), ((4, 4, 128, 128), True)])
+def test_cfg_branch_pair_two_gpus_matches_single_gpu(geom, fresh):
+    """One CFG branch per GPU (``initialize_sequence_parallel_state(2, partition="sequences")``): rank 0 runs the
+    conditional sequence, rank 1 the unconditional one, each stores its half of the prediction into both ranks'
+    buffers over NVLink and both apply the same update inside the step graph -- bit for bit the single-GPU latents,
+    x1 and v, first clip and a second one on the kept plan and graph."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    _spawn_with_deadline((2, _free_port(), ret, geom, fresh, "sequences"), 2, 240)
     want = {"x10": True, "x11": True, "v0": True, "v1": True, "sharded": True}
     assert dict(ret) == {0: want, 1: want}

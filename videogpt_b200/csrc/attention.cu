@@ -296,11 +296,8 @@ static int launch_attn(const void* q, int q_ld, void* out, int out_ld, const voi
                        cudaStream_t s) {
   using S = AttnSmem<D>;
   auto kern = attn_clip_causal_kernel<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  // per launch: the attribute is per device, and a process may drive several devices (cheap, capture-safe)
+  VGPT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
   dim3 grid(max_q_tiles, H, num_seqs);
   kern<<<grid, kAttnThreads, S::kTotal, s>>>(
       (const __nv_bfloat16*)q, q_ld, (__nv_bfloat16*)out, out_ld, (const __nv_bfloat16*)k_pool,

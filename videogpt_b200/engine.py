@@ -119,7 +119,8 @@ class ClipPlan:
     step: PhaseArrays
     lat_row0: torch.Tensor
     max_pos: int
-    shard: Optional[tuple] = None      # (rank, world) of a row-sharded (sequence-parallel) plan
+    shard: Optional[tuple] = None      # (rank, world) of a sharded plan (one rank of a peer group)
+    partition: str = "rows"            # what the ranks of a sharded plan own: "rows" | "sequences"
 
 
 def frame_block_specs(input_ids, position_ids, input_image_sizes, denoise_image_sizes, time_emb_inx):
@@ -236,18 +237,16 @@ def codes_dense_mask(spec_codes: np.ndarray, pad: int) -> np.ndarray:
     return qc[:, None] >= kc[None, :]
 
 
-SHARD_ALIGN = 128      # attention query tile; GEMM tiles are 256 rows (pairs of 128)
+SHARD_ALIGN = 128      # attention query tile; GEMM tiles and attention CTAs are 256 rows (pairs of 128)
 
 
 def shard_rows(lo: int, hi: int, rank: int, world: int):
-    """Rows [lo, hi) dealt to ``world`` ranks as contiguous chunks, like the reference's
+    """Rows [lo, hi) dealt to ``world`` ranks as ONE contiguous chunk each, like the reference's
     ``input_emb[:, r*L/P:(r+1)*L/P]`` (``LVM/model.py:459-464``) but without its divisibility
-    requirement: every row-wise op is independent of the partition and attention sees all keys, so any
-    partition gives the same numbers.  When every rank gets at least one 128-row tile the chunk
-    boundaries are rounded down to multiples of 128 rows (the last rank takes the remainder): a shard
-    then starts on a tile boundary of the attention kernel (a 129-row shard would cost a second, almost
-    empty query tile on EVERY rank instead of on one) and the remainder rows meet the GEMM as one tail
-    (``gemm_pair_tcgen05.cu``: tail rows in the k-loop).  Otherwise sizes differ by at most one."""
+    requirement.  When every rank gets at least one 128-row tile the chunk boundaries are rounded down
+    to multiples of 128 rows (the last rank takes the remainder): a shard then starts on a tile boundary
+    of the attention kernel and the remainder rows meet the GEMM as one tail.  Otherwise sizes differ
+    by at most one.  (``shard_ranges`` falls back to this for short ranges.)"""
     n = hi - lo
     if n >= SHARD_ALIGN * world:
         cut = lambda r: n if r >= world else (n * r // world) // SHARD_ALIGN * SHARD_ALIGN
@@ -256,12 +255,50 @@ def shard_rows(lo: int, hi: int, rank: int, world: int):
     return lo + cut(rank), lo + cut(rank + 1)
 
 
+def shard_ranges(lo: int, hi: int, rank: int, world: int, flip: bool = False):
+    """Rows [lo, hi) of one sequence dealt to ``world`` ranks, balanced for the CAUSAL attention cost: every
+    row-wise op is independent of the partition and attention sees all keys through the token codes, so a rank may
+    own ANY subset of the rows and gets the same numbers (tests/test_sequence_parallel.py, bit for bit).
+
+    Later rows see more keys (a generated frame sees the context and every earlier generated frame), so with one
+    contiguous chunk per rank the last rank's attention launch walks up to 1.6x the KV tiles of the first rank's and
+    everybody waits for it at every layer's barrier.  Here the range is cut into ``2 * world`` chunks on 256-row
+    boundaries (one attention CTA = one GEMM tile row; 128 when the range is too short for that) and rank r takes
+    chunk r and chunk ``2 * world - 1 - r`` -- the cheapest with the dearest.  The remainder rows (a frame is 258 or
+    1026 tokens: 8 rows at the end of every sequence) cost their owner an attention CTA of its own that walks every
+    KV tile; ``flip`` (odd sequences) mirrors the deal, so the conditional sequence's remainder lands on rank 0 and
+    the unconditional one's on the last rank instead of both on the same.  Returns ascending (start, end) ranges."""
+    n = hi - lo
+    unit = next((u for u in (2 * SHARD_ALIGN, SHARD_ALIGN) if n >= u * 2 * world), 0)
+    r = world - 1 - rank if flip else rank
+    if not unit:
+        a, b = shard_rows(lo, hi, r, world)
+        return [(a, b)] if b > a else []
+    cut = lambda i: n if i >= 2 * world else (n * i // (2 * world)) // unit * unit
+    first, second = (cut(r), cut(r + 1)), (cut(2 * world - 1 - r), cut(2 * world - r))
+    if first[1] == second[0]:                  # the two middle chunks are neighbours
+        return [(lo + first[0], lo + second[1])]
+    return [(lo + a, lo + b) for a, b in (first, second) if b > a]
+
+
+def sequence_owner(s: int, n_seqs: int, world: int) -> int:
+    """Rank that owns sequence ``s`` of ``n_seqs`` under ``partition="sequences"``: contiguous blocks, so with the
+    reference's batch order ``[conditional rows | unconditional rows]`` (``LVM/pipeline.py:441-448``) and two ranks,
+    rank 0 runs every conditional sequence (context + clip) and rank 1 every unconditional one -- the CFG-branch
+    axis of SURVEY.md 8(e)."""
+    if n_seqs % world:
+        raise ValueError(f"{n_seqs} sequences cannot be dealt to {world} ranks as whole sequences")
+    return s * world // n_seqs
+
+
 def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int, lat_h: int,
                lat_w: int, device, shard: Optional[tuple] = None, max_pages: Optional[int] = None,
-               pool_pages: Optional[int] = None) -> ClipPlan:
-    """``shard=(rank, world)``: row-sharded plan of one rank of a sequence-parallel group -- the
-    page table, key codes and tile classification describe the WHOLE sequences (every rank holds
-    all K/V), the per-phase row arrays only this rank's chunk of every sequence.
+               pool_pages: Optional[int] = None, partition: str = "rows") -> ClipPlan:
+    """``shard=(rank, world)``: plan of one rank of a peer group.  ``partition="rows"`` (sequence
+    parallelism): the page table, key codes and tile classification describe the WHOLE sequences
+    (every rank holds all K/V), the per-phase row arrays only this rank's chunk of every sequence.
+    ``partition="sequences"`` (CFG branches on rank pairs): a rank owns whole sequences
+    (``sequence_owner``) and no rows of the others; K/V never travel, only the prediction does.
 
     ``max_pages`` / ``pool_pages``: fixed capacities of the page table (logical pages per
     sequence) and of the pool, for plans that are refreshed in place round after round
@@ -272,6 +309,10 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
         s_rank, s_world = shard
         if not (0 <= s_rank < s_world):
             raise ValueError(f"bad shard {shard}")
+        if partition not in ("rows", "sequences"):
+            raise ValueError(f"unknown partition {partition!r}")
+        if partition == "sequences":
+            sequence_owner(0, S, s_world)          # raises when whole sequences cannot be dealt evenly
     for sp in specs:
         T = sp.n_prefix + sp.n_active
         assert all(len(a) == T for a in (sp.positions, sp.codes, sp.kinds, sp.arg_a, sp.arg_b))
@@ -330,13 +371,16 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
         for s, sp in enumerate(specs):
             lo, hi = (sp.n_cached, sp.n_prefix) if which == "prefix" else (sp.n_prefix, sp.n_prefix + sp.n_active)
             kv_len = hi                        # every key up to the end of this phase's rows
-            if shard is not None:
-                lo, hi = shard_rows(lo, hi, s_rank, s_world)
-            n = hi - lo
-            logical = np.arange(lo, hi)
-            pos.append(sp.positions[lo:hi])
+            ranges = [(lo, hi)]
+            if shard is not None and partition == "rows":
+                ranges = shard_ranges(lo, hi, s_rank, s_world, flip=bool(s & 1))
+            elif shard is not None and sequence_owner(s, S, s_world) != s_rank:
+                ranges = []                        # somebody else's sequence: present (page table, codes), no rows here
+            logical = np.concatenate([np.arange(a, b) for a, b in ranges] + [np.zeros(0, np.int64)]).astype(np.int64)
+            n = len(logical)
+            pos.append(sp.positions[logical])
             slot.append(page_table[s, logical // PAGE_TOKENS] * PAGE_TOKENS + logical % PAGE_TOKENS)
-            qc.append(sp.codes[lo:hi]); kd.append(sp.kinds[lo:hi]); aa.append(sp.arg_a[lo:hi]); ab.append(sp.arg_b[lo:hi])
+            qc.append(sp.codes[logical]); kd.append(sp.kinds[logical]); aa.append(sp.arg_a[logical]); ab.append(sp.arg_b[logical])
             seqs.append([row0, n, kv_len, 0])
             row0 += n
             max_q = max(max_q, n)
@@ -358,7 +402,7 @@ def build_plan(specs: Sequence[SequenceSpec], n_latents: int, n_ctx_latents: int
                     k_code=torch.from_numpy(k_code).to(device),
                     k_tile_minmax=torch.from_numpy(minmax).to(device), total_pages=base,
                     prefix=prefix, step=step, lat_row0=torch.from_numpy(lat_row0).to(device),
-                    max_pos=max_pos, shard=shard)
+                    max_pos=max_pos, shard=shard, partition=partition if shard is not None else "rows")
 
 
 # --------------------------------------------------------------------------------------------
@@ -548,17 +592,19 @@ class NextClipEngine:
         n, plan = ph.rows, self.plan
         hidden, xn, qkv, attn, mlp_h = (self.hidden[:n], self.xn[:n], self.qkv[:n], self.attn[:n], self.mlp_h[:n])
         scale = 1.0 / math.sqrt(self.D)
+        # K/V travel only when ranks share sequences; a rank that owns whole sequences keeps its K/V to itself
+        share_kv = self.peers is not None and plan.partition == "rows"
         for li, lw in enumerate(self.w.layers):
             if n:
                 ops.rmsnorm(hidden, lw["ln1"], self.eps, out=xn)
                 ops.gemm(xn, lw["qkv"], out=qkv)
-                if self.peers is None:
+                if not share_kv:
                     ops.rope_kv_append(qkv, ph.row_pos, ph.row_slot, self._rope_tab, self.kv[li, 0], self.kv[li, 1],
                                        self.H, self.D)
                 else:                 # RoPE + K/V append + all-gather: stores into every rank's pool
                     ops.rope_kv_append_peers(qkv, ph.row_pos, ph.row_slot, self._rope_tab, self._kv_ptrs[li][0],
                                              self._kv_ptrs[li][1], self.peers.world, self.H, self.D)
-            if self.peers is not None:
+            if share_kv:
                 yield "kv"
             if kv_only_last and li == self.L - 1:
                 break                     # prefix rows: nothing after the last K/V append is read
@@ -601,27 +647,34 @@ class NextClipEngine:
     def _predict_kernels(self):
         plan = self.plan
         st = plan.step
+        if self.peers is not None and plan.partition == "sequences":
+            # The only other barrier of such a step is the one after the prediction stores, and a peer's stores of
+            # step i+1 must not land in this rank's `pred` before its update of step i has read it.  (Row-sharded
+            # steps have a barrier per layer in between.)
+            yield "start"
         self._time_embeddings(plan.n_latents)
         if st.rows:
             self._assemble(st)
         yield from self._layers(st, kv_only_last=False)
         # llm.norm + FinalLayer + unpatchify (+ the scheduler update in the fused loop): one kernel on the raw residual stream
+        n_half = plan.n_latents // 2 if self.euler_mode is not None and self.euler_mode[0] else plan.n_latents
         if self.peers is None:
             euler = None
             if self.euler_mode is not None:
                 use_cfg, x1_mode = self.euler_mode
-                n_half = plan.n_latents // 2 if use_cfg else plan.n_latents
                 euler = (self.z, self.scalars, use_cfg, x1_mode, self.vel[:n_half])
             ops.final_layer(self.hidden[:st.rows], plan.lat_row0, self.mod[:plan.n_latents], self.w.final_w,
                             self.w.final_b, self.pred, norm_weight=self.w.norm, rms_eps=self.eps, euler=euler)
         else:                             # prediction stored into every rank's pred buffer
-            if self.euler_mode is not None:
-                raise RuntimeError("the fused scheduler update is single-GPU only: sequence-parallel ranks apply vgpt_cfg_euler")
             if st.rows:
                 ops.final_layer_rows(self.hidden[:st.rows], st.kind, st.arg_a, st.arg_b, self.mod[:plan.n_latents],
                                      self.w.final_w, self.w.final_b, self._pred_ptrs, self.peers.world,
                                      plan.lat_h, plan.lat_w, norm_weight=self.w.norm, rms_eps=self.eps)
             yield "pred"
+            if self.euler_mode is not None:
+                # every rank applies the same update to its full copy of the latents (64 KB): latents never travel
+                use_cfg, x1_mode = self.euler_mode
+                ops.cfg_euler(self.z, self.pred, use_cfg, x1_mode, scalars_dev=self.scalars, vel_out=self.vel[:n_half])
 
     def predict_steps(self):
         """Generator form of ``predict`` without CUDA-graph capture (lockstep execution)."""
@@ -664,7 +717,9 @@ class NextClipEngine:
     def launches_per_predict(self) -> int:
         """Kernels of this library per predict() (torch's two replicate copies under uniform_t are
         not counted)."""
-        sync = (self.L + 1) if self.peers is not None and not self.peers.lockstep else 0
+        sync = 0
+        if self.peers is not None and not self.peers.lockstep:
+            sync = 2 if self.plan is not None and self.plan.partition == "sequences" else self.L + 1
         return 6 + 1 + 8 * self.L + 1 + sync
 
     @property

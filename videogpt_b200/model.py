@@ -346,7 +346,9 @@ class LVM(nn.Module):
         """Peer group of this rank when ``initialize_sequence_parallel_state(P > 1)`` ran (the
         reference's switch for sequence parallelism, ``LVM/model.py:459``): the ranks of
         ``hccl_info.group`` then share every video -- each computes a contiguous chunk of the rows
-        of every sequence and stores its K/V and predictions into all peers (``peer.py``)."""
+        of every sequence and stores its K/V and predictions into all peers (``peer.py``); or, with
+        ``hccl_info.partition == "sequences"``, whole sequences (one CFG branch per rank of a pair)
+        and only the predictions travel."""
         if hccl_info.world_size in (0, 1, None):
             return None
         if self._peers is None:
@@ -364,8 +366,11 @@ class LVM(nn.Module):
         self._plan_key = self._layout_key = self._plan_refs = None
 
     def _shard(self):
+        """``shard=`` / ``partition=`` of ``engine.build_plan`` for this rank (nothing on a single GPU)."""
         e = self._engine
-        return None if e is None or e.peers is None else (e.peers.rank, e.peers.world)
+        if e is None or e.peers is None:
+            return {}
+        return dict(shard=(e.peers.rank, e.peers.world), partition=getattr(hccl_info, "partition", "rows"))
 
     @staticmethod
     def _identity(*objs):
@@ -402,7 +407,8 @@ class LVM(nn.Module):
             return e
         ids_host, pos_host = input_ids.cpu(), position_ids.cpu()
         layout = (ids_host.numpy().tobytes(), pos_host.numpy().tobytes(), tuple(ids_host.shape),
-                  self._identity(input_image_sizes, denoise_image_sizes, time_emb_inx), lat_h, lat_w)
+                  self._identity(input_image_sizes, denoise_image_sizes, time_emb_inx), lat_h, lat_w,
+                  hccl_info.partition)
         n_ctx = sum(len(v) for v in input_image_sizes.values())
         if n_ctx != len(input_img_latents or []):
             raise AssertionError("number of context latents does not match input_image_sizes")   # model.py:454
@@ -411,7 +417,7 @@ class LVM(nn.Module):
                                                        denoise_image_sizes, time_emb_inx)
             if check_mask and attention_mask is not None:
                 self._check_mask(attention_mask, specs, e.device)
-            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device, shard=self._shard()))
+            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device, **self._shard()))
             self._layout_key = layout
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)
@@ -486,7 +492,7 @@ class LVM(nn.Module):
             return e
         ids_host, pos_host = input_ids.cpu(), position_ids.cpu()
         layout = ("single", ids_host.numpy().tobytes(), pos_host.numpy().tobytes(), tuple(ids_host.shape),
-                  self._identity(input_image_sizes), lat_h, lat_w)
+                  self._identity(input_image_sizes), lat_h, lat_w, hccl_info.partition)
         n_tok = (lat_h // self.patch_size) * (lat_w // self.patch_size)
         n_ctx = sum(len(v) for v in input_image_sizes.values())
         assert n_ctx == len(input_img_latents or [])                                   # model.py:358
@@ -498,7 +504,7 @@ class LVM(nn.Module):
             specs, n_lat, n_ctx = eng.single_frame_specs(ids_host, pos_host, input_image_sizes, n_tok)
             if check_mask and attention_mask is not None:
                 self._check_mask(attention_mask, specs, e.device)
-            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device, shard=self._shard()))
+            e.set_plan(eng.build_plan(specs, n_lat, n_ctx, lat_h, lat_w, e.device, **self._shard()))
             self._layout_key = layout
         ctx = torch.cat([x.reshape(1, 4, lat_h, lat_w) for x in input_img_latents], 0) if n_ctx else None
         e.prefill(ctx)

@@ -23,20 +23,33 @@ class COMM_INFO:
         # all (an NCCL barrier is an all-reduce kernel that has to share the GPUs with spinning
         # vgpt_peer_barrier kernels, and NCCL's own set-up may block in the driver)
         self.host_group = None
+        # what the ranks of the group own (engine.build_plan): "rows" = a chunk of the rows of every sequence, the
+        # reference's sequence parallelism (LVM/model.py:459-464); "sequences" = whole sequences -- with two ranks,
+        # one CFG branch each (CFG axis): K/V stay local, only the prediction is exchanged
+        self.partition = "rows"
 
 
 hccl_info = COMM_INFO()
 _SEQUENCE_PARALLEL_STATE = False
 
 
-def initialize_sequence_parallel_state(sequence_parallel_size: int):
-    """parallel_states.py:24-37."""
+def initialize_sequence_parallel_state(sequence_parallel_size: int, partition: str = "rows"):
+    """parallel_states.py:24-37.  ``partition`` (not in the reference): see ``COMM_INFO.partition``."""
     global _SEQUENCE_PARALLEL_STATE
+    if partition not in ("rows", "sequences"):
+        raise ValueError(f"unknown partition {partition!r}")
+    hccl_info.partition = partition
     if sequence_parallel_size > 1:
         _SEQUENCE_PARALLEL_STATE = True
         initialize_sequence_parallel_group(sequence_parallel_size)
     else:
         hccl_info.group, hccl_info.world_size, hccl_info.rank, hccl_info.host_group = None, 1, 0, None
+
+
+def initialize_cfg_branch_parallel_state():
+    """Pairs of ranks share a video, one CFG branch each: rank 0 of a pair runs the conditional sequences (context +
+    clip), rank 1 the unconditional ones (clip only, RoPE restarting at 0: quirk q9, so K/V are never shareable)."""
+    initialize_sequence_parallel_state(2, partition="sequences")
 
 
 def get_sequence_parallel_state() -> bool:
@@ -62,6 +75,7 @@ def initialize_sequence_parallel_group(sequence_parallel_size: int):
 def destroy_sequence_parallel_group():
     global _SEQUENCE_PARALLEL_STATE
     hccl_info.group, hccl_info.world_size, hccl_info.rank, hccl_info.host_group = None, 0, -1, None
+    hccl_info.partition = "rows"
     _SEQUENCE_PARALLEL_STATE = False
 
 

@@ -9,7 +9,6 @@ applies the update with the CUDA kernel.  CPU tensors are rejected: there is no 
 """
 from __future__ import annotations
 
-import gc
 from typing import Callable, Optional
 
 import torch
@@ -43,7 +42,11 @@ class LVMScheduler:
             out = self._run_engine(z, model, model_kwargs, prediction_type)
         else:
             out = self._run_generic(z, func, model_kwargs, prediction_type)
-        gc.collect()
+        # (The reference ends with `del cache; torch.cuda.empty_cache(); gc.collect()` -- scheduler.py:205-207 -- to
+        # drop the throw-away DynamicCache of quirk q14.  There is no such garbage here, and a full collection costs
+        # ~90 ms of host time in a process that holds torch + transformers: hidden behind queued GPU work on one GPU,
+        # but fully exposed in a peer group, whose ranks synchronise with their GPUs at every clip boundary --
+        # 0.599 instead of 0.53 s/clip for a CFG-branch pair at cfg2, tools/gpu/r02s.sh.)
         return out
 
     # ---- engine loop -----------------------------------------------------------------------------
@@ -73,22 +76,22 @@ class LVMScheduler:
         # (the scalars exactly as the reference forms them); one device-to-device copy per step selects row i
         rows = [[float(self.sigma[i])] * n + list(self._scalars(i)) + [guidance] for i in range(self.num_steps)]
         table = torch.tensor(rows, dtype=torch.float32).to(e.step_inputs.device, non_blocking=True)
-        fused = e.peers is None          # single GPU: the update rides in the final-layer kernel of the step graph
         e.uniform_t = True               # one sigma for every latent (scheduler.py:171)
-        e.euler_mode = (use_cfg, x1) if fused else None
+        # The update is part of the step graph: inside the final-layer kernel on one GPU; in a peer group (sequence
+        # parallel, CFG-branch pairs) as vgpt_cfg_euler behind the barrier that orders the peers' prediction stores,
+        # applied by every rank to its full copy of z.
+        e.euler_mode = (use_cfg, x1)
         try:
             for i in range(self.num_steps):
                 e.step_inputs.copy_(table[i])
                 e.predict()
-                if not fused:            # sequence-parallel ranks: every rank applies the update to its full copy of z
-                    ops.cfg_euler(e.z, e.pred, use_cfg, x1, scalars_dev=e.scalars, vel_out=e.vel[:n_half])
                 if self.record_velocity is not None:
                     self.record_velocity.append(e.vel[:n_half].clone())
         finally:
             e.uniform_t = False
             e.euler_mode = None
         if e.peers is not None:
-            # sequence parallel: a barrier that timed out (a peer died or fell behind by ~10 s) lets this rank run
+            # peer group: a barrier that timed out (a peer died or fell behind by ~10 s) lets this rank run
             # on K/V and prediction rows its peers never delivered -- never return such latents as a result
             e.peers.check()
         if not is_list:
