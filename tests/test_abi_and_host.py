@@ -158,23 +158,6 @@ def test_single_frame_codes_reproduce_the_reference_mask(case):
     assert plan.step.rows == 2 * (n_tok + 1) and plan.prefix.rows == specs[0].n_prefix + 1
 
 
-def test_branch_spec_renumbers_latents_locally():
-    from videogpt_b200 import parallel
-    d = po.frame_block_inputs(3, 2, 64, 64, True, 1)
-    specs, n_lat, n_c = eng.frame_block_specs(d["input_ids"], d["position_ids"], d["input_image_sizes"],
-                                              d["denoise_image_sizes"], d["time_emb_inx"])
-    cond, n0, c0 = parallel.branch_spec(specs, 0)
-    unc, n1, c1 = parallel.branch_spec(specs, 1)
-    assert (n0, c0, n1, c1) == (2, 3, 2, 0)
-    assert [l for l, _ in cond.latent_rows] == [0, 1] and [l for l, _ in unc.latent_rows] == [0, 1]
-    noisy = unc.kinds == ops.ROW_NOISY_PATCH
-    assert set(unc.arg_a[noisy].tolist()) == {0, 1} and set(specs[1].arg_a[noisy].tolist()) == {2, 3}
-    plan = eng.build_plan([unc], n1, c1, 8, 8, "cpu")
-    assert plan.prefix.rows == 0 and plan.step.rows == 2 * 18 and plan.lat_row0[:2].tolist() == [2, 20]
-    plan = eng.build_plan([cond], n0, c0, 8, 8, "cpu")
-    assert plan.prefix.rows == 3 * 18 and plan.step.seqs.tolist() == [[0, 36, 90, 0]]
-
-
 @pytest.mark.parametrize("case", [(3, 2, 64, 64, 1), (2, 3, 64, 96, 8)])
 def test_codes_from_mask_recovers_block_causal_masks(case):
     from videogpt_b200.transform import codes_from_mask

@@ -34,27 +34,6 @@ def _spawn(world, fn):
     return dict(ret)
 
 
-def _cfg_exchange(rank, world):
-    grp = parallel.CfgBranchGroup()
-    n_gen = 3
-    pred = torch.full((n_gen, 4, 2, 2), float(10 * grp.video_group + grp.branch))
-    both = grp.exchange_predictions(pred)
-    # layout consumed by vgpt_cfg_euler: cond latents first, then uncond latents
-    ok = both.shape == (2 * n_gen, 4, 2, 2) and bool((both[:n_gen] == 10 * grp.video_group).all()) \
-        and bool((both[n_gen:] == 10 * grp.video_group + 1).all())
-    return ok, grp.video_group, grp.branch, grp.select_branch(["cond", "uncond"])
-
-
-def test_cfg_branch_exchange_world2():
-    out = _spawn(2, _cfg_exchange)
-    assert out[0] == (True, 0, 0, "cond") and out[1] == (True, 0, 1, "uncond")
-
-
-def test_cfg_branch_exchange_world4_two_videos():
-    out = _spawn(4, _cfg_exchange)
-    assert [out[r][1:3] for r in range(4)] == [(0, 0), (0, 1), (1, 0), (1, 1)] and all(out[r][0] for r in range(4))
-
-
 def _dp(rank, world):
     mine = parallel.shard_videos(7, rank, world)
     t = parallel.max_over_ranks(1.0 + rank)
@@ -178,6 +157,26 @@ def test_peer_groups_of_two_in_world4():
     assert [out[r][1] for r in range(4)] == [0, 1, 0, 1] and all(out[r][2] for r in range(4))
 
 
+def _cfg_pairs(rank, world):
+    from videogpt_b200 import parallel_states as ps
+    os.environ["RANK"], os.environ["WORLD_SIZE"] = str(rank), str(world)
+    ps.initialize_cfg_branch_parallel_state()           # pairs of ranks, one CFG branch each
+    try:
+        ranks = dist.get_process_group_ranks(ps.hccl_info.group)
+        return ranks, (ranks[0] // 2, ps.hccl_info.rank), ps.hccl_info.partition, ps.hccl_info.world_size
+    finally:
+        ps.destroy_sequence_parallel_group()
+        assert ps.hccl_info.partition == "rows"
+
+
+def test_cfg_branch_pairs_in_world4():
+    """Ranks (2g, 2g+1) serve video group g, branch = rank inside the pair (``parallel.cfg_pair_layout``)."""
+    out = _spawn(4, _cfg_pairs)
+    assert [out[r][0] for r in range(4)] == [[0, 1], [0, 1], [2, 3], [2, 3]]
+    assert [out[r][1] for r in range(4)] == [parallel.cfg_pair_layout(r, 4) for r in range(4)]
+    assert all(out[r][2:] == ("sequences", 2) for r in range(4))
+
+
 # ------------------------------------------------------------------------------------------------
 # The whole sequence-parallel HOST flow on CPU: LVM + LVMScheduler under
 # initialize_sequence_parallel_state(2), kernels stubbed, peer memory faked, but the host
@@ -264,74 +263,3 @@ def test_cfg_branch_pair_host_flow_world2():
     assert out[0][0] == out[1][0] == [2 * 2] * 3
     assert out[0][1] == (0, 2) and out[1][1] == (1, 2) and out[0][4] == out[1][4] == "sequences"
     assert out[0][2] == (3 * 26, 2 * 26) and out[1][2] == (0, 2 * 26)
-
-
-# ---- CFG-branch pairs, numerically: two gloo ranks, kernel wrappers emulated on CPU (fp32) --------
-def _cfg_split_numeric(rank, world):
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    import emu_ops
-    from transformers import Phi3Config
-    from oracle import model_oracle as mo, processor_oracle as po, scheduler_oracle as so
-    from videogpt_b200 import LVM, LVMScheduler, engine, model as model_mod, scheduler as sched_mod, synth
-    torch.set_num_threads(2)
-    for mod in (engine, model_mod, sched_mod):
-        mod.ops = emu_ops
-    engine.ACT_DTYPE = torch.float32
-    torch.cuda.is_available = lambda: True
-    dims = synth.REDUCED
-    sd = synth.init_state_dict(dims, seed=0)
-    m = LVM(Phi3Config(**dims.phi3_kwargs()), device="cpu")
-    m.load_state_dict(sd)
-    m.float().eval()
-
-    def engine_cpu(self):
-        if self._engine is None:
-            d = self.dims()
-            w = engine.EngineWeights(self.state_dict(), d.num_hidden_layers, "cpu")
-            self._engine = engine.NextClipEngine(w, d.hidden_size, d.intermediate_size, d.num_hidden_layers,
-                                                 d.num_attention_heads, d.rms_norm_eps, d.rope_theta, "cpu",
-                                                 use_cuda_graph=False)
-        return self._engine
-    LVM.engine = engine_cpu
-    # the split path calls ops through `from . import ops` inside the function: patch the package attribute too
-    import videogpt_b200
-    videogpt_b200.ops = emu_ops
-    sys.modules["videogpt_b200.ops"] = emu_ops
-
-    n_ctx, n_gen, H, W, steps = 3, 2, 64, 96, 3
-    d = po.frame_block_inputs(n_ctx, n_gen, H, W, True, 1)
-    lat = synth.synthetic_latents(n_ctx + n_gen, H, W, seed=42)
-    mk = dict(input_ids=d["input_ids"], input_img_latents=lat[:n_ctx], input_image_sizes=d["input_image_sizes"],
-              attention_mask=d["attention_mask"], position_ids=d["position_ids"],
-              denoise_image_sizes=d["denoise_image_sizes"], time_emb_inx=d["time_emb_inx"], img_cfg_scale=1.5,
-              use_img_cfg=True)
-    grp = parallel.CfgBranchGroup()
-    errs = {}
-    for pt in ("x1", "v"):
-        got = parallel.sample_cfg_split(m, LVMScheduler(steps), [x.clone() for x in lat[n_ctx:]] * 2, mk, grp, pt)
-        cfg = mo.OracleConfig(hidden_size=dims.hidden_size, intermediate_size=dims.intermediate_size,
-                              num_hidden_layers=dims.num_hidden_layers, num_attention_heads=dims.num_attention_heads)
-        w = {k: v.float() for k, v in sd.items()}
-        with torch.no_grad():
-            want = so.euler_sample([x.clone() for x in lat[n_ctx:]] * 2,
-                                   lambda z, t, **kw: mo.frame_block_forward_with_cfg(w, cfg, z, t, **kw),
-                                   mk, num_steps=steps, prediction_type=pt)[:n_gen]
-        a, b = torch.cat(got), torch.cat(want)
-        errs[pt] = float((a - b).abs().max() / b.abs().max())
-    return grp.branch, e_rows(m), errs
-
-
-def e_rows(m):
-    return int(m._engine.plan.step.rows)
-
-
-def test_cfg_branch_split_reproduces_the_oracle_numerically_world2():
-    """Rank 0 runs the conditional sequence (context + clip), rank 1 the unconditional one (clip only,
-    latents renumbered by ``branch_spec``); one all-gather of the raw prediction per Euler step; both
-    ranks must end on the oracle's latents (fp32, kernel wrappers emulated: tests/emu_ops.py)."""
-    out = _spawn(2, _cfg_split_numeric)
-    assert out[0][0] == 0 and out[1][0] == 1
-    assert out[0][1] == out[1][1] == 2 * (64 * 96 // 256 + 2)         # each rank: only its own branch's rows
-    for r in (0, 1):
-        assert all(v < 5e-5 for v in out[r][2].values()), out[r][2]
