@@ -65,31 +65,42 @@ def test_sharded_plans_partition_the_unsharded_plan(world, geom):
                 assert max(sizes) - min(sizes) <= (1 if sum(sizes) < eng.SHARD_ALIGN * world else 2 * eng.SHARD_ALIGN - 1)
 
 
-def _attention_tiles(ranges, block, n_ctx_blocks):
-    """KV tiles a rank's attention CTAs walk for the given generated rows (frame-block causal)."""
+def _prefill_attention_tiles(ranges, block):
+    """KV tiles a rank's attention CTAs (256 query rows each) walk for the given CONTEXT rows: context is
+    frame-causal (`create_mask_frame_block_inference`: a context frame sees itself and the frames before it)."""
     rows = np.concatenate([np.arange(a, b) for a, b in ranges]) if ranges else np.zeros(0, int)
     total = 0
     for c0 in range(0, len(rows), 256):
         last = rows[min(c0 + 256, len(rows)) - 1]
-        total += -(-((n_ctx_blocks + last // block + 1) * block) // 128)
+        total += -(-((last // block + 1) * block) // 128)
     return total
 
 
-@pytest.mark.parametrize("world,n", [(2, 4104), (4, 4104), (8, 4104), (2, 1032), (2, 8256), (8, 8256)])
-def test_shard_ranges_balance_the_causal_attention_cost(world, n):
-    """BASELINE configs[4] / [1] geometries: with one contiguous chunk per rank the last rank walks far more KV tiles
-    than the first (its queries are the last frames); cheapest-with-dearest chunk pairs even that out, and the two
-    sequences' remainder rows (an attention CTA of their own each) land on different ranks."""
-    block, ctx = n // 4, 4
-    contiguous = [_attention_tiles([eng.shard_rows(0, n, r, world)], block, ctx) for r in range(world)]
-    paired = [_attention_tiles(eng.shard_ranges(0, n, r, world), block, ctx) for r in range(world)]
+@pytest.mark.parametrize("world,n,block", [(2, 4104, 1026), (4, 4104, 1026), (8, 4104, 1026), (2, 8256, 258), (8, 8256, 258)])
+def test_shard_ranges_balance_the_causal_attention_cost_of_the_prefill(world, n, block):
+    """Context rows of BASELINE configs[4] (4 frames of 1026 tokens) and configs[2] (32 frames of 258): with one
+    contiguous chunk per rank the last rank's prefill attention walks far more KV tiles than the first (its queries
+    are the last frames); cheapest-with-dearest chunk pairs even that out.  (The rows of the clip being denoised see
+    every key whatever their frame -- the generated clip is bidirectional -- so for them only the placement of the
+    remainder rows matters: next test.)"""
+    contiguous = [_prefill_attention_tiles([eng.shard_rows(0, n, r, world)], block) for r in range(world)]
+    paired = [_prefill_attention_tiles(eng.shard_ranges(0, n, r, world), block) for r in range(world)]
     assert sum(paired) <= sum(contiguous) + world and max(paired) < max(contiguous)
-    # slowest rank over the mean: 1.21 -> 1.07 (cfg5, 2 ranks), 1.71 -> 1.50 (8 ranks: what is left is the CTA of the 8
-    # remainder rows, which walks every KV tile like a full one), 1.18 -> 1.04 (cfg3's prefill, 2 ranks)
     assert max(paired) / (sum(paired) / world) < max(contiguous) / (sum(contiguous) / world) - 0.1
+
+
+@pytest.mark.parametrize("world,n", [(2, 4104), (8, 4104), (2, 1032), (4, 1032)])
+def test_remainder_rows_of_the_two_cfg_sequences_land_on_different_ranks(world, n):
+    """A frame is 258 or 1026 tokens, so every sequence ends in 8 rows beyond the last 128-row tile: an attention CTA
+    of their own per head (walking every KV tile) and a GEMM tail for whoever owns them.  `flip` (odd sequences)
+    mirrors the deal: the conditional sequence's remainder goes to rank 0, the unconditional one's to the last rank
+    (one contiguous chunk per rank put both on the last rank, and everybody waited for it at every layer)."""
     tail_owner = [r for r in range(world) if any(b == n for _, b in eng.shard_ranges(0, n, r, world))]
     tail_owner_flipped = [r for r in range(world) if any(b == n for _, b in eng.shard_ranges(0, n, r, world, flip=True))]
     assert tail_owner == [0] and tail_owner_flipped == [world - 1]
+    for flip in (False, True):
+        sizes = [sum(b - a for a, b in eng.shard_ranges(0, n, r, world, flip)) for r in range(world)]
+        assert sorted(x % eng.SHARD_ALIGN for x in sizes) == [0] * (world - 1) + [n % eng.SHARD_ALIGN]
 
 
 @pytest.mark.parametrize("geom", [(4, 4, 256, 256), (3, 2, 64, 96), (1, 1, 64, 64)])

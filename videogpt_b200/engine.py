@@ -256,18 +256,20 @@ def shard_rows(lo: int, hi: int, rank: int, world: int):
 
 
 def shard_ranges(lo: int, hi: int, rank: int, world: int, flip: bool = False):
-    """Rows [lo, hi) of one sequence dealt to ``world`` ranks, balanced for the CAUSAL attention cost: every
-    row-wise op is independent of the partition and attention sees all keys through the token codes, so a rank may
-    own ANY subset of the rows and gets the same numbers (tests/test_sequence_parallel.py, bit for bit).
+    """Rows [lo, hi) of one sequence dealt to ``world`` ranks, balanced for the attention cost: every row-wise op
+    is independent of the partition and attention sees all keys through the token codes, so a rank may own ANY
+    subset of the rows and gets the same numbers (tests/test_sequence_parallel.py, bit for bit).
 
-    Later rows see more keys (a generated frame sees the context and every earlier generated frame), so with one
-    contiguous chunk per rank the last rank's attention launch walks up to 1.6x the KV tiles of the first rank's and
-    everybody waits for it at every layer's barrier.  Here the range is cut into ``2 * world`` chunks on 256-row
-    boundaries (one attention CTA = one GEMM tile row; 128 when the range is too short for that) and rank r takes
-    chunk r and chunk ``2 * world - 1 - r`` -- the cheapest with the dearest.  The remainder rows (a frame is 258 or
-    1026 tokens: 8 rows at the end of every sequence) cost their owner an attention CTA of its own that walks every
-    KV tile; ``flip`` (odd sequences) mirrors the deal, so the conditional sequence's remainder lands on rank 0 and
-    the unconditional one's on the last rank instead of both on the same.  Returns ascending (start, end) ranges."""
+    Context rows are frame-causal (a context frame sees itself and the frames before it), so with one contiguous
+    chunk per rank the last rank's PREFILL attention walks up to twice the KV tiles of the average rank and everybody
+    waits for it at every layer's barrier.  Here the range is cut into ``2 * world`` chunks on 256-row boundaries
+    (one attention CTA = one GEMM tile row; 128 when the range is too short for that) and rank r takes chunk r and
+    chunk ``2 * world - 1 - r`` -- the cheapest with the dearest.  (The rows of the clip being denoised see every key
+    whatever their frame; for them the deal changes nothing but the next point.)  The remainder rows (a frame is 258
+    or 1026 tokens: 8 rows at the end of every sequence) cost their owner an attention CTA of its own per head that
+    walks every KV tile, and a GEMM tail; ``flip`` (odd sequences) mirrors the deal, so the conditional sequence's
+    remainder lands on rank 0 and the unconditional one's on the last rank instead of both on the same.  Returns
+    ascending (start, end) ranges."""
     n = hi - lo
     unit = next((u for u in (2 * SHARD_ALIGN, SHARD_ALIGN) if n >= u * 2 * world), 0)
     r = world - 1 - rank if flip else rank
