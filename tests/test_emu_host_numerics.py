@@ -413,14 +413,12 @@ def test_row_sharded_virtual_ranks_reproduce_the_unsharded_engine_and_the_oracle
         assert _maxerr([e.z], [torch.cat(want, 0)]) < 5 * TOL
 
 
-def test_cfg_branch_pair_through_model_and_scheduler_reproduces_the_oracle(emu):
-    """The user-facing flow of a CFG-branch pair: ``initialize_sequence_parallel_state(2, partition="sequences")``
-    (here: its state set by hand, two ranks as threads), then ``LVMScheduler`` on ``frame_block_forward_with_cfg``
-    as on one GPU.  Barriers per clip: none in the prefill, two per Euler step; both ranks end on the oracle's
-    latents, x1 and v, and a second clip with fresh context tensors reuses the plan."""
+def _ranks_as_threads(emu, world, partition, body):
+    """Run ``body(rank, model, counts)`` on ``world`` ranks as threads: every rank gets its own model whose engine is
+    a member of one peer group (barrier = threading.Barrier, peer buffers = every rank's buffers registered with the
+    kernel emulation), under ``hccl_info.partition = partition``.  ``counts[rank]`` counts the data-path barriers."""
     import threading
-    from videogpt_b200 import LVMScheduler, engine as eng, parallel_states as ps, peer
-    world, n_ctx, n_gen, H, W, steps = 2, 3, 2, 64, 96, 3
+    from videogpt_b200 import engine as eng, parallel_states as ps, peer
     bar, lock = threading.Barrier(world), threading.Lock()
     counts = [0] * world
 
@@ -444,8 +442,7 @@ def test_cfg_branch_pair_through_model_and_scheduler_reproduces_the_oracle(emu):
     registry = []
     members = [ThreadPeers(r, world, torch.device("cpu"), registry) for r in range(world)]
     models = [_model()[0] for _ in range(world)]
-    sd = _model()[1]
-    got, errors, rows = [dict() for _ in range(world)], [], [None] * world
+    results, errors = [None] * world, []
 
     def rank_main(r):
         try:
@@ -455,19 +452,12 @@ def test_cfg_branch_pair_through_model_and_scheduler_reproduces_the_oracle(emu):
                                            d.rms_norm_eps, d.rope_theta, "cpu", use_cuda_graph=False, peers=members[r])
             m._engine_key = tuple(p._version for p in m.parameters())
             m.engine = lambda: m._engine
-            for pt in ("x1", "v"):
-                for clip in range(2):
-                    mk, z_list = _mk(n_ctx, n_gen, H, W)
-                    before = counts[r]
-                    out = LVMScheduler(steps)([x.clone() for x in z_list] * 2, m.frame_block_forward_with_cfg, mk,
-                                              prediction_type=pt)
-                    got[r][(pt, clip)] = (out, counts[r] - before)
-            rows[r] = (m._engine.plan.partition, m._engine.plan.prefix.rows, m._engine.plan.step.rows)
-        except BaseException as exc:          # a dead rank must not leave the other waiting forever
+            results[r] = body(r, m, counts)
+        except BaseException as exc:          # a dead rank must not leave the others waiting forever
             errors.append(exc)
             bar.abort()
 
-    ps.hccl_info.partition = "sequences"
+    ps.hccl_info.partition = partition
     try:
         threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
         for t in threads:
@@ -477,8 +467,32 @@ def test_cfg_branch_pair_through_model_and_scheduler_reproduces_the_oracle(emu):
     finally:
         ps.hccl_info.partition = "rows"
     assert not errors, errors
+    return results
+
+
+def test_cfg_branch_pair_through_model_and_scheduler_reproduces_the_oracle(emu):
+    """The user-facing flow of a CFG-branch pair: ``initialize_sequence_parallel_state(2, partition="sequences")``
+    (here: its state set by hand, two ranks as threads), then ``LVMScheduler`` on ``frame_block_forward_with_cfg``
+    as on one GPU.  Barriers per clip: none in the prefill, two per Euler step; both ranks end on the oracle's
+    latents, x1 and v, and a second clip with fresh context tensors reuses the plan."""
+    from videogpt_b200 import LVMScheduler
+    world, n_ctx, n_gen, H, W, steps = 2, 3, 2, 64, 96, 3
+    sd = _model()[1]
+
+    def body(r, m, counts):
+        got = {}
+        for pt in ("x1", "v"):
+            for clip in range(2):
+                mk, z_list = _mk(n_ctx, n_gen, H, W)
+                before = counts[r]
+                out = LVMScheduler(steps)([x.clone() for x in z_list] * 2, m.frame_block_forward_with_cfg, mk,
+                                          prediction_type=pt)
+                got[(pt, clip)] = (out, counts[r] - before)
+        return got, (m._engine.plan.partition, m._engine.plan.prefix.rows, m._engine.plan.step.rows)
+
+    res = _ranks_as_threads(emu, world, "sequences", body)
     block = H * W // 256 + 2
-    assert rows == [("sequences", n_ctx * block, n_gen * block), ("sequences", 0, n_gen * block)]
+    assert [x[1] for x in res] == [("sequences", n_ctx * block, n_gen * block), ("sequences", 0, n_gen * block)]
     for pt in ("x1", "v"):
         mk, z_list = _mk(n_ctx, n_gen, H, W)
         with torch.no_grad():
@@ -487,9 +501,46 @@ def test_cfg_branch_pair_through_model_and_scheduler_reproduces_the_oracle(emu):
                                    mk, num_steps=steps, prediction_type=pt)
         for r in range(world):
             for clip in range(2):
-                out, n_barriers = got[r][(pt, clip)]
+                out, n_barriers = res[r][0][(pt, clip)]
                 assert n_barriers == 2 * steps, (r, pt, clip, n_barriers)
                 assert _maxerr(out, want) < 5 * TOL, (r, pt, clip)
+
+
+@pytest.mark.parametrize("world,partition,geom", [(2, "sequences", (2, 64, 64, 1)), (2, "rows", (3, 48, 80, 4)),
+                                                  (3, "rows", (2, 64, 64, 1))])
+def test_single_frame_path_in_a_peer_group_reproduces_the_oracle(emu, world, partition, geom):
+    """``pipeline.__call__``'s layout (``LVM.forward_with_cfg``: condition tokens as the cached prefix, [time | image]
+    rows active, a one-token unconditional row) with the rows of every sequence dealt to the ranks, and with one CFG
+    branch per rank: every rank ends on the oracle's latents."""
+    from videogpt_b200 import LVMScheduler
+    n_ctx, H, W, sp = geom
+    sd = _model()[1]
+    d = po.single_frame_inputs(n_ctx, H, W, True, sp)
+    lat = synth.synthetic_latents(n_ctx + 1, H, W, seed=7)
+    z0 = torch.cat([lat[n_ctx]] * 2, 0)
+
+    def mk():
+        return dict(input_ids=d["input_ids"], input_img_latents=[x.clone() for x in lat[:n_ctx]],
+                    input_image_sizes=d["input_image_sizes"], attention_mask=d["attention_mask"],
+                    position_ids=d["position_ids"], img_cfg_scale=1.5, use_img_cfg=True, use_kv_cache=False,
+                    offload_model=False)
+
+    with torch.no_grad():
+        want = so.euler_sample(z0.clone(),
+                               lambda z, t, **kw: mo.single_frame_forward_with_cfg(sd, _ocfg(synth.REDUCED), z, t, **kw),
+                               mk(), num_steps=3, prediction_type="x1")
+
+    def body(r, m, counts):
+        got = LVMScheduler(num_steps=3)(z0.clone(), m.forward_with_cfg, mk(), use_kv_cache=False, prediction_type="x1")
+        return got, m._engine.plan.partition, m._engine.plan.step.rows
+
+    res = _ranks_as_threads(emu, world, partition, body)
+    n_tok = H * W // 256
+    assert sum(x[2] for x in res) == 2 * (n_tok + 1) and all(x[1] == partition for x in res)
+    if partition == "sequences":
+        assert [x[2] for x in res] == [n_tok + 1, n_tok + 1]
+    for r in range(world):
+        assert _maxerr([res[r][0]], [want]) < 5 * TOL, r
 
 
 def test_rollout_under_sequence_parallelism_matches_the_single_rank_rollout(emu):
