@@ -30,7 +30,7 @@ def _specs(n_ctx, n_gen, H, W):
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
-@pytest.mark.parametrize("geom", [(4, 4, 256, 256), (3, 2, 64, 96), (1, 1, 64, 64)])
+@pytest.mark.parametrize("geom", [(4, 4, 256, 256), (3, 2, 64, 96), (1, 1, 64, 64), (32, 4, 256, 256), (4, 4, 512, 512)])
 def test_sharded_plans_partition_the_unsharded_plan(world, geom):
     n_ctx, n_gen, H, W = geom
     _, specs, n_lat, n_ctx_lat = _specs(n_ctx, n_gen, H, W)
