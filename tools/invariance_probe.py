@@ -46,9 +46,9 @@ for impl in ("tcgen05", "mma_sync"):
             idx = []
             for s_, sp in enumerate(specs):
                 lo, hi = (0, sp.n_prefix) if which == "prefix" else (sp.n_prefix, sp.n_prefix + sp.n_active)
-                a_, b_ = eng.shard_rows(lo, hi, r, world)
                 base = int(ph.seqs[s_, 0]) - lo
-                idx.append(torch.arange(a_ + base, b_ + base, device=dev))
+                for a_, b_ in eng.shard_ranges(lo, hi, r, world, flip=bool(s_ & 1)):     # as build_plan deals them
+                    idx.append(torch.arange(a_ + base, b_ + base, device=dev))
             idx = torch.cat(idx)
             ql = q[idx].contiguous()
             ol = torch.zeros(len(idx), H * D, device=dev, dtype=bf)
