@@ -432,9 +432,10 @@ class NextClipEngine:
         # sampler loop: scheduler.py:171 builds `timesteps` from one sigma): the three small MLPs
         # then run on ONE row and the result is replicated -- identical numbers, 1/n of the work.
         self.uniform_t = False
-        # Set by the sampler's fused loop (scheduler.run_prepared): (use_cfg, x1_mode) -> the final-layer kernel also
-        # applies the step's x1 -> v / CFG / Euler update to self.z, reading the step scalars from self.scalars; None:
-        # predict() only produces self.pred (the S2 callback seam, CFG-branch pairs, sequence-parallel groups)
+        # Set by the sampler's fused loop (scheduler.run_prepared): (use_cfg, x1_mode) -> the step also applies its
+        # x1 -> v / CFG / Euler update to self.z, reading the step scalars from self.scalars -- inside the final-layer
+        # kernel on one GPU, as vgpt_cfg_euler behind the last barrier in a peer group; None: predict() only produces
+        # self.pred (the S2 callback seam)
         self.euler_mode = None
         self._graph_key = None
         self.plan: Optional[ClipPlan] = None
